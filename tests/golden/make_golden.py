@@ -169,6 +169,19 @@ def main():
         # all of detection + vault + timeout in one env: tiny max_steps
         ("short", 10, 10, 14, ([], [{"row": 7, "col": 7, "fov_angle": 120, "heading": 300, "rotation_speed": 0,
                                     "vision_range": 6}], [], 15), np.array([2] * 7 + [4] * 7 + [0] * 6, np.int8)),
+        # unsolvable layout (start boxed in): the env still steps (trainer would skip it)
+        ("blocked", 10, 10, 200, ([(1, 2), (2, 1), (2, 2)], [], [], 15),
+         np.array([4, 2, 0, 1, 3, 2, 4, 4, 2, 2], np.int8)),
+        # many timeouts with partial credit (environment.py:291-297)
+        ("timeouts", 10, 10, 9, ([(4, 4)], [], [], 15), biased_actions(rng, 72)),
+        # three vault runs back to back through auto-reset
+        ("vaultrun", 10, 10, 200, ([], [], [], 15), np.array(([2] * 7 + [4] * 7) * 3, np.int8)),
+        # guard parked on the vault: detection and vault fire in the same step (:273-288)
+        ("vaultguard", 10, 10, 200,
+         ([], [], [{"patrol_path": [(8, 8)], "speed": 1, "vision_range": 1, "fov_angle": 30.0}], 15),
+         np.array([2] * 7 + [4] * 7 + [0, 4], np.int8)),
+        # vault + timeout in the same step (max_steps == path length)
+        ("vaulttimeout", 10, 10, 14, ([], [], [], 15), np.array([2] * 7 + [4] * 7 + [2, 2], np.int8)),
     ]
     cases = list(fixed)
     plan = [(10, 10, 60, 8, 40), (20, 20, 200, 20, 48), (32, 32, 200, 6, 40), (64, 64, 200, 2, 30),
