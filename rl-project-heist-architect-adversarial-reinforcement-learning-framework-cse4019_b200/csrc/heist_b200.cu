@@ -1,0 +1,292 @@
+// heist_b200.cu -- C ABI (include/heist_b200.h) over the sm_100a kernels.
+//
+// Build (see build.py): nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false
+//                       -shared -Xcompiler -fPIC -o libheist_b200.so heist_b200.cu
+#include "../../include/heist_b200.h"
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+
+#include "heist_common.cuh"
+#include "heist_layout.cuh"
+#include "heist_step.cuh"
+#include "heist_stream.cuh"
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) return fail((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+struct HeistHandle {
+    HeistParams p;
+    int N, device;
+    Dev d;
+    LayoutDev lz;  // decode output buffers
+    size_t step_smem, layout_smem;
+    void *allocs[64];
+    int n_allocs;
+};
+
+template <typename T>
+static cudaError_t dalloc(HeistHandle *h, T **ptr, size_t count) {
+    void *p = nullptr;
+    size_t bytes = count * sizeof(T);
+    if (bytes == 0) bytes = sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return e;
+    h->allocs[h->n_allocs++] = p;
+    *ptr = (T *)p;
+    return cudaSuccess;
+}
+
+static inline int env_blocks(int N) { return (N + HEIST_WARPS_PER_CTA - 1) / HEIST_WARPS_PER_CTA; }
+
+extern "C" int heist_abi_version(void) { return HEIST_ABI_VERSION; }
+extern "C" const char *heist_last_error(void) { return g_err.c_str(); }
+
+extern "C" int heist_destroy(HeistHandle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+    delete h;
+    return 0;
+}
+
+extern "C" int heist_create(const HeistParams *params, int num_envs, int device, HeistHandle **out) {
+    if (!params || !out) return fail(-1, "heist_create: null argument");
+    const HeistParams &p = *params;
+    if (num_envs <= 0) return fail(-2, "heist_create: num_envs must be positive");
+    if (p.grid_rows < 3 || p.grid_cols < 3 || p.grid_rows > HEIST_MAX_DIM || p.grid_cols > HEIST_MAX_DIM)
+        return fail(-3, "heist_create: grid %dx%d outside 3..%d", p.grid_rows, p.grid_cols, HEIST_MAX_DIM);
+    if (p.start_row < 0 || p.start_row >= p.grid_rows || p.start_col < 0 || p.start_col >= p.grid_cols ||
+        p.vault_row < 0 || p.vault_row >= p.grid_rows || p.vault_col < 0 || p.vault_col >= p.grid_cols)
+        return fail(-4, "heist_create: start/vault outside the grid");
+    if (p.max_walls < 0 || p.max_cams < 0 || p.max_cams > 32 || p.max_guards < 0 || p.max_guards > 32 ||
+        p.max_path < 1 || p.max_path > 255)
+        return fail(-5, "heist_create: capacities out of range (max_cams, max_guards <= 32; 1 <= max_path <= 255)");
+    if (p.max_steps < 1) return fail(-6, "heist_create: max_steps must be >= 1");
+    CUDA_TRY(cudaSetDevice(device));
+
+    HeistHandle *h = new HeistHandle();
+    memset(h, 0, sizeof(*h));
+    h->p = p; h->N = num_envs; h->device = device;
+    Dev &d = h->d;
+    d.N = num_envs; d.R = p.grid_rows; d.C = p.grid_cols; d.W = (p.grid_cols + 31) / 32;
+    d.RW = d.R * d.W; d.RC = d.R * d.C;
+    d.max_steps = p.max_steps; d.start_r = p.start_row; d.start_c = p.start_col;
+    d.vault_r = p.vault_row; d.vault_c = p.vault_col; d.budget = p.architect_budget;
+    d.Kw = p.max_walls > 0 ? p.max_walls : 1; d.Kc = p.max_cams > 0 ? p.max_cams : 1;
+    d.Kg = p.max_guards > 0 ? p.max_guards : 1; d.L = p.max_path;
+    d.reward_vault = p.reward_vault; d.reward_detection = p.reward_detection; d.reward_step = p.reward_step;
+    d.deg2rad = 3.14159265358979323846 / 180.0;  // Py_MATH_PI / 180.0 (mathmodule.c degToRad)
+    const size_t N = num_envs;
+    cudaError_t e = cudaSuccess;
+#define A(ptr, count) if (e == cudaSuccess) e = dalloc(h, &(ptr), (count))
+    A(d.tile, N * d.RC); A(d.wall, N * d.RW); A(d.env_s, N * 4);
+    A(d.cam_f, N * d.Kc * 2); A(d.cam_i, N * d.Kc * 4);
+    A(d.guard_fov, N * d.Kg); A(d.guard_i, N * d.Kg * 4); A(d.guard_path, N * d.Kg * d.L * 2);
+    A(d.guard_head, N * d.Kg * d.L);
+    A(d.env_d, N * 8); A(d.cam_heading, N * d.Kc); A(d.guard_heading, N * d.Kg); A(d.guard_idx, N * d.Kg);
+    A(d.vis, N * d.RW); A(d.pos_tab, (size_t)d.RC); A(d.err, (size_t)1);
+    LayoutDev &z = h->lz;
+    A(z.n_walls, N); A(z.wall_rc, N * d.Kw * 2); A(z.n_cams, N); A(z.cam_rc, N * d.Kc * 2);
+    A(z.cam_f, N * d.Kc * 3); A(z.cam_range, N * d.Kc); A(z.n_guards, N); A(z.guard_len, N * d.Kg);
+    A(z.guard_path, N * d.Kg * d.L * 2); A(z.guard_head, N * d.Kg * d.L); A(z.guard_speed, N * d.Kg);
+    A(z.guard_range, N * d.Kg); A(z.guard_fov, N * d.Kg);
+#undef A
+    if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc: %s", cudaGetErrorString(e)); }
+
+    // cos / -sin of exact multiples of 30 degrees from the host libm (see heist_common.cuh)
+    double ndx[NICE_N], ndy[NICE_N];
+    for (int k = -NICE_K; k <= NICE_K; ++k) {
+        volatile double a = (double)k * 30.0;
+        volatile double rad = a * d.deg2rad;
+        ndx[k + NICE_K] = cos(rad);
+        ndy[k + NICE_K] = -sin(rad);
+    }
+    CUDA_TRY(cudaMemcpyToSymbol(c_nice_dx, ndx, sizeof(ndx)));
+    CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
+
+    h->step_smem = HEIST_WARPS_PER_CTA * warp_env_bytes(d.RW, d.Kc, d.Kg);
+    h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
+
+    // HeistEnvironment.__init__: bordered grid with START/VAULT, solver at start (environment.py:62-96)
+    k_pos_table<<<(d.RC + 127) / 128, 128>>>(d);
+    k_init_dyn<<<(num_envs + 127) / 128, 128>>>(d);
+    LayoutDev none;
+    memset(&none, 0, sizeof(none));
+    k_set_layout<<<env_blocks(num_envs), HEIST_WARPS_PER_CTA * 32, h->layout_smem>>>(d, none, nullptr, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaDeviceSynchronize());
+    *out = h;
+    return 0;
+}
+
+static int launch_set_layout(HeistHandle *h, const LayoutDev &lz, const int32_t *budget, uint8_t *valid_out,
+                             cudaStream_t s) {
+    k_set_layout<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->layout_smem, s>>>(h->d, lz, budget, valid_out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_decode_validate(HeistHandle *h, const int8_t *asset_map, const float *cam_params,
+                                     const int32_t *budget, int allow_cameras, int allow_guards, uint8_t *valid_out,
+                                     void *stream) {
+    if (!h || !asset_map || !cam_params) return fail(-1, "heist_decode_validate: null argument");
+    if (h->d.L < 8) return fail(-7, "heist_decode_validate: max_path must be >= 8 (patrol has 8 waypoints)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    k_decode<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, 0, s>>>(h->d, h->lz, asset_map, cam_params, budget,
+                                                                   allow_cameras, allow_guards);
+    CUDA_TRY(cudaGetLastError());
+    return launch_set_layout(h, h->lz, budget, valid_out, s);
+}
+
+extern "C" int heist_set_layout_explicit(HeistHandle *h, const HeistLayoutArrays *a, const int32_t *budget,
+                                         uint8_t *valid_out, void *stream) {
+    if (!h || !a) return fail(-1, "heist_set_layout_explicit: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    LayoutDev lz;
+    lz.n_walls = (int32_t *)a->n_walls; lz.wall_rc = (int16_t *)a->wall_rc;
+    lz.n_cams = (int32_t *)a->n_cams; lz.cam_rc = (int16_t *)a->cam_rc; lz.cam_f = (double *)a->cam_f;
+    lz.cam_range = (int32_t *)a->cam_range;
+    lz.n_guards = (int32_t *)a->n_guards; lz.guard_len = (int32_t *)a->guard_len;
+    lz.guard_path = (int16_t *)a->guard_path; lz.guard_head = (double *)a->guard_head;
+    lz.guard_speed = (int32_t *)a->guard_speed; lz.guard_range = (int32_t *)a->guard_range;
+    lz.guard_fov = (double *)a->guard_fov;
+    if (lz.n_walls && !lz.wall_rc) return fail(-8, "heist_set_layout_explicit: n_walls without wall_rc");
+    if (lz.n_cams && (!lz.cam_rc || !lz.cam_f || !lz.cam_range)) return fail(-8, "heist_set_layout_explicit: camera arrays missing");
+    if (lz.n_guards && (!lz.guard_len || !lz.guard_path || !lz.guard_head || !lz.guard_speed || !lz.guard_range || !lz.guard_fov))
+        return fail(-8, "heist_set_layout_explicit: guard arrays missing");
+    return launch_set_layout(h, lz, budget, valid_out, (cudaStream_t)stream);
+}
+
+extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
+    if (!h) return fail(-1, "heist_reset: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_reset<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(h->d, mask);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_step(HeistHandle *h, const int8_t *actions, float *reward, double *reward64, uint8_t *done,
+                          uint8_t *status, void *stream) {
+    if (!h || !actions) return fail(-1, "heist_step: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_step_many<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(
+        h->d, actions, 1, 0, reward, reward64, done, status, nullptr);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward,
+                               uint8_t *done, uint8_t *status, uint32_t *vis_traj, void *stream) {
+    if (!h || !actions) return fail(-1, "heist_step_many: null argument");
+    if (T < 0) return fail(-9, "heist_step_many: negative T");
+    if (T == 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_step_many<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(
+        h->d, actions, T, autoreset, reward, nullptr, done, status, vis_traj);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_observe(HeistHandle *h, float *state, void *stream) {
+    if (!h || !state) return fail(-1, "heist_observe: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const Dev &d = h->d;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d.C % 4 == 0 && ((uintptr_t)state & 15) == 0) {
+        long long total = (long long)d.N * 3 * (d.RC / 4);
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        k_observe_vec4<<<(int)blocks, 256, 0, s>>>(d, (float4 *)state);
+    } else {
+        long long total = (long long)d.N * 3 * d.RC;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 32) blocks = 148LL * 32;
+        k_observe_scalar<<<(int)blocks, 256, 0, s>>>(d, state);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_observation_vectors(HeistHandle *h, float *obs_vec, void *stream) {
+    if (!h || !obs_vec) return fail(-1, "heist_observation_vectors: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_obs_vectors<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, obs_vec);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_get_state(HeistHandle *h, HeistStateView *v) {
+    if (!h || !v) return fail(-1, "heist_get_state: null argument");
+    const Dev &d = h->d;
+    v->tile = d.tile; v->wall_bits = d.wall; v->vis_bits = d.vis; v->env_static = d.env_s; v->env_dyn = d.env_d;
+    v->cam_f = d.cam_f; v->cam_i = d.cam_i; v->cam_heading = d.cam_heading;
+    v->guard_fov = d.guard_fov; v->guard_i = d.guard_i; v->guard_path = d.guard_path;
+    v->guard_heading = d.guard_heading; v->guard_idx = d.guard_idx;
+    return 0;
+}
+
+extern "C" int heist_gae(const float *rew, const float *val, const uint8_t *done, int T, int n_cols, double gamma,
+                         double gae_lambda, float *adv, float *ret, int device, void *stream) {
+    if (!rew || !val || !done || !adv || !ret) return fail(-1, "heist_gae: null argument");
+    if (T < 0 || n_cols < 0) return fail(-9, "heist_gae: negative size");
+    if (T == 0 || n_cols == 0) return 0;
+    CUDA_TRY(cudaSetDevice(device));
+    const float g = (float)gamma;                  // torch casts the Python scalar to the tensor dtype
+    const float gl = (float)(gamma * gae_lambda);  // self.gamma * self.gae_lambda is a Python double product
+    k_gae<8><<<(n_cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_architect_reward(HeistHandle *h, double *reward_out, double *solve_rate_out, void *stream) {
+    if (!h || !reward_out) return fail(-1, "heist_architect_reward: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    k_architect_reward<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, reward_out, solve_rate_out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_check_errors(HeistHandle *h, void *stream) {
+    if (!h) return fail(-1, "heist_check_errors: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    int flags = 0;
+    CUDA_TRY(cudaMemcpy(&flags, h->d.err, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flags) {
+        CUDA_TRY(cudaMemset(h->d.err, 0, sizeof(int)));
+        return fail(-100 - flags, "device-side layout error:%s%s%s",
+                    (flags & ERR_CAPACITY) ? " capacity exceeded (max_walls/max_cams/max_guards/max_path)" : "",
+                    (flags & ERR_WAYPOINT) ? " guard waypoint outside the grid" : "",
+                    (flags & ERR_RAYS) ? " fov/vision_range too large" : "");
+    }
+    return 0;
+}

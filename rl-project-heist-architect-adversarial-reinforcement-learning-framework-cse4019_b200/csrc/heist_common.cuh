@@ -1,0 +1,78 @@
+// heist_common.cuh -- device-side state description and exact-arithmetic helpers.
+//
+// Everything that decides a bit of the visibility map / positions / done flags is written with
+// explicit IEEE operations in the reference's order (CPython double arithmetic):
+// separate multiply and add (no FMA contraction; the TU is also compiled with -fmad=false),
+// round-half-even tile rounding, Python float modulo.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define HEIST_WARPS_PER_CTA 4
+#define NICE_K 48                 // exact multiples of 30 degrees covered: |angle| <= 1440
+#define NICE_N (2 * NICE_K + 1)
+
+// cos / -sin of exact multiples of 30 degrees, evaluated by the HOST libm at heist_create
+// (CPython's math.cos/sin call the same libm; security.py:71-75).  These are the only angles where
+// the last ulp of cos/sin can decide a tile (cos = +-1/2, +-1: exact .5 ties in col + dx*dist),
+// so they are taken from the platform the reference runs on instead of the device's sincos.
+__constant__ double c_nice_dx[NICE_N];
+__constant__ double c_nice_dy[NICE_N];
+
+struct Dev {
+    int N, R, C, W, RW, RC;
+    int max_steps, start_r, start_c, vault_r, vault_c, budget;
+    int Kw, Kc, Kg, L;
+    double reward_vault, reward_detection, reward_step;
+    double deg2rad;  // Py_MATH_PI / 180.0 evaluated on the host (math.radians)
+    // static per layout
+    uint8_t *tile;        // [N][RC]
+    uint32_t *wall;       // [N][RW]
+    int32_t *env_s;       // [N][4]  n_cams, n_guards, valid, spent
+    double *cam_f;        // [N][Kc][2] fov, speed
+    int16_t *cam_i;       // [N][Kc][4] row, col, range, num_rays
+    double *guard_fov;    // [N][Kg]
+    int32_t *guard_i;     // [N][Kg][4] len, speed, range, num_rays
+    uint8_t *guard_path;  // [N][Kg][L][2]
+    double *guard_head;   // [N][Kg][L] heading after leaving waypoint i (NaN: unchanged)
+    // dynamic
+    int32_t *env_d;       // [N][8]
+    double *cam_heading;  // [N][Kc]
+    double *guard_heading;// [N][Kg]
+    int32_t *guard_idx;   // [N][Kg]
+    uint32_t *vis;        // [N][RW]
+    float *pos_tab;       // [RC] float32(-0.3 * (manhattan(cell, vault) / (R + C)))
+    int *err;             // sticky device error flags
+};
+
+enum { ERR_CAPACITY = 1, ERR_WAYPOINT = 2, ERR_RAYS = 4 };
+enum { F_DONE = 1, F_DETECTED = 2, F_VAULT = 4 };
+
+// Python `x % 360.0` (floatobject.c float_rem): fmod, then shift negative remainders up.
+__device__ __forceinline__ double py_mod360(double x) {
+    double m;
+    if (fabs(x) < 360.0) m = x;                       // fmod is the identity here
+    else if (x >= 360.0 && x < 720.0) m = x - 360.0;  // exact (Sterbenz), equals fmod
+    else m = fmod(x, 360.0);                          // CUDA fmod is exact
+    if (m != 0.0) { if (m < 0.0) m = __dadd_rn(m, 360.0); }
+    else m = 0.0;                                     // copysign(0.0, 360.0)
+    return m;
+}
+
+// Python int %: result has the divisor's sign (len > 0).
+__device__ __forceinline__ int py_imod(int a, int n) { int m = a % n; return m < 0 ? m + n : m; }
+
+// Ray direction for angle_deg: dx = cos(radians(a)), dy = -sin(radians(a))  (security.py:71-75).
+__device__ __forceinline__ void ray_dir(double angle_deg, double deg2rad, double &dx, double &dy) {
+    double k = rint(angle_deg * (1.0 / 30.0));
+    if (fabs(k) <= (double)NICE_K && __dmul_rn(k, 30.0) == angle_deg) {
+        int i = (int)k + NICE_K;
+        dx = c_nice_dx[i];
+        dy = c_nice_dy[i];
+        return;
+    }
+    double s, c;
+    sincos(__dmul_rn(angle_deg, deg2rad), &s, &c);
+    dx = c;
+    dy = -s;
+}

@@ -1,0 +1,148 @@
+// heist_stream.cuh -- HBM-streaming kernels: dense observation expand, GAE/returns scan,
+// architect reward.  Reference: HeistEnvironment.get_state_tensor / _get_observation
+// (environment.py:305-374), SolverAgent._compute_gae (agents/solver.py:228-244),
+// RewardCalculator.calculate_architect_reward (rewards.py:43-73).
+#pragma once
+#include "heist_common.cuh"
+
+// pos_tab[cell] = float32(-0.3 * (manhattan(cell, vault) / (R + C)))   (environment.py:361-365;
+// numpy >= 2: np.float32 += python float rounds the float to float32, then adds in float32)
+__global__ void k_pos_table(Dev D) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= D.RC) return;
+    int r = i / D.C, c = i - r * D.C;
+    int d = abs(r - D.vault_r) + abs(c - D.vault_c);
+    double v = __dmul_rn(-0.3, __ddiv_rn((double)d, (double)(D.R + D.C)));
+    D.pos_tab[i] = (float)v;
+}
+
+// state[N][3][R][C] float32.  One thread per 4 consecutive cells of one channel (C % 4 == 0)
+// -> one 16-byte store; inputs are bytes / bits and stay in L1/L2.
+__global__ void __launch_bounds__(256) k_observe_vec4(Dev D, float4 *__restrict__ out) {
+    const int quads = D.RC >> 2;
+    const long long total = (long long)D.N * 3 * quads;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int env = (int)(idx / (3 * quads));
+        int rem = (int)(idx - (long long)env * 3 * quads);
+        int ch = rem / quads;
+        int cell = (rem - ch * quads) << 2;
+        float4 v;
+        if (ch == 0) {  // occupancy = grid.astype(float32) / 5   (:319)
+            uchar4 t = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + cell);
+            v.x = __fdiv_rn((float)t.x, 5.0f); v.y = __fdiv_rn((float)t.y, 5.0f);
+            v.z = __fdiv_rn((float)t.z, 5.0f); v.w = __fdiv_rn((float)t.w, 5.0f);
+        } else if (ch == 1) {  // visibility (:322)
+            int r = cell / D.C, c = cell - r * D.C;
+            uint32_t bits = D.vis[(size_t)env * D.RW + r * D.W + (c >> 5)] >> (c & 31);
+            v.x = (float)(bits & 1u); v.y = (float)((bits >> 1) & 1u);
+            v.z = (float)((bits >> 2) & 1u); v.w = (float)((bits >> 3) & 1u);
+        } else {  // position channel (:356-365): solver +1, vault -1 (vault wins), plus gradient
+            int pos = D.env_d[(size_t)env * 8];
+            int scell = (pos & 0xffff) * D.C + (pos >> 16);
+            int vcell = D.vault_r * D.C + D.vault_c;
+            float4 g = *reinterpret_cast<const float4 *>(D.pos_tab + cell);
+            float b0 = (cell + 0 == vcell) ? -1.0f : ((cell + 0 == scell) ? 1.0f : 0.0f);
+            float b1 = (cell + 1 == vcell) ? -1.0f : ((cell + 1 == scell) ? 1.0f : 0.0f);
+            float b2 = (cell + 2 == vcell) ? -1.0f : ((cell + 2 == scell) ? 1.0f : 0.0f);
+            float b3 = (cell + 3 == vcell) ? -1.0f : ((cell + 3 == scell) ? 1.0f : 0.0f);
+            v.x = __fadd_rn(b0, g.x); v.y = __fadd_rn(b1, g.y); v.z = __fadd_rn(b2, g.z); v.w = __fadd_rn(b3, g.w);
+        }
+        out[idx] = v;
+    }
+}
+
+// Scalar fallback for C % 4 != 0.
+__global__ void __launch_bounds__(256) k_observe_scalar(Dev D, float *__restrict__ out) {
+    const long long total = (long long)D.N * 3 * D.RC;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        int env = (int)(idx / (3 * D.RC));
+        int rem = (int)(idx - (long long)env * 3 * D.RC);
+        int ch = rem / D.RC;
+        int cell = rem - ch * D.RC;
+        float v;
+        if (ch == 0) v = __fdiv_rn((float)D.tile[(size_t)env * D.RC + cell], 5.0f);
+        else if (ch == 1) {
+            int r = cell / D.C, c = cell - r * D.C;
+            v = (float)((D.vis[(size_t)env * D.RW + r * D.W + (c >> 5)] >> (c & 31)) & 1u);
+        } else {
+            int pos = D.env_d[(size_t)env * 8];
+            int scell = (pos & 0xffff) * D.C + (pos >> 16);
+            int vcell = D.vault_r * D.C + D.vault_c;
+            float b = (cell == vcell) ? -1.0f : ((cell == scell) ? 1.0f : 0.0f);
+            v = __fadd_rn(b, D.pos_tab[cell]);
+        }
+        out[idx] = v;
+    }
+}
+
+// solver_position, vault_direction, time_feature (environment.py:324-337): double divide -> float32.
+__global__ void k_obs_vectors(Dev D, float *__restrict__ out) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= D.N) return;
+    int pos = D.env_d[(size_t)env * 8], tick = D.env_d[(size_t)env * 8 + 1];
+    int r = pos & 0xffff, c = pos >> 16;
+    float *o = out + (size_t)env * 5;
+    o[0] = (float)__ddiv_rn((double)r, (double)D.R);
+    o[1] = (float)__ddiv_rn((double)c, (double)D.C);
+    o[2] = (float)__ddiv_rn((double)(D.vault_r - r), (double)D.R);
+    o[3] = (float)__ddiv_rn((double)(D.vault_c - c), (double)D.C);
+    o[4] = (float)__ddiv_rn((double)tick, (double)D.max_steps);
+}
+
+// GAE + returns, one thread per time-major column, fp32 ops in the reference's order, no FMA:
+//   delta = r + (g * next_v) * (1 - d) - v ;  A = delta + (gl * (1 - d)) * A ;  ret = A + v
+// Loads do not depend on the recurrence, so each thread prefetches CH timesteps at a time.
+template <int CH>
+__global__ void __launch_bounds__(128)
+k_gae(const float *__restrict__ rew, const float *__restrict__ val, const uint8_t *__restrict__ done, int T, int n,
+      float g, float gl, float *__restrict__ adv, float *__restrict__ ret) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    float last = 0.0f, nv = 0.0f;
+    int t = T - 1;
+    while (t >= 0) {
+        float r[CH], v[CH], om[CH];
+        const int cnt = min(CH, t + 1);
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (k < cnt) {
+                size_t i = (size_t)(t - k) * n + j;
+                r[k] = rew[i]; v[k] = val[i]; om[k] = __fsub_rn(1.0f, (float)done[i]);
+            }
+#pragma unroll
+        for (int k = 0; k < CH; ++k)
+            if (k < cnt) {
+                size_t i = (size_t)(t - k) * n + j;
+                float delta = __fsub_rn(__fadd_rn(r[k], __fmul_rn(__fmul_rn(g, nv), om[k])), v[k]);
+                float A = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, om[k]), last));
+                adv[i] = A;
+                ret[i] = __fadd_rn(A, v[k]);
+                last = A;
+                nv = v[k];
+            }
+        t -= cnt;
+    }
+}
+
+// calculate_architect_reward (rewards.py:43-73) with solve_rate = vault / finished episodes
+// (training.py:535-550) per env.
+__global__ void k_architect_reward(Dev D, double *__restrict__ reward, double *__restrict__ solve_rate_out) {
+    int env = blockIdx.x * blockDim.x + threadIdx.x;
+    if (env >= D.N) return;
+    const int32_t *d = D.env_d + (size_t)env * 8;
+    int valid = D.env_s[(size_t)env * 4 + 2];
+    int nv = d[5], total = d[5] + d[6] + d[7];
+    double sr = total > 0 ? __ddiv_rn((double)nv, (double)total) : 0.0;
+    double rw;
+    if (!valid) rw = -1.0;
+    else {
+        rw = __dmul_rn(__dsub_rn(1.0, sr), 1.0);
+        rw = __dadd_rn(0.0, rw);
+        if (sr > 0.8) rw = __dadd_rn(rw, -0.5);
+        if (0.2 <= sr && sr <= 0.6) rw = __dadd_rn(rw, 0.2);
+    }
+    reward[env] = rw;
+    if (solve_rate_out) solve_rate_out[env] = sr;
+}

@@ -1,0 +1,409 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against golden fixtures from the reference
+and against the CPU oracle on seeded inputs.
+
+Bars: visibility bitmaps, positions, ticks, done/status, grids, BFS validity, budgets: bit-exact.
+Rewards: float64 == against golden (and float32 == against the oracle's float32 cast).
+State tensors / observation vectors: float32 ==.  GAE advantages / returns: float32 == (the
+north-star tolerance is 1e-5 relative; the op order is reproduced, so equality holds).
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import heist_b200  # noqa: E402
+from heist_b200 import BatchedHeistEnv, EnvironmentConfig, synthetic  # noqa: E402
+from oracle import heist_oracle as ho  # noqa: E402
+
+
+def u32(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+# --------------------------------------------------------------------------------------------
+# golden traces (outputs of the unmodified reference)
+# --------------------------------------------------------------------------------------------
+def _groups(golden):
+    groups = {}
+    for name, t in golden.traces.items():
+        key = (t["R"], t["C"], t["max_steps"], len(golden.arr(name, "actions")))
+        groups.setdefault(key, []).append(name)
+    return groups
+
+
+def test_golden_traces_bit_exact(golden):
+    for (R, C, ms, T), names in _groups(golden).items():
+        N = len(names)
+        env = BatchedHeistEnv(EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=ms), N,
+                              max_walls=64, max_cams=8, max_guards=4, max_path=8)
+        lays = [golden.layout(n) for n in names]
+        valid = env.set_layout_explicit([l[:3] for l in lays], budget=np.array([l[3] for l in lays]))
+        env.check_errors()
+        assert valid.cpu().tolist() == [golden.traces[n]["valid"] for n in names]
+        assert env.budget_spent.cpu().tolist() == [golden.traces[n]["spent"] for n in names]
+        ncam = env.env_static[:, 0].cpu().numpy()
+        ngrd = env.env_static[:, 1].cpu().numpy()
+        for j, n in enumerate(names):
+            assert [ncam[j], ngrd[j]] == golden.traces[n]["n_placed"][1:], n
+            assert np.array_equal(env.tile_codes[j].cpu().numpy().astype(np.int8), golden.arr(n, "grid")), n
+        env.reset()
+        vis = u32(env.visibility_bits)
+        for j, n in enumerate(names):
+            assert np.array_equal(vis[j], golden.arr(n, "vis0")), n
+        acts = np.stack([golden.arr(n, "actions") for n in names], 1)
+        G = {k: [golden.arr(n, k) for n in names] for k in
+             ["reward", "done", "status", "pos", "tick", "vis", "vis_post", "cam_heading", "guard_idx",
+              "guard_heading", "state_t", "state", "obs_vec"]}
+        si = [0] * N
+        for t in range(T):
+            rew, done, status, r64 = env.step(acts[t], want_reward64=True)
+            r64, rew = r64.cpu().numpy(), rew.cpu().numpy()
+            done_h, status_h = done.cpu().numpy(), status.cpu().numpy()
+            pos, tick = env.solver_pos.cpu().numpy(), env.tick.cpu().numpy()
+            vis = u32(env.visibility_bits)
+            ch, gh, gx = env.cam_heading.cpu().numpy(), env.guard_heading.cpu().numpy(), env.guard_idx.cpu().numpy()
+            need_state = any(si[j] < len(G["state_t"][j]) and G["state_t"][j][si[j]] == t for j in range(N))
+            if need_state:
+                state = env.observe().cpu().numpy()
+                o = env.observation()
+                vec = torch.cat([o["solver_position"], o["vault_direction"], o["time_feature"]], 1).cpu().numpy()
+                assert np.array_equal(o["occupancy_grid"].cpu().numpy(), state[:, 0])
+                assert np.array_equal(o["visibility_map"].cpu().numpy(), state[:, 1])
+            for j, n in enumerate(names):
+                where = (n, t)
+                assert r64[j] == G["reward"][j][t], where
+                assert rew[j] == np.float32(G["reward"][j][t]), where
+                assert done_h[j] == bool(G["done"][j][t]) and status_h[j] == G["status"][j][t], where
+                assert tuple(pos[j]) == tuple(G["pos"][j][t]) and tick[j] == G["tick"][j][t], where
+                assert np.array_equal(vis[j], G["vis"][j][t]), where
+                assert np.array_equal(ch[j, :ncam[j]], G["cam_heading"][j][t, :ncam[j]]), where
+                assert np.array_equal(gx[j, :ngrd[j]], G["guard_idx"][j][t, :ngrd[j]]), where
+                assert np.array_equal(gh[j, :ngrd[j]], G["guard_heading"][j][t, :ngrd[j]]), where
+                if si[j] < len(G["state_t"][j]) and G["state_t"][j][si[j]] == t:
+                    assert np.array_equal(state[j], G["state"][j][si[j]]), where
+                    assert np.array_equal(vec[j], G["obs_vec"][j][si[j]]), where
+                    si[j] += 1
+            env.reset(mask=done)  # the trainer's pattern: reset after a finished episode
+            vis = u32(env.visibility_bits)
+            for j, n in enumerate(names):
+                assert np.array_equal(vis[j], G["vis_post"][j][t]), (n, t, "post")
+        env.close()
+
+
+def test_golden_traces_step_many(golden):
+    """Same traces through the multi-step kernel with in-kernel auto-reset."""
+    for (R, C, ms, T), names in _groups(golden).items():
+        N = len(names)
+        env = BatchedHeistEnv(EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=ms), N)
+        lays = [golden.layout(n) for n in names]
+        env.set_layout_explicit([l[:3] for l in lays], budget=np.array([l[3] for l in lays]))
+        env.reset()
+        acts = np.stack([golden.arr(n, "actions") for n in names], 1)
+        out = env.step_many(acts, autoreset=True, want_vis=True)
+        rew, done, status, vis = (out["reward"].cpu().numpy(), out["done"].cpu().numpy(),
+                                  out["status"].cpu().numpy(), u32(out["vis_bits"]))
+        for j, n in enumerate(names):
+            assert np.array_equal(rew[:, j], golden.arr(n, "reward").astype(np.float32)), n
+            assert np.array_equal(done[:, j], golden.arr(n, "done")), n
+            assert np.array_equal(status[:, j], golden.arr(n, "status")), n
+            assert np.array_equal(vis[:, j], golden.arr(n, "vis_post")), n
+        env.close()
+
+
+def test_survey_kat20_hash(golden):
+    import hashlib
+    walls, cams, guards, budget = golden.layout("kat20")
+    env = BatchedHeistEnv(EnvironmentConfig(), 1)
+    assert env.set_layout_explicit([(walls, cams, guards)], budget=budget).item()
+    env.reset()
+    v0 = u32(env.visibility_bits)[0]
+    out = env.step_many(np.zeros((400, 1), np.int8), autoreset=True, want_vis=True)
+    vis = np.concatenate([v0[None], u32(out["vis_bits"])[:-1, 0]])  # map seen before each of the 400 steps
+    dense = ((vis[:, :, 0, None] >> np.arange(20)) & 1).astype(bool)
+    h = hashlib.sha256()
+    for t in range(400):
+        h.update(np.packbits(dense[t]).tobytes())
+    assert h.hexdigest() == "513d958ef974b21eade9aa03015912517dece7e4b253561dd48067fbad01e8b6"
+    assert int(dense.sum()) == 28938 and int(out["done"].sum().item()) == 2
+    assert env.cam_heading[0, :2].cpu().tolist() == [21.5, 80.0]
+
+
+def test_decode_golden(golden):
+    for k, d in enumerate(golden.meta["decode"]):
+        am = golden.z[f"decode{k}/asset_map"]
+        env = BatchedHeistEnv(EnvironmentConfig(grid_rows=d["H"], grid_cols=d["W"]), 1, max_walls=64, max_cams=8,
+                              max_guards=8)
+        valid = env.set_layout_from_asset_map(am[None], np.asarray([d["params"]], np.float32), budget=d["budget"],
+                                              allow_cameras=d["allow_cameras"], allow_guards=d["allow_guards"])
+        env.check_errors()
+        assert bool(valid.item()) == d["valid"], k
+        assert env.budget_spent.item() == d["spent"], k
+        assert np.array_equal(env.tile_codes[0].cpu().numpy().astype(np.int8), golden.z[f"decode{k}/grid"]), k
+        env.reset()
+        assert np.array_equal(u32(env.visibility_bits)[0], golden.z[f"decode{k}/vis0"]), k
+        env.close()
+
+
+def test_bfs_golden(golden):
+    grids, dims, ans = golden.z["bfs/grids"], golden.z["bfs/dims"], golden.z["bfs/answer"]
+    for g, (R, C, sr, sc, gr, gc), a in zip(grids, dims, ans):
+        walls = [(int(r), int(c)) for r, c in zip(*np.nonzero(g[1:R - 1, 1:C - 1] == 1))]
+        walls = [(r + 1, c + 1) for r, c in walls]
+        env = BatchedHeistEnv(EnvironmentConfig(grid_rows=int(R), grid_cols=int(C), start_pos=(int(sr), int(sc)),
+                                                vault_pos=(int(gr), int(gc))), 1, max_walls=4096)
+        valid = env.set_layout_explicit([(walls, [], [])], budget=100000)
+        env.check_errors()
+        assert bool(valid.item()) == bool(a)
+        assert np.array_equal(env.tile_codes[0].cpu().numpy(), g[:R, :C].astype(np.uint8))
+        env.close()
+
+
+def test_gae_golden(golden):
+    for k in range(golden.meta["gae_cases"]):
+        g = {key: golden.z[f"gae{k}/{key}"] for key in ["rew", "val", "done", "adv", "ret", "norm"]}
+        adv, ret = heist_b200.compute_gae(torch.from_numpy(g["rew"]).cuda(), torch.from_numpy(g["val"]).cuda(),
+                                          torch.from_numpy(g["done"]).cuda().to(torch.uint8))
+        assert np.array_equal(adv.cpu().numpy(), g["adv"]), k
+        assert np.array_equal(ret.cpu().numpy(), g["ret"]), k
+        norm = heist_b200.normalize_advantages(adv)
+        np.testing.assert_allclose(norm.cpu().numpy(), g["norm"], rtol=1e-5, atol=1e-6)
+
+
+def test_architect_reward_golden(golden):
+    # drive the per-env outcome counters to the golden solve rates through the state view
+    rates = [(k, 20) for k in range(21)] + [(1, 3), (2, 3)]
+    env = BatchedHeistEnv(EnvironmentConfig(grid_rows=10, grid_cols=10), len(rates))
+    for j, (k, n) in enumerate(rates):
+        env.env_dyn[j, 5] = k
+        env.env_dyn[j, 6] = n - k
+    rw, sr = env.architect_reward()
+    exp = {float(s): float(r) for s, r in zip(golden.z["arch/solve_rate"], golden.z["arch/reward_valid"])}
+    for j, (k, n) in enumerate(rates):
+        assert sr[j].item() == k / n and rw[j].item() == exp[k / n], (k, n)
+    env.set_layout_explicit([([(1, 2), (2, 1), (2, 2)], [], [])] * len(rates))
+    rw, _ = env.architect_reward()
+    assert (rw == -1.0).all()
+
+
+# --------------------------------------------------------------------------------------------
+# seeded differential tests against the CPU oracle
+# --------------------------------------------------------------------------------------------
+def oracle_envs(am, cp, cfg, budget, allow_cameras=True, allow_guards=True):
+    envs, valid = [], []
+    for i in range(am.shape[0]):
+        walls, cams, guards, _ = ho.decode_layout(am[i], budget, cp[i, 0], cp[i, 1], cp[i, 2])
+        e = ho.OracleEnv(cfg.grid_rows, cfg.grid_cols, max_steps=cfg.max_steps, budget=budget)
+        valid.append(e.set_layout(walls, cams if allow_cameras else [], guards if allow_guards else []))
+        envs.append(e)
+    return envs, np.asarray(valid)
+
+
+@pytest.mark.parametrize("R,C,N,T,budget,nice", [
+    (20, 20, 512, 200, 15, False),     # config 2 parity subset (>= 256 envs x 200 ticks)
+    (20, 20, 256, 200, 15, True),      # tie-prone "nice" angles (fov 60, speed 15, heading k*15)
+    (32, 32, 128, 120, 22, False),     # config 3 shape
+    (64, 64, 48, 80, 22, False),       # config 4 shape
+    (12, 17, 64, 50, 8, False),        # ragged grid, C not a multiple of 4
+])
+def test_rollout_matches_oracle(R, C, N, T, budget, nice):
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=min(200, T))
+    env = BatchedHeistEnv(cfg, N)
+    rng = np.random.default_rng(synthetic.BASE_SEED + R * 1000 + N)
+    am = synthetic.sample_asset_maps(rng, N, R, C)
+    cp = synthetic.sample_cam_params(rng, N, nice)
+    valid = env.set_layout_from_asset_map(am, cp, budget)
+    env.check_errors()
+    oenvs, ovalid = oracle_envs(am, cp, cfg, budget)
+    assert np.array_equal(valid.cpu().numpy(), ovalid)
+    assert np.array_equal(env.tile_codes.cpu().numpy(), np.stack([e.grid for e in oenvs]).astype(np.uint8))
+    assert env.budget_spent.cpu().tolist() == [e.info()["spent"] for e in oenvs]
+    env.reset()
+    ho.reset_all(oenvs)
+    assert np.array_equal(u32(env.visibility_bits), np.stack([ho.pack_bits(e.visibility) for e in oenvs]))
+    acts = synthetic.sample_actions(rng, T, N)
+    out = env.step_many(acts, autoreset=True, want_vis=True)
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    assert np.array_equal(out["done"].cpu().numpy(), ref["done"])
+    assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
+    assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+    assert np.array_equal(out["reward"].cpu().numpy(), ref["reward"])  # float32(double) on both sides
+    # final state: positions, ticks, headings, observation tensors
+    info = [e.info() for e in oenvs]
+    assert env.solver_pos.cpu().tolist() == [[i["solver_r"], i["solver_c"]] for i in info]
+    assert env.tick.cpu().tolist() == [i["tick"] for i in info]
+    ch = env.cam_heading.cpu().numpy()
+    for j, e in enumerate(oenvs):
+        assert np.array_equal(ch[j, :info[j]["n_cams"]], e.cam_headings()), j
+    state = env.observe().cpu().numpy()
+    assert np.array_equal(state, np.stack([e.state_tensor() for e in oenvs]))
+    o = env.observation()
+    vec = torch.cat([o["solver_position"], o["vault_direction"], o["time_feature"]], 1).cpu().numpy()
+    assert np.array_equal(vec, np.stack([np.concatenate(e.obs_vectors()) for e in oenvs]))
+    # outcome counters -> architect reward
+    rw, sr = env.architect_reward()
+    st = ref["status"]
+    for j in range(N):
+        nv, nd, nt = (st[:, j] == 2).sum(), (st[:, j] == 1).sum(), (st[:, j] == 3).sum()
+        rate = nv / (nv + nd + nt) if (nv + nd + nt) else 0.0
+        assert sr[j].item() == rate and rw[j].item() == ho.architect_reward(ovalid[j], rate), j
+    env.close()
+
+
+def test_no_autoreset_done_envs_freeze():
+    cfg = EnvironmentConfig(max_steps=30)
+    env = BatchedHeistEnv(cfg, 64)
+    rng = np.random.default_rng(5)
+    am, cp = synthetic.sample_asset_maps(rng, 64, 20, 20), synthetic.sample_cam_params(rng, 64)
+    env.set_layout_from_asset_map(am, cp, 15)
+    oenvs, _ = oracle_envs(am, cp, cfg, 15)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, 45, 64)
+    out = env.step_many(acts, autoreset=False, want_vis=True)
+    ref = ho.rollout(oenvs, acts, autoreset=False, want_vis=True)
+    for k in ["done", "status", "reward"]:
+        assert np.array_equal(out[k].cpu().numpy(), ref[k]), k
+    assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+    assert (ref["status"][-1] == 4).all()  # everything timed out at tick 30 at the latest
+
+
+@pytest.mark.parametrize("allow_c,allow_g", [(False, False), (True, False), (True, True)])
+def test_decode_validate_matches_oracle_dense_maps(allow_c, allow_g):
+    """Dense early-training asset maps (75 % non-zero) and the BFS stress variant (~50 % invalid)."""
+    R = C = 32
+    N = 768
+    rng = np.random.default_rng(77)
+    am = synthetic.sample_asset_maps(rng, N, R, C, 0.25, 0.25, 0.25)
+    am[N // 2:] = synthetic.sample_asset_maps(rng, N - N // 2, R, C, 0.30, 0.004, 0.002)
+    cp = synthetic.sample_cam_params(rng, N)
+    budgets = rng.choice([0, 5, 8, 15, 22, 60], N).astype(np.int32)
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C)
+    env = BatchedHeistEnv(cfg, N, max_walls=64, max_cams=20, max_guards=12)
+    valid = env.set_layout_from_asset_map(am, cp, budgets, allow_c, allow_g).cpu().numpy()
+    env.check_errors()
+    env.reset()
+    vis = u32(env.visibility_bits)
+    tiles, spent = env.tile_codes.cpu().numpy(), env.budget_spent.cpu().numpy()
+    n_invalid = 0
+    for i in range(N):
+        walls, cams, guards, _ = ho.decode_layout(am[i], int(budgets[i]), *cp[i])
+        e = ho.OracleEnv(R, C, budget=int(budgets[i]))
+        v = e.set_layout(walls, cams if allow_c else [], guards if allow_g else [])
+        n_invalid += not v
+        assert v == valid[i], i
+        assert np.array_equal(e.grid.astype(np.uint8), tiles[i]) and e.info()["spent"] == spent[i], i
+        e.reset()
+        assert np.array_equal(ho.pack_bits(e.visibility), vis[i]), i
+    assert n_invalid > 0
+
+
+def test_bfs_stress_half_invalid():
+    R = C = 32
+    N = 1024
+    rng = np.random.default_rng(99)
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C)
+    env = BatchedHeistEnv(cfg, N, max_walls=1024)
+    lays, exp = [], []
+    for i in range(N):
+        p = rng.uniform(0.25, 0.5)
+        g = np.zeros((R, C), np.int32)
+        g[0, :] = g[-1, :] = g[:, 0] = g[:, -1] = 1
+        g[1:-1, 1:-1] = rng.random((R - 2, C - 2)) < p
+        g[1, 1], g[R - 2, C - 2] = 2, 3
+        walls = [(int(r), int(c)) for r, c in zip(*np.nonzero(g == 1)) if 0 < r < R - 1 and 0 < c < C - 1]
+        lays.append((walls, [], []))
+        exp.append(ho.bfs(g, (1, 1), (R - 2, C - 2)))
+    valid = env.set_layout_explicit(lays, budget=10000).cpu().numpy()
+    env.check_errors()
+    assert np.array_equal(valid, np.asarray(exp))
+    assert 0.1 < np.mean(exp) < 0.9
+
+
+def test_gae_matches_oracle_large():
+    rng = np.random.default_rng(11)
+    T, N = 200, 4096
+    rew = rng.normal(size=(T, N)).astype(np.float32)
+    val = rng.normal(size=(T, N)).astype(np.float32)
+    dn = (rng.random((T, N)) < 0.02).astype(np.uint8)
+    adv, ret = heist_b200.compute_gae(torch.from_numpy(rew).cuda(), torch.from_numpy(val).cuda(),
+                                      torch.from_numpy(dn).cuda())
+    oadv, oret = ho.gae(rew, val, dn.astype(np.float32))
+    assert np.array_equal(adv.cpu().numpy(), oadv) and np.array_equal(ret.cpu().numpy(), oret)
+
+
+def test_full_size_config2_properties_and_subset_parity():
+    """BASELINE config 2 at full size: 4096 envs, 20x20, random valid layouts, T=200, auto-reset."""
+    cfg = EnvironmentConfig()
+    N, T = 4096, 200
+    env = BatchedHeistEnv(cfg, N)
+    am, cp = synthetic.make_valid_workload(env, synthetic.BASE_SEED, 15)
+    assert env.valid.all()
+    acts = synthetic.sample_actions(np.random.default_rng(synthetic.BASE_SEED + 1), T, N)
+    env.reset()
+    a = env.step_many(acts, autoreset=True, want_vis=True)
+    a = {k: v.clone() for k, v in a.items()}
+    # idempotence / determinism: same layouts, reset, same actions -> identical trajectory
+    env.set_layout_from_asset_map(am, cp, 15)
+    env.reset()
+    b = env.step_many(acts, autoreset=True, want_vis=True)
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
+    # size-independent invariants
+    st, dn, rw = a["status"], a["done"].bool(), a["reward"]
+    assert ((st == 0) == ~dn).all()                  # running <=> not done (auto-reset: never already_done)
+    assert (st <= 3).all()
+    assert (rw[st == 2] > 8.0).all()                 # vault bonus present
+    assert (rw[st == 0].abs() <= 0.26 + 1e-6).all()  # running step: -0.01 +- 0.1 (+ <= 0.15 proximity)
+    # first 256 envs bit-exact against the oracle
+    sub = 256
+    oenvs, ovalid = oracle_envs(am[:sub], cp[:sub], cfg, 15)
+    assert ovalid.all()
+    ho.reset_all(oenvs)
+    ref = ho.rollout(oenvs, acts[:, :sub].copy(), autoreset=True, want_vis=True)
+    assert np.array_equal(a["done"][:, :sub].cpu().numpy(), ref["done"])
+    assert np.array_equal(a["status"][:, :sub].cpu().numpy(), ref["status"])
+    assert np.array_equal(a["reward"][:, :sub].cpu().numpy(), ref["reward"])
+    assert np.array_equal(u32(a["vis_bits"][:, :sub]), ref["vis_bits"])
+
+
+# --------------------------------------------------------------------------------------------
+# facade: the reference's own smoke scripts, through the HeistEnvironment-compatible class
+# --------------------------------------------------------------------------------------------
+def test_facade_reference_smoke_scripts():
+    cfg = EnvironmentConfig(grid_rows=10, grid_cols=10, start_pos=(1, 1), vault_pos=(8, 8))
+    env = heist_b200.HeistEnvironment(cfg)
+    valid = env.set_layout(
+        [(3, 3), (3, 4), (3, 5)],
+        [{"row": 5, "col": 5, "fov_angle": 60, "heading": 0, "rotation_speed": 15, "vision_range": 4}],
+        [{"patrol_path": [(7, 2), (7, 3), (7, 4), (7, 5)], "speed": 1, "vision_range": 3, "fov_angle": 90}])
+    assert valid and env.budget.spent == 11
+    obs = env.reset()
+    assert sorted(obs) == ["occupancy_grid", "solver_position", "time_feature", "vault_direction", "visibility_map"]
+    assert int((env.visibility_map.visibility > 0.5).sum()) == 23
+    rewards = []
+    for _ in range(5):
+        obs, reward, done, info = env.step(4)
+        rewards.append(reward)
+        if done:
+            break
+    assert rewards == [0.09000000000000001] * 4 + [-0.91]
+    assert env.solver_pos == (1, 6) and env.tick == 5 and info == {"status": "detected", "tick": 4}
+    assert int((env.visibility_map.visibility > 0.5).sum()) == 21
+    assert [c.heading for c in env.cameras] == [75.0] and [g.heading for g in env.guards] == [0.0]
+    assert env.step(0)[1:] == (0.0, True, {"status": "already_done"})
+    assert env.get_state_tensor().shape == (3, 10, 10)
+    assert env.render_text().splitlines()[5] == "#....C...#"
+    # test_fixes.py:13-37
+    env = heist_b200.HeistEnvironment(EnvironmentConfig(grid_rows=10, grid_cols=10))
+    env.set_layout([], [], [])
+    env.reset()
+    tot = sum(env.step(2)[1] for _ in range(7))
+    assert f"{tot:+.3f}" == "+0.630"
+    for _ in range(7):
+        obs, r, done, info = env.step(4)
+        tot += r
+    assert f"{tot:+.3f}" == "+11.560" and info["status"] == "vault_reached" and env.vault_reached
+    env.reset()
+    s = env.get_state_tensor()
+    assert f"{s[2].min():.3f}" == "-1.000" and f"{s[2].max():.3f}" == "0.790"
