@@ -178,6 +178,12 @@ int heist_gae(const float *rew, const float *val, const uint8_t *done, int T, in
  */
 int heist_architect_reward(HeistHandle *h, double *reward_out, double *solve_rate_out, void *stream);
 
+/*
+ * Verification knob: exact_only != 0 routes every ray sample through the fp64 reference arithmetic
+ * (no fixed-point fast path).  Results are bit-identical either way; tests compare the two modes.
+ */
+int heist_set_mode(HeistHandle *h, int exact_only);
+
 /* Synchronises `stream` and reports sticky device-side errors (capacity overflow, bad waypoint). */
 int heist_check_errors(HeistHandle *h, void *stream);
 

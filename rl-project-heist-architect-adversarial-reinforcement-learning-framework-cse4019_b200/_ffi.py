@@ -45,6 +45,7 @@ EXPORTS = {
     "heist_gae": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_double, C.c_double, c_vp, c_vp, C.c_int, c_vp]),
     "heist_architect_reward": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "heist_check_errors": (C.c_int, [c_vp, c_vp]),
+    "heist_set_mode": (C.c_int, [c_vp, C.c_int]),
 }
 
 

@@ -139,6 +139,10 @@ class BatchedHeistEnv:
             t = torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
         return t.contiguous()
 
+    def set_exact_only(self, flag):
+        """Verification knob: force the all-fp64 ray-march (bit-identical to the default filtered path)."""
+        _ffi.check(self._lib.heist_set_mode(self._h, int(bool(flag))), "heist_set_mode")
+
     def check_errors(self):
         _ffi.check(self._lib.heist_check_errors(self._h, self._stream()), "heist_check_errors")
 

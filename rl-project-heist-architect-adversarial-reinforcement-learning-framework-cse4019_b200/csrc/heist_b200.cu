@@ -42,6 +42,7 @@ struct HeistHandle {
     Dev d;
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
+    int exact_only;  // heist_set_mode: 1 = every sample through the fp64 reference arithmetic
     void *allocs[64];
     int n_allocs;
 };
@@ -129,10 +130,12 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dx, ndx, sizeof(ndx)));
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
 
-    h->step_smem = HEIST_WARPS_PER_CTA * warp_env_bytes(d.RW, d.Kc, d.Kg);
+    h->step_smem = HEIST_WARPS_PER_CTA * warp_ctx_bytes(d.R, d.C, d.Kc, d.Kg);
     h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_reset, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
 
     // HeistEnvironment.__init__: bordered grid with START/VAULT, solver at start (environment.py:62-96)
@@ -189,8 +192,26 @@ extern "C" int heist_set_layout_explicit(HeistHandle *h, const HeistLayoutArrays
 extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     if (!h) return fail(-1, "heist_reset: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    k_reset<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(h->d, mask);
+    if (h->exact_only)
+        k_reset<true><<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(h->d, mask);
+    else
+        k_reset<false><<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(h->d, mask);
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static void launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
+                        uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
+    const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
+    if (h->exact_only)
+        k_step_many<true><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
+    else
+        k_step_many<false><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
+}
+
+extern "C" int heist_set_mode(HeistHandle *h, int exact_only) {
+    if (!h) return fail(-1, "heist_set_mode: null handle");
+    h->exact_only = exact_only ? 1 : 0;
     return 0;
 }
 
@@ -198,8 +219,7 @@ extern "C" int heist_step(HeistHandle *h, const int8_t *actions, float *reward, 
                           uint8_t *status, void *stream) {
     if (!h || !actions) return fail(-1, "heist_step: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    k_step_many<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(
-        h->d, actions, 1, 0, reward, reward64, done, status, nullptr);
+    launch_step(h, actions, 1, 0, reward, reward64, done, status, nullptr, (cudaStream_t)stream);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -210,8 +230,7 @@ extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int
     if (T < 0) return fail(-9, "heist_step_many: negative T");
     if (T == 0) return 0;
     CUDA_TRY(cudaSetDevice(h->device));
-    k_step_many<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(
-        h->d, actions, T, autoreset, reward, nullptr, done, status, vis_traj);
+    launch_step(h, actions, T, autoreset, reward, nullptr, done, status, vis_traj, (cudaStream_t)stream);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

@@ -3,46 +3,75 @@
 // Reference: HeistEnvironment.reset / step (environment.py:183-299), Camera.update and
 // get_vision_cone_tiles (security.py:49-101), Guard.update and get_visible_tiles
 // (security.py:145-192), DynamicVisibilityMap.update (visibility.py:31-65).
+//
+// Visibility is the reference's sample-point ray-march, not a geometric rasterisation.  Every
+// sample is decided by a FILTERED-EXACT scheme:
+//   fast path  - ray direction from an fp32 polynomial sincos of the (fp64-reduced) angle, sample
+//                positions as 8.24 fixed-point integers x_j = x_0 + j*sx.  Its error is bounded by
+//                ~1.3e-6 tile; a sample whose fractional part lies within 2^-16 tile of a rounding
+//                boundary is declared ambiguous;
+//   exact path - from the first ambiguous sample on, the ray is re-evaluated exactly as the reference
+//                does it: fp64 cos/sin of radians(angle) (host-libm table at multiples of 30 degrees),
+//                separate fp64 multiply and add, round-half-even.
+// Unambiguous samples round to the same tile in both paths, so the result is bit-identical to the
+// all-fp64 evaluation (heist_set_mode(h, 1) forces the exact path everywhere; tests compare the two).
 #pragma once
 #include "heist_common.cuh"
 
-// Per-warp shared-memory working set of one env.
-struct WarpEnv {
-    uint32_t *wall;      // [RW] grid == WALL row bitmaps
-    uint32_t *vis;       // [RW] visibility row bitmaps (rebuilt every tick)
-    double *cam_fov;     // [Kc]
-    double *cam_speed;   // [Kc]
-    double *cam_head;    // [Kc]
-    int4 *cam_i;         // [Kc] row, col, range, num_rays
-    double *g_fov;       // [Kg]
-    double *g_head;      // [Kg]
-    int4 *g_i;           // [Kg] len, speed, range, num_rays
-    int *g_idx;          // [Kg]
-    int2 *g_pos;         // [Kg] current (row, col)
+#define FX_BITS 24
+#define FX_ONE (1 << FX_BITS)
+#define FX_MASK (FX_ONE - 1)
+#define FX_EPS 256  // 2^-16 tile
+
+// Per-asset (camera or guard) working record in shared memory.
+struct __align__(16) AssetW {
+    double base;     // heading - fov/2 (refreshed every tick)
+    double step;     // fov / num_rays: ray pitch for the fast path
+    double fov;      // exact path
+    double heading;  // current heading
+    int x0, y0;      // fixed-point origin in the padded map, +0.5 rounding bias included
+    int own;         // byte offset of the asset's tile (cameras: excluded from marking), -1 for guards
+    int nsamp;       // 2*range (cameras, unit 0.5) or range (guards, unit 1)
+    int shift;       // 23 for cameras, 24 for guards: sx = dx * 2^shift
+    int num_rays;
+    int row, col;
 };
 
-__host__ __device__ inline size_t warp_env_bytes(int RW, int Kc, int Kg) {
+struct WarpCtx {
+    uint8_t *wallb;   // [(R+2)*S] 1 = blocks sight (WALL or the out-of-bounds ring)
+    uint8_t *visb;    // [(R+2)*S] 1 = visible
+    AssetW *asset;    // [Kc+Kg] cameras first, then guards
+    int *pre;         // [Kc+Kg+1] prefix sums of (num_rays+1)
+    double *speed;    // [Kc] camera rotation speed
+    int4 *g_i;        // [Kg] len, speed, range, num_rays
+    int *g_idx;       // [Kg]
+    int S;            // row stride in bytes (multiple of 4)
+    int map_bytes;    // (R+2)*S rounded up to 16
+};
+
+__host__ __device__ inline int map_stride(int C) { return (C + 2 + 3) & ~3; }
+__host__ __device__ inline int map_bytes(int R, int C) { return ((R + 2) * map_stride(C) + 15) & ~15; }
+__host__ __device__ inline size_t warp_ctx_bytes(int R, int C, int Kc, int Kg) {
     size_t b = 0;
-    b += (size_t)Kc * (3 * sizeof(double) + sizeof(int4));
-    b += (size_t)Kg * (2 * sizeof(double) + sizeof(int4) + sizeof(int2) + sizeof(int));
-    b += (size_t)2 * RW * sizeof(uint32_t);
+    b += (size_t)(Kc + Kg) * sizeof(AssetW);
+    b += (size_t)Kg * sizeof(int4);
+    b += (size_t)Kc * sizeof(double);
+    b += 2 * (size_t)map_bytes(R, C);
+    b += (size_t)(Kc + Kg + 1) * sizeof(int) + (size_t)Kg * sizeof(int);
     return (b + 15) & ~(size_t)15;
 }
 
-__device__ __forceinline__ WarpEnv carve_warp_env(unsigned char *base, int RW, int Kc, int Kg) {
-    WarpEnv S;
-    unsigned char *p = base;  // 16-byte aligned
-    S.cam_i = (int4 *)p;      p += (size_t)Kc * sizeof(int4);
-    S.g_i = (int4 *)p;        p += (size_t)Kg * sizeof(int4);
-    S.cam_fov = (double *)p;  p += (size_t)Kc * sizeof(double);
-    S.cam_speed = (double *)p;p += (size_t)Kc * sizeof(double);
-    S.cam_head = (double *)p; p += (size_t)Kc * sizeof(double);
-    S.g_fov = (double *)p;    p += (size_t)Kg * sizeof(double);
-    S.g_head = (double *)p;   p += (size_t)Kg * sizeof(double);
-    S.g_pos = (int2 *)p;      p += (size_t)Kg * sizeof(int2);
-    S.g_idx = (int *)p;       p += (size_t)Kg * sizeof(int);
-    S.wall = (uint32_t *)p;   p += (size_t)RW * sizeof(uint32_t);
-    S.vis = (uint32_t *)p;
+__device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *p, int R, int C, int Kc, int Kg) {
+    WarpCtx S;
+    S.S = map_stride(C);
+    S.map_bytes = map_bytes(R, C);
+    S.asset = (AssetW *)p;  p += (size_t)(Kc + Kg) * sizeof(AssetW);
+    S.g_i = (int4 *)p;      p += (size_t)Kg * sizeof(int4);
+    S.wallb = p;            p += S.map_bytes;
+    S.visb = p;             p += S.map_bytes;
+    S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
+    S.pre = (int *)p;       p += (size_t)(Kc + Kg + 1) * sizeof(int);
+    S.g_idx = (int *)p;
     return S;
 }
 
@@ -50,51 +79,98 @@ struct EnvRegs {
     int r, c, tick, prev, init, flags, n_vault, n_detect, n_timeout;
 };
 
-// One vision cone: rays i = lane, lane+32, ... <= num_rays; samples dist = unit*j, j = 1..nsamp.
-// Cameras: unit 0.5, nsamp 2*range (the reference's sub-steps 0/.5/1 repeat integer distances,
-// which is idempotent).  Guards: unit 1, nsamp = range.  First out-of-bounds or WALL sample ends a ray.
-__device__ __forceinline__ void cone_march(const Dev &D, const WarpEnv &S, int lane, int row, int col, double fov,
-                                           double heading, int num_rays, int nsamp, double unit) {
-    const double half_fov = __ddiv_rn(fov, 2.0);
-    const double base = __dsub_rn(heading, half_fov);
-    const double drow = (double)row, dcol = (double)col, dn = (double)num_rays;
-    for (int i = lane; i <= num_rays; i += 32) {
-        double angle_deg = __dadd_rn(base, __ddiv_rn(__dmul_rn(fov, (double)i), dn));
-        double dx, dy;
-        ray_dir(angle_deg, D.deg2rad, dx, dy);
+#define RINT_MAGIC 6755399441055744.0  // 2^52 + 2^51: (x + M) has rint(x) in its low 32 bits (RN-even)
+
+__device__ __forceinline__ int rint_even(double x) { return __double2loint(__dadd_rn(x, RINT_MAGIC)); }
+
+// Exact continuation of ray `ri` of asset A from sample j on (security.py:69-99 / 170-190).
+// Returns nothing: marks visb until the first out-of-bounds or WALL sample.
+__device__ __noinline__ void ray_exact(const WarpCtx &S, const AssetW &A, double deg2rad, int ri, int j) {
+    const double half_fov = __ddiv_rn(A.fov, 2.0);
+    const double angle_deg =
+        __dadd_rn(__dsub_rn(A.heading, half_fov), __ddiv_rn(__dmul_rn(A.fov, (double)ri), (double)A.num_rays));
+    double dx, dy;
+    ray_dir(angle_deg, deg2rad, dx, dy);
+    const double unit = (A.shift == 23) ? 0.5 : 1.0;
+    const double dcol = (double)A.col, drow = (double)A.row;
+    for (; j <= A.nsamp; ++j) {
+        const double dist = unit * (double)j;  // exact
+        int c = rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
+        int r = rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
+        // the ring of blocking cells around the grid catches every first out-of-bounds sample
+        // (consecutive samples move by at most one tile per axis)
+        int off = (r + 1) * S.S + (c + 1);
+        if (S.wallb[off]) return;
+        if (off != A.own) S.visb[off] = 1;
+    }
+}
+
+// DynamicVisibilityMap.update (visibility.py:31-65): all rays of all assets of the env, flattened
+// over the warp's lanes.
+template <bool EXACT_ONLY>
+__device__ __forceinline__ void compute_visibility(const Dev &D, const WarpCtx &S, int lane, int n_cams, int n_assets) {
+    for (int i = lane * 16; i < S.map_bytes; i += 512) *reinterpret_cast<int4 *>(S.visb + i) = make_int4(0, 0, 0, 0);
+    __syncwarp();
+    const int total = S.pre[n_assets];
+    int seg = -1, seg_lo = 0, seg_hi = 0;
+    double base = 0.0, step = 0.0;
+    int x0 = 0, y0 = 0, own = -1, nsamp = 0;
+    float scale = 0.0f;
+    for (int i = lane; i < total; i += 32) {
+        if (i >= seg_hi) {
+            do { ++seg; seg_lo = seg_hi; seg_hi = S.pre[seg + 1]; } while (i >= seg_hi);
+            const AssetW &A = S.asset[seg];
+            base = A.base; step = A.step; x0 = A.x0; y0 = A.y0; own = A.own; nsamp = A.nsamp;
+            scale = (A.shift == 23) ? 8388608.0f : 16777216.0f;
+        }
+        const int ri = i - seg_lo;
+        if (EXACT_ONLY) { ray_exact(S, S.asset[seg], D.deg2rad, ri, 1); continue; }
+        // ---- fast path: direction (error <~ 1.5e-7) ----
+        const double a = fma((double)ri, step, base);                   // degrees
+        const double t = fma(a, 1.0 / 90.0, RINT_MAGIC);
+        const int q = __double2loint(t);                                // nearest quadrant
+        const float r = (float)(fma(t - RINT_MAGIC, -90.0, a) * 0.017453292519943295);  // |r| <= pi/4 (+eps)
+        const float r2 = r * r;
+        float sn = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+        float cs = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                        fmaf(r2, -0.5f, 1.0f));
+        float c_a = (q & 1) ? sn : cs;   // cos(q*90 + r)
+        float s_a = (q & 1) ? cs : sn;   // sin(q*90 + r)
+        if ((q + 1) & 2) c_a = -c_a;
+        if (q & 2) s_a = -s_a;
+        const int sx = __float2int_rn(c_a * scale);    // dx =  cos
+        const int sy = __float2int_rn(-s_a * scale);   // dy = -sin
+        // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
+        int x = x0, y = y0;
         for (int j = 1; j <= nsamp; ++j) {
-            double dist = unit * (double)j;  // exact
-            double fx = __dadd_rn(dcol, __dmul_rn(dx, dist));
-            double fy = __dadd_rn(drow, __dmul_rn(dy, dist));
-            int c = __double2int_rn(fx);  // round half to even, like round()
-            int r = __double2int_rn(fy);
-            if ((unsigned)r >= (unsigned)D.R || (unsigned)c >= (unsigned)D.C) break;
-            int word = r * D.W + (c >> 5);
-            uint32_t bit = 1u << (c & 31);
-            if (S.wall[word] & bit) break;
-            if (r != row || c != col) atomicOr(&S.vis[word], bit);
+            x += sx; y += sy;
+            if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {
+                ray_exact(S, S.asset[seg], D.deg2rad, ri, j);
+                break;
+            }
+            const int off = (y >> FX_BITS) * S.S + (x >> FX_BITS);
+            if (S.wallb[off]) break;
+            if (off != own) S.visb[off] = 1;
         }
     }
-}
-
-// DynamicVisibilityMap.update (visibility.py:31-65)
-__device__ __forceinline__ void compute_visibility(const Dev &D, const WarpEnv &S, int lane, int n_cams, int n_guards) {
-    for (int i = lane; i < D.RW; i += 32) S.vis[i] = 0u;
     __syncwarp();
-    for (int k = 0; k < n_cams; ++k) {
-        int4 ci = S.cam_i[k];
-        cone_march(D, S, lane, ci.x, ci.y, S.cam_fov[k], S.cam_head[k], ci.w, 2 * ci.z, 0.5);
-    }
-    for (int k = 0; k < n_guards; ++k) {
-        int4 gi = S.g_i[k];
-        int2 gp = S.g_pos[k];
-        cone_march(D, S, lane, gp.x, gp.y, S.g_fov[k], S.g_head[k], gi.w, gi.z, 1.0);
-        if (lane == 0) atomicOr(&S.vis[gp.x * D.W + (gp.y >> 5)], 1u << (gp.y & 31));  // guard's own tile
+    // guard's own tile is always dangerous (visibility.py:59)
+    if (lane >= n_cams && lane < n_assets) {
+        const AssetW &A = S.asset[lane];
+        S.visb[(A.row + 1) * S.S + A.col + 1] = 1;
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ void load_env(const Dev &D, const WarpEnv &S, int env, int lane, EnvRegs &E, int &n_cams,
+// per-tick refresh of an asset record after its heading / position changed
+__device__ __forceinline__ void refresh_asset(const WarpCtx &S, AssetW &A, bool is_cam) {
+    A.base = A.heading - A.fov * 0.5;
+    A.x0 = ((A.col + 1) << FX_BITS) + (FX_ONE >> 1);
+    A.y0 = ((A.row + 1) << FX_BITS) + (FX_ONE >> 1);
+    A.own = is_cam ? (A.row + 1) * S.S + A.col + 1 : -1;
+}
+
+__device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int &n_cams,
                                          int &n_guards) {
     const int4 es = *reinterpret_cast<const int4 *>(D.env_s + (size_t)env * 4);
     n_cams = es.x;
@@ -103,29 +179,64 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpEnv &S, int env
     const int4 d1 = *reinterpret_cast<const int4 *>(D.env_d + (size_t)env * 8 + 4);
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    for (int i = lane; i < D.RW; i += 32) S.wall[i] = D.wall[(size_t)env * D.RW + i];
+    // byte maps with a blocking ring: wallb from the wall bitmap, visb from the stored visibility
+    const uint32_t *wall = D.wall + (size_t)env * D.RW, *vis = D.vis + (size_t)env * D.RW;
+    for (int i = lane; i < S.map_bytes; i += 32) {
+        int rr = i / S.S - 1, cc = i - (rr + 1) * S.S - 1;
+        bool inside = rr >= 0 && rr < D.R && cc >= 0 && cc < D.C;
+        uint8_t w = 1, v = 0;
+        if (inside) {
+            w = (wall[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
+            v = (vis[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
+        }
+        S.wallb[i] = w;
+        S.visb[i] = v;
+    }
     if (lane < n_cams) {
         size_t o = (size_t)env * D.Kc + lane;
-        S.cam_fov[lane] = D.cam_f[o * 2];
-        S.cam_speed[lane] = D.cam_f[o * 2 + 1];
-        S.cam_head[lane] = D.cam_heading[o];
+        AssetW &A = S.asset[lane];
         const int16_t *ci = D.cam_i + o * 4;
-        S.cam_i[lane] = make_int4(ci[0], ci[1], ci[2], ci[3]);
+        A.fov = D.cam_f[o * 2];
+        S.speed[lane] = D.cam_f[o * 2 + 1];
+        A.heading = D.cam_heading[o];
+        A.row = ci[0]; A.col = ci[1]; A.nsamp = 2 * ci[2]; A.shift = 23; A.num_rays = ci[3];
+        A.step = A.fov / (double)A.num_rays;
+        refresh_asset(S, A, true);
     }
     if (lane < n_guards) {
         size_t o = (size_t)env * D.Kg + lane;
-        S.g_fov[lane] = D.guard_fov[o];
-        S.g_head[lane] = D.guard_heading[o];
-        S.g_i[lane] = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);
+        AssetW &A = S.asset[n_cams + lane];
+        const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);
+        S.g_i[lane] = gi;
+        A.fov = D.guard_fov[o];
+        A.heading = D.guard_heading[o];
         int idx = D.guard_idx[o];
         S.g_idx[lane] = idx;
         const uint8_t *p = D.guard_path + (o * D.L + idx) * 2;
-        S.g_pos[lane] = make_int2(p[0], p[1]);
+        A.row = p[0]; A.col = p[1]; A.nsamp = gi.z; A.shift = 24; A.num_rays = gi.w;
+        A.step = A.fov / (double)A.num_rays;
+        refresh_asset(S, A, false);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int acc = 0;
+        S.pre[0] = 0;
+        for (int k = 0; k < n_cams + n_guards; ++k) { acc += S.asset[k].num_rays + 1; S.pre[k + 1] = acc; }
     }
     __syncwarp();
 }
 
-__device__ __forceinline__ void store_env(const Dev &D, const WarpEnv &S, int env, int lane, const EnvRegs &E, int status,
+// row bitmaps of the byte visibility map -> dst[RW]
+__device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, int lane, uint32_t *dst) {
+    for (int r = 0; r < D.R; ++r)
+        for (int w = 0; w < D.W; ++w) {
+            int c = w * 32 + lane;
+            unsigned m = __ballot_sync(0xffffffffu, c < D.C && S.visb[(r + 1) * S.S + c + 1]);
+            if (lane == 0) dst[r * D.W + w] = m;
+        }
+}
+
+__device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, int env, int lane, const EnvRegs &E, int status,
                                           int n_cams, int n_guards) {
     if (lane == 0) {
         int4 d0 = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
@@ -133,17 +244,18 @@ __device__ __forceinline__ void store_env(const Dev &D, const WarpEnv &S, int en
         *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = d0;
         *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) = d1;
     }
-    if (lane < n_cams) D.cam_heading[(size_t)env * D.Kc + lane] = S.cam_head[lane];
+    if (lane < n_cams) D.cam_heading[(size_t)env * D.Kc + lane] = S.asset[lane].heading;
     if (lane < n_guards) {
         size_t o = (size_t)env * D.Kg + lane;
-        D.guard_heading[o] = S.g_head[lane];
+        D.guard_heading[o] = S.asset[n_cams + lane].heading;
         D.guard_idx[o] = S.g_idx[lane];
     }
-    for (int i = lane; i < D.RW; i += 32) D.vis[(size_t)env * D.RW + i] = S.vis[i];
+    pack_vis(D, S, lane, D.vis + (size_t)env * D.RW);
 }
 
 // HeistEnvironment.reset (environment.py:183-214): camera and guard headings persist.
-__device__ __forceinline__ void reset_env(const Dev &D, const WarpEnv &S, int env, int lane, EnvRegs &E, int n_cams,
+template <bool EXACT_ONLY>
+__device__ __forceinline__ void reset_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
                                           int n_guards) {
     E.r = D.start_r; E.c = D.start_c; E.tick = 0;
     E.flags = 0;
@@ -152,48 +264,56 @@ __device__ __forceinline__ void reset_env(const Dev &D, const WarpEnv &S, int en
     if (lane < n_guards) {
         S.g_idx[lane] = 0;
         const uint8_t *p = D.guard_path + ((size_t)env * D.Kg + lane) * D.L * 2;
-        S.g_pos[lane] = make_int2(p[0], p[1]);
+        AssetW &A = S.asset[n_cams + lane];
+        A.row = p[0]; A.col = p[1];
+        refresh_asset(S, A, false);
     }
     __syncwarp();
-    compute_visibility(D, S, lane, n_cams, n_guards);
+    compute_visibility<EXACT_ONLY>(D, S, lane, n_cams, n_cams + n_guards);
 }
 
 // HeistEnvironment.step (environment.py:216-299).  All lanes carry the scalar env state redundantly.
-__device__ __forceinline__ int step_env(const Dev &D, const WarpEnv &S, int env, int lane, EnvRegs &E, int n_cams,
+template <bool EXACT_ONLY>
+__device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
                                         int n_guards, int action, double &reward_out) {
     if (E.flags & F_DONE) { reward_out = 0.0; return HEIST_ALREADY_DONE; }  // :232-233
     double reward = D.reward_step;                                           // :235
     int status = HEIST_RUNNING;
-    // 1. move (:239-246) -- blocked only by out-of-bounds or WALL
+    // 1. move (:239-246) -- blocked only by out-of-bounds (the ring) or WALL
     int nr = E.r + (action == 2) - (action == 1);
     int nc = E.c + (action == 4) - (action == 3);
-    if ((unsigned)nr < (unsigned)D.R && (unsigned)nc < (unsigned)D.C &&
-        !((S.wall[nr * D.W + (nc >> 5)] >> (nc & 31)) & 1u)) { E.r = nr; E.c = nc; }
+    if (!S.wallb[(nr + 1) * S.S + nc + 1]) { E.r = nr; E.c = nc; }
     // 2. cameras rotate (security.py:49-51), guards advance (security.py:145-159)
-    if (lane < n_cams) S.cam_head[lane] = py_mod360(__dadd_rn(S.cam_head[lane], S.cam_speed[lane]));
+    if (lane < n_cams) {
+        AssetW &A = S.asset[lane];
+        A.heading = py_mod360(__dadd_rn(A.heading, S.speed[lane]));
+        A.base = A.heading - A.fov * 0.5;
+    }
     if (lane < n_guards) {
         int4 gi = S.g_i[lane];
         if (gi.x >= 2) {
+            AssetW &A = S.asset[n_cams + lane];
             int old = S.g_idx[lane];
             int ni = py_imod(old + gi.y, gi.x);
             size_t o = ((size_t)env * D.Kg + lane) * D.L;
             double h = D.guard_head[o + old];
-            if (h == h) S.g_head[lane] = h;  // NaN <=> the move is (0,0): heading unchanged
+            if (h == h) A.heading = h;  // NaN <=> the move is (0,0): heading unchanged
             S.g_idx[lane] = ni;
             const uint8_t *p = D.guard_path + (o + ni) * 2;
-            S.g_pos[lane] = make_int2(p[0], p[1]);
+            A.row = p[0]; A.col = p[1];
+            refresh_asset(S, A, false);
         }
     }
     __syncwarp();
     // 3. visibility (:257-258)
-    compute_visibility(D, S, lane, n_cams, n_guards);
+    compute_visibility<EXACT_ONLY>(D, S, lane, n_cams, n_cams + n_guards);
     // 4. shaping (:261-269)
     int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
     reward = __dadd_rn(reward, __dmul_rn((double)(E.prev - curr), 0.1));
     E.prev = curr;
     if (curr <= 3 && E.init > 3) reward = __dadd_rn(reward, __dmul_rn(0.05, (double)(3 - curr)));
     // 5. detection (:273-281), vault (:284-288), timeout (:291-297)
-    if ((S.vis[E.r * D.W + (E.c >> 5)] >> (E.c & 31)) & 1u) {
+    if (S.visb[(E.r + 1) * S.S + E.c + 1]) {
         E.flags |= F_DETECTED | F_DONE;
         reward = __dadd_rn(reward, D.reward_detection);
         status = HEIST_DETECTED;
@@ -219,7 +339,8 @@ __device__ __forceinline__ int step_env(const Dev &D, const WarpEnv &S, int env,
 }
 
 // T steps per launch; T = 1 with vis_traj = NULL is HeistEnvironment.step for the batch.
-__global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32)
+template <bool EXACT_ONLY>
+__global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
             double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
             uint32_t *__restrict__ vis_traj) {
@@ -227,45 +348,40 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * HEIST_WARPS_PER_CTA + warp;
     if (env >= D.N) return;
-    WarpEnv S = carve_warp_env(smem + (size_t)warp * warp_env_bytes(D.RW, D.Kc, D.Kg), D.RW, D.Kc, D.Kg);
+    WarpCtx S = carve_warp_ctx(smem + (size_t)warp * warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg), D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams, n_guards;
     load_env(D, S, env, lane, E, n_cams, n_guards);
-    // the visibility map is state too (a done env keeps it): start from the stored one
-    for (int i = lane; i < D.RW; i += 32) S.vis[i] = D.vis[(size_t)env * D.RW + i];
-    __syncwarp();
     int status = HEIST_RUNNING;
     for (int t = 0; t < T; ++t) {
         const size_t o = (size_t)t * D.N + env;
         int action = actions[o];
         double rw;
-        status = step_env(D, S, env, lane, E, n_cams, n_guards, action, rw);
+        status = step_env<EXACT_ONLY>(D, S, env, lane, E, n_cams, n_guards, action, rw);
         if (lane == 0) {
             if (reward) reward[o] = (float)rw;
             if (reward64) reward64[o] = rw;
             if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
             if (status_out) status_out[o] = (uint8_t)status;
         }
-        if (autoreset && (E.flags & F_DONE)) reset_env(D, S, env, lane, E, n_cams, n_guards);
-        if (vis_traj) {
-            uint32_t *vt = vis_traj + o * D.RW;
-            for (int i = lane; i < D.RW; i += 32) vt[i] = S.vis[i];
-        }
+        if (autoreset && (E.flags & F_DONE)) reset_env<EXACT_ONLY>(D, S, env, lane, E, n_cams, n_guards);
+        if (vis_traj) pack_vis(D, S, lane, vis_traj + o * D.RW);
     }
     store_env(D, S, env, lane, E, status, n_cams, n_guards);
 }
 
-__global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32)
+template <bool EXACT_ONLY>
+__global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_reset(Dev D, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int env = blockIdx.x * HEIST_WARPS_PER_CTA + warp;
     if (env >= D.N) return;
     if (mask && !mask[env]) return;
-    WarpEnv S = carve_warp_env(smem + (size_t)warp * warp_env_bytes(D.RW, D.Kc, D.Kg), D.RW, D.Kc, D.Kg);
+    WarpCtx S = carve_warp_ctx(smem + (size_t)warp * warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg), D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams, n_guards;
     load_env(D, S, env, lane, E, n_cams, n_guards);
-    reset_env(D, S, env, lane, E, n_cams, n_guards);
+    reset_env<EXACT_ONLY>(D, S, env, lane, E, n_cams, n_guards);
     store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
 }

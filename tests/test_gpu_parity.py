@@ -407,3 +407,35 @@ def test_facade_reference_smoke_scripts():
     env.reset()
     s = env.get_state_tensor()
     assert f"{s[2].min():.3f}" == "-1.000" and f"{s[2].max():.3f}" == "0.790"
+
+
+@pytest.mark.parametrize("R,C,N,T,counts,nice", [
+    (20, 20, 4096, 200, None, False),
+    (20, 20, 2048, 200, None, True),
+    (32, 32, 2048, 100, (2, 4, 2), False),   # config 3: budget 22 = 4 cameras + 2 guards (+2 walls)
+    (32, 32, 1024, 100, (1, 7, 0), True),
+    (64, 64, 1024, 60, (2, 4, 2), False),
+])
+def test_filtered_fast_path_equals_all_fp64_path(R, C, N, T, counts, nice):
+    """Device vs device at full size: the fixed-point filter + exact fallback must give the same
+    bits as routing every sample through the fp64 reference arithmetic."""
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C)
+    env = BatchedHeistEnv(cfg, N)
+    rng = np.random.default_rng(4242 + R + N)
+    am = (synthetic.sample_asset_maps(rng, N, R, C) if counts is None
+          else synthetic.sample_asset_maps_exact(rng, N, R, C, *counts))
+    cp = synthetic.sample_cam_params(rng, N, nice)
+    acts = synthetic.sample_actions(rng, T, N)
+    res = []
+    for exact in (False, True):
+        env.set_exact_only(exact)
+        env.set_layout_from_asset_map(am, cp, 22 if counts else 15)
+        env.reset()
+        v0 = env.visibility_bits.clone()
+        out = env.step_many(acts, autoreset=True, want_vis=True)
+        res.append((v0, {k: v.clone() for k, v in out.items()}, env.cam_heading.clone(), env.env_dyn.clone()))
+    assert torch.equal(res[0][0], res[1][0])
+    for k in res[0][1]:
+        assert torch.equal(res[0][1][k], res[1][1][k]), k
+    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+    assert res[0][1]["vis_bits"].ne(0).any()
