@@ -42,6 +42,7 @@ struct HeistHandle {
     Dev d;
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
+    int log2s;       // row-stride class of the shared-memory cell map (template selector)
     int exact_only;  // heist_set_mode: 1 = every sample through the fp64 reference arithmetic
     void *allocs[64];
     int n_allocs;
@@ -111,6 +112,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     A(d.guard_head, N * d.Kg * d.L);
     A(d.env_d, N * 8); A(d.cam_heading, N * d.Kc); A(d.guard_heading, N * d.Kg); A(d.guard_idx, N * d.Kg);
     A(d.vis, N * d.RW); A(d.pos_tab, (size_t)d.RC); A(d.err, (size_t)1);
+    A(d.cost, N); A(d.slot2env, (size_t)env_blocks(num_envs) * HEIST_WARPS_PER_CTA);
     LayoutDev &z = h->lz;
     A(z.n_walls, N); A(z.wall_rc, N * d.Kw * 2); A(z.n_cams, N); A(z.cam_rc, N * d.Kc * 2);
     A(z.cam_f, N * d.Kc * 3); A(z.cam_range, N * d.Kc); A(z.n_guards, N); A(z.guard_len, N * d.Kg);
@@ -132,10 +134,14 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 
     h->step_smem = HEIST_WARPS_PER_CTA * warp_ctx_bytes(d.R, d.C, d.Kc, d.Kg);
     h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+#define SET_SMEM(L)                                                                                                          \
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<false, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<true, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));  \
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<false, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));     \
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<true, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    SET_SMEM(0) SET_SMEM(5) SET_SMEM(6)
+#undef SET_SMEM
+    h->log2s = map_log2s(d.C);
     CUDA_TRY(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
 
     // HeistEnvironment.__init__: bordered grid with START/VAULT, solver at start (environment.py:62-96)
@@ -144,6 +150,8 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     LayoutDev none;
     memset(&none, 0, sizeof(none));
     k_set_layout<<<env_blocks(num_envs), HEIST_WARPS_PER_CTA * 32, h->layout_smem>>>(d, none, nullptr, nullptr);
+    CUDA_TRY(cudaMemsetAsync(d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(num_envs) * HEIST_WARPS_PER_CTA, 0));
+    k_build_order<<<1, 1024>>>(d, env_blocks(num_envs));
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
@@ -153,6 +161,9 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 static int launch_set_layout(HeistHandle *h, const LayoutDev &lz, const int32_t *budget, uint8_t *valid_out,
                              cudaStream_t s) {
     k_set_layout<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->layout_smem, s>>>(h->d, lz, budget, valid_out);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemsetAsync(h->d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(h->N) * HEIST_WARPS_PER_CTA, s));
+    k_build_order<<<1, 1024, 0, s>>>(h->d, env_blocks(h->N));
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -192,10 +203,12 @@ extern "C" int heist_set_layout_explicit(HeistHandle *h, const HeistLayoutArrays
 extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     if (!h) return fail(-1, "heist_reset: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
-    if (h->exact_only)
-        k_reset<true><<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(h->d, mask);
-    else
-        k_reset<false><<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->step_smem, (cudaStream_t)stream>>>(h->d, mask);
+    const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
+    cudaStream_t s = (cudaStream_t)stream;
+#define GO(E, L) k_reset<E, L><<<grid, block, h->step_smem, s>>>(h->d, mask)
+    if (h->exact_only) { if (h->log2s == 5) GO(true, 5); else if (h->log2s == 6) GO(true, 6); else GO(true, 0); }
+    else { if (h->log2s == 5) GO(false, 5); else if (h->log2s == 6) GO(false, 6); else GO(false, 0); }
+#undef GO
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -203,10 +216,10 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
 static void launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
                         uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
-    if (h->exact_only)
-        k_step_many<true><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
-    else
-        k_step_many<false><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
+#define GO(E, L) k_step_many<E, L><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
+    if (h->exact_only) { if (h->log2s == 5) GO(true, 5); else if (h->log2s == 6) GO(true, 6); else GO(true, 0); }
+    else { if (h->log2s == 5) GO(false, 5); else if (h->log2s == 6) GO(false, 6); else GO(false, 0); }
+#undef GO
 }
 
 extern "C" int heist_set_mode(HeistHandle *h, int exact_only) {

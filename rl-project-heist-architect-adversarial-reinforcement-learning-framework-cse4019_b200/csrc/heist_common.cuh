@@ -42,6 +42,8 @@ struct Dev {
     int32_t *guard_idx;   // [N][Kg]
     uint32_t *vis;        // [N][RW]
     float *pos_tab;       // [RC] float32(-0.3 * (manhattan(cell, vault) / (R + C)))
+    int32_t *cost;        // [N] ray-march samples per tick (load-balance estimate)
+    int32_t *slot2env;    // [ceil(N/4)*4] warp slot -> env (-1: empty), cost-balanced
     int *err;             // sticky device error flags
 };
 

@@ -171,7 +171,7 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
         tile[i] = (r == 0 || r == R - 1 || c == 0 || c == C - 1) ? HEIST_WALL : HEIST_EMPTY;
     }
     __syncwarp();
-    int n_cams = 0, n_guards = 0, spent = 0;
+    int n_cams = 0, n_guards = 0, spent = 0, cost = 0;
     if (lane == 0) {
         tile[D.start_r * C + D.start_c] = HEIST_START;
         tile[D.vault_r * C + D.vault_c] = HEIST_VAULT;
@@ -210,6 +210,7 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
                 D.cam_heading[d] = heading;
                 int16_t *ci = D.cam_i + d * 4;
                 ci[0] = r; ci[1] = c; ci[2] = rng; ci[3] = num_rays;
+                cost += (num_rays + 1) * (2 * max(rng, 0) + 4);
                 n_cams++;
             }
         }
@@ -242,6 +243,7 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
                     D.guard_path[(d * D.L + k) * 2 + 1] = (uint8_t)Lz.guard_path[(o * D.L + k) * 2 + 1];
                     D.guard_head[d * D.L + k] = Lz.guard_head[o * D.L + k];
                 }
+                cost += (num_rays + 1) * (max(Lz.guard_range[o], 0) + 4);
                 D.guard_heading[d] = 0.0;  // Guard.heading default (security.py:131)
                 D.guard_idx[d] = 0;
                 tile[Lz.guard_path[o * D.L * 2] * C + Lz.guard_path[o * D.L * 2 + 1]] = HEIST_GUARD;  // :148
@@ -269,6 +271,7 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
         int32_t *d = D.env_d + (size_t)env * 8;
         d[5] = 0; d[6] = 0; d[7] = 0;
         if (valid_out) valid_out[env] = valid ? 1 : 0;
+        D.cost[env] = cost + 64;
     }
 }
 

@@ -23,6 +23,9 @@
 #define FX_MASK (FX_ONE - 1)
 #define FX_EPS 256  // 2^-16 tile
 
+#define CELL_BLOCK 1u  // WALL, or the out-of-bounds ring around the grid
+#define CELL_VIS 2u    // under surveillance this tick
+
 // Per-asset (camera or guard) working record in shared memory.
 struct __align__(16) AssetW {
     double base;     // heading - fov/2 (refreshed every tick)
@@ -30,26 +33,31 @@ struct __align__(16) AssetW {
     double fov;      // exact path
     double heading;  // current heading
     int x0, y0;      // fixed-point origin in the padded map, +0.5 rounding bias included
-    int own;         // byte offset of the asset's tile (cameras: excluded from marking), -1 for guards
+    unsigned own;    // map offset of the asset's tile (cameras: excluded from marking), ~0 for guards
     int nsamp;       // 2*range (cameras, unit 0.5) or range (guards, unit 1)
     int shift;       // 23 for cameras, 24 for guards: sx = dx * 2^shift
     int num_rays;
     int row, col;
 };
 
+// Per-warp shared-memory working set of one env.  The padded cell map has one byte per tile plus a
+// one-tile ring of blocking cells, so an out-of-bounds sample needs no bounds test.
 struct WarpCtx {
-    uint8_t *wallb;   // [(R+2)*S] 1 = blocks sight (WALL or the out-of-bounds ring)
-    uint8_t *visb;    // [(R+2)*S] 1 = visible
+    uint8_t *cell;    // [(R+2)*S] CELL_BLOCK | CELL_VIS
+    uint8_t *wall0;   // [(R+2)*S] pristine copy with only CELL_BLOCK (source of the per-tick clear)
     AssetW *asset;    // [Kc+Kg] cameras first, then guards
     int *pre;         // [Kc+Kg+1] prefix sums of (num_rays+1)
     double *speed;    // [Kc] camera rotation speed
     int4 *g_i;        // [Kg] len, speed, range, num_rays
     int *g_idx;       // [Kg]
-    int S;            // row stride in bytes (multiple of 4)
+    unsigned cell_sa; // shared-space address of cell[]
+    int S;            // row stride in bytes
     int map_bytes;    // (R+2)*S rounded up to 16
 };
 
-__host__ __device__ inline int map_stride(int C) { return (C + 2 + 3) & ~3; }
+// Row stride: a power of two when it does not blow up the map (offset = shift+or), else C+2 rounded to 4.
+__host__ __device__ inline int map_log2s(int C) { return C + 2 <= 32 ? 5 : (C + 2 <= 64 ? 6 : 0); }
+__host__ __device__ inline int map_stride(int C) { int l = map_log2s(C); return l ? (1 << l) : ((C + 2 + 3) & ~3); }
 __host__ __device__ inline int map_bytes(int R, int C) { return ((R + 2) * map_stride(C) + 15) & ~15; }
 __host__ __device__ inline size_t warp_ctx_bytes(int R, int C, int Kc, int Kg) {
     size_t b = 0;
@@ -67,12 +75,22 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *p, int R, int C
     S.map_bytes = map_bytes(R, C);
     S.asset = (AssetW *)p;  p += (size_t)(Kc + Kg) * sizeof(AssetW);
     S.g_i = (int4 *)p;      p += (size_t)Kg * sizeof(int4);
-    S.wallb = p;            p += S.map_bytes;
-    S.visb = p;             p += S.map_bytes;
+    S.cell = p;             p += S.map_bytes;
+    S.wall0 = p;            p += S.map_bytes;
     S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
     S.pre = (int *)p;       p += (size_t)(Kc + Kg + 1) * sizeof(int);
     S.g_idx = (int *)p;
+    S.cell_sa = (unsigned)__cvta_generic_to_shared(S.cell);
     return S;
+}
+
+__device__ __forceinline__ unsigned lds_u8(unsigned sa) {
+    unsigned v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_u8(unsigned sa, unsigned v) {
+    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }
 
 struct EnvRegs {
@@ -83,9 +101,10 @@ struct EnvRegs {
 
 __device__ __forceinline__ int rint_even(double x) { return __double2loint(__dadd_rn(x, RINT_MAGIC)); }
 
-// Exact continuation of ray `ri` of asset A from sample j on (security.py:69-99 / 170-190).
-// Returns nothing: marks visb until the first out-of-bounds or WALL sample.
-__device__ __noinline__ void ray_exact(const WarpCtx &S, const AssetW &A, double deg2rad, int ri, int j) {
+// Exact continuation of ray `ri` of asset `seg` from sample j on (security.py:69-99 / 170-190):
+// marks cells until the first out-of-bounds (ring) or WALL sample.
+__device__ __noinline__ void ray_exact(const AssetW *asset, int seg, unsigned cell_sa, int S, double deg2rad, int ri, int j) {
+    const AssetW A = asset[seg];  // private copy: no re-reads of shared memory in the loop
     const double half_fov = __ddiv_rn(A.fov, 2.0);
     const double angle_deg =
         __dadd_rn(__dsub_rn(A.heading, half_fov), __ddiv_rn(__dmul_rn(A.fov, (double)ri), (double)A.num_rays));
@@ -97,24 +116,28 @@ __device__ __noinline__ void ray_exact(const WarpCtx &S, const AssetW &A, double
         const double dist = unit * (double)j;  // exact
         int c = rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
         int r = rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
-        // the ring of blocking cells around the grid catches every first out-of-bounds sample
-        // (consecutive samples move by at most one tile per axis)
-        int off = (r + 1) * S.S + (c + 1);
-        if (S.wallb[off]) return;
-        if (off != A.own) S.visb[off] = 1;
+        // consecutive samples move by at most one tile per axis, so the first out-of-bounds sample
+        // always lands on the blocking ring
+        unsigned off = (unsigned)((r + 1) * S + (c + 1));
+        if (lds_u8(cell_sa + off) == CELL_BLOCK) return;
+        if (off != A.own) sts_u8(cell_sa + off, CELL_VIS);
     }
 }
 
 // DynamicVisibilityMap.update (visibility.py:31-65): all rays of all assets of the env, flattened
 // over the warp's lanes.
-template <bool EXACT_ONLY>
+template <bool EXACT_ONLY, int LOG2S>
 __device__ __forceinline__ void compute_visibility(const Dev &D, const WarpCtx &S, int lane, int n_cams, int n_assets) {
-    for (int i = lane * 16; i < S.map_bytes; i += 512) *reinterpret_cast<int4 *>(S.visb + i) = make_int4(0, 0, 0, 0);
+    for (int i = lane * 16; i < S.map_bytes; i += 512)
+        *reinterpret_cast<int4 *>(S.cell + i) = *reinterpret_cast<const int4 *>(S.wall0 + i);
     __syncwarp();
     const int total = S.pre[n_assets];
+    const unsigned cell_sa = S.cell_sa;
+    const int stride = S.S;
     int seg = -1, seg_lo = 0, seg_hi = 0;
     double base = 0.0, step = 0.0;
-    int x0 = 0, y0 = 0, own = -1, nsamp = 0;
+    int x0 = 0, y0 = 0, nsamp = 0;
+    unsigned own = ~0u;
     float scale = 0.0f;
     for (int i = lane; i < total; i += 32) {
         if (i >= seg_hi) {
@@ -124,8 +147,8 @@ __device__ __forceinline__ void compute_visibility(const Dev &D, const WarpCtx &
             scale = (A.shift == 23) ? 8388608.0f : 16777216.0f;
         }
         const int ri = i - seg_lo;
-        if (EXACT_ONLY) { ray_exact(S, S.asset[seg], D.deg2rad, ri, 1); continue; }
-        // ---- fast path: direction (error <~ 1.5e-7) ----
+        if (EXACT_ONLY) { ray_exact(S.asset, seg, cell_sa, stride, D.deg2rad, ri, 1); continue; }
+        // ---- fast path: direction (error < 1e-7) ----
         const double a = fma((double)ri, step, base);                   // degrees
         const double t = fma(a, 1.0 / 90.0, RINT_MAGIC);
         const int q = __double2loint(t);                                // nearest quadrant
@@ -142,22 +165,25 @@ __device__ __forceinline__ void compute_visibility(const Dev &D, const WarpCtx &
         const int sy = __float2int_rn(-s_a * scale);   // dy = -sin
         // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
         int x = x0, y = y0;
+#pragma unroll 2
         for (int j = 1; j <= nsamp; ++j) {
             x += sx; y += sy;
             if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {
-                ray_exact(S, S.asset[seg], D.deg2rad, ri, j);
+                ray_exact(S.asset, seg, cell_sa, stride, D.deg2rad, ri, j);
                 break;
             }
-            const int off = (y >> FX_BITS) * S.S + (x >> FX_BITS);
-            if (S.wallb[off]) break;
-            if (off != own) S.visb[off] = 1;
+            unsigned off;
+            if (LOG2S) off = (((unsigned)y >> (FX_BITS - LOG2S)) & (~0u << LOG2S)) | ((unsigned)x >> FX_BITS);
+            else off = (unsigned)((y >> FX_BITS) * stride + (x >> FX_BITS));
+            if (lds_u8(cell_sa + off) == CELL_BLOCK) break;  // blocking cells are never marked, so == suffices
+            if (off != own) sts_u8(cell_sa + off, CELL_VIS);
         }
     }
     __syncwarp();
     // guard's own tile is always dangerous (visibility.py:59)
     if (lane >= n_cams && lane < n_assets) {
         const AssetW &A = S.asset[lane];
-        S.visb[(A.row + 1) * S.S + A.col + 1] = 1;
+        S.cell[(A.row + 1) * S.S + A.col + 1] |= CELL_VIS;
     }
     __syncwarp();
 }
@@ -167,7 +193,7 @@ __device__ __forceinline__ void refresh_asset(const WarpCtx &S, AssetW &A, bool 
     A.base = A.heading - A.fov * 0.5;
     A.x0 = ((A.col + 1) << FX_BITS) + (FX_ONE >> 1);
     A.y0 = ((A.row + 1) << FX_BITS) + (FX_ONE >> 1);
-    A.own = is_cam ? (A.row + 1) * S.S + A.col + 1 : -1;
+    A.own = is_cam ? (unsigned)((A.row + 1) * S.S + A.col + 1) : ~0u;
 }
 
 __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int &n_cams,
@@ -179,18 +205,18 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env
     const int4 d1 = *reinterpret_cast<const int4 *>(D.env_d + (size_t)env * 8 + 4);
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    // byte maps with a blocking ring: wallb from the wall bitmap, visb from the stored visibility
+    // cell map with a blocking ring: CELL_BLOCK from the wall bitmap, CELL_VIS from the stored visibility
     const uint32_t *wall = D.wall + (size_t)env * D.RW, *vis = D.vis + (size_t)env * D.RW;
     for (int i = lane; i < S.map_bytes; i += 32) {
         int rr = i / S.S - 1, cc = i - (rr + 1) * S.S - 1;
         bool inside = rr >= 0 && rr < D.R && cc >= 0 && cc < D.C;
-        uint8_t w = 1, v = 0;
+        unsigned w = CELL_BLOCK, v = 0;
         if (inside) {
             w = (wall[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
-            v = (vis[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
+            v = ((vis[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u) << 1;
         }
-        S.wallb[i] = w;
-        S.visb[i] = v;
+        S.wall0[i] = (uint8_t)w;
+        S.cell[i] = (uint8_t)(w | v);
     }
     if (lane < n_cams) {
         size_t o = (size_t)env * D.Kc + lane;
@@ -226,12 +252,12 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env
     __syncwarp();
 }
 
-// row bitmaps of the byte visibility map -> dst[RW]
+// row bitmaps of the visibility bits of the cell map -> dst[RW]
 __device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, int lane, uint32_t *dst) {
     for (int r = 0; r < D.R; ++r)
         for (int w = 0; w < D.W; ++w) {
             int c = w * 32 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, c < D.C && S.visb[(r + 1) * S.S + c + 1]);
+            unsigned m = __ballot_sync(0xffffffffu, c < D.C && (S.cell[(r + 1) * S.S + c + 1] & CELL_VIS));
             if (lane == 0) dst[r * D.W + w] = m;
         }
 }
@@ -254,7 +280,7 @@ __device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, int en
 }
 
 // HeistEnvironment.reset (environment.py:183-214): camera and guard headings persist.
-template <bool EXACT_ONLY>
+template <bool EXACT_ONLY, int LOG2S>
 __device__ __forceinline__ void reset_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
                                           int n_guards) {
     E.r = D.start_r; E.c = D.start_c; E.tick = 0;
@@ -269,11 +295,11 @@ __device__ __forceinline__ void reset_env(const Dev &D, const WarpCtx &S, int en
         refresh_asset(S, A, false);
     }
     __syncwarp();
-    compute_visibility<EXACT_ONLY>(D, S, lane, n_cams, n_cams + n_guards);
+    compute_visibility<EXACT_ONLY, LOG2S>(D, S, lane, n_cams, n_cams + n_guards);
 }
 
 // HeistEnvironment.step (environment.py:216-299).  All lanes carry the scalar env state redundantly.
-template <bool EXACT_ONLY>
+template <bool EXACT_ONLY, int LOG2S>
 __device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
                                         int n_guards, int action, double &reward_out) {
     if (E.flags & F_DONE) { reward_out = 0.0; return HEIST_ALREADY_DONE; }  // :232-233
@@ -282,7 +308,7 @@ __device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env,
     // 1. move (:239-246) -- blocked only by out-of-bounds (the ring) or WALL
     int nr = E.r + (action == 2) - (action == 1);
     int nc = E.c + (action == 4) - (action == 3);
-    if (!S.wallb[(nr + 1) * S.S + nc + 1]) { E.r = nr; E.c = nc; }
+    if (!(S.cell[(nr + 1) * S.S + nc + 1] & CELL_BLOCK)) { E.r = nr; E.c = nc; }
     // 2. cameras rotate (security.py:49-51), guards advance (security.py:145-159)
     if (lane < n_cams) {
         AssetW &A = S.asset[lane];
@@ -306,14 +332,14 @@ __device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env,
     }
     __syncwarp();
     // 3. visibility (:257-258)
-    compute_visibility<EXACT_ONLY>(D, S, lane, n_cams, n_cams + n_guards);
+    compute_visibility<EXACT_ONLY, LOG2S>(D, S, lane, n_cams, n_cams + n_guards);
     // 4. shaping (:261-269)
     int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
     reward = __dadd_rn(reward, __dmul_rn((double)(E.prev - curr), 0.1));
     E.prev = curr;
     if (curr <= 3 && E.init > 3) reward = __dadd_rn(reward, __dmul_rn(0.05, (double)(3 - curr)));
     // 5. detection (:273-281), vault (:284-288), timeout (:291-297)
-    if (S.visb[(E.r + 1) * S.S + E.c + 1]) {
+    if (S.cell[(E.r + 1) * S.S + E.c + 1] & CELL_VIS) {
         E.flags |= F_DETECTED | F_DONE;
         reward = __dadd_rn(reward, D.reward_detection);
         status = HEIST_DETECTED;
@@ -339,15 +365,16 @@ __device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env,
 }
 
 // T steps per launch; T = 1 with vis_traj = NULL is HeistEnvironment.step for the batch.
-template <bool EXACT_ONLY>
+// Warp slot -> env through D.slot2env (cost-balanced order built after every set_layout).
+template <bool EXACT_ONLY, int LOG2S>
 __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
             double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
             uint32_t *__restrict__ vis_traj) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * HEIST_WARPS_PER_CTA + warp;
-    if (env >= D.N) return;
+    const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
+    if (env < 0) return;
     WarpCtx S = carve_warp_ctx(smem + (size_t)warp * warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg), D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams, n_guards;
@@ -357,31 +384,72 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
         const size_t o = (size_t)t * D.N + env;
         int action = actions[o];
         double rw;
-        status = step_env<EXACT_ONLY>(D, S, env, lane, E, n_cams, n_guards, action, rw);
+        status = step_env<EXACT_ONLY, LOG2S>(D, S, env, lane, E, n_cams, n_guards, action, rw);
         if (lane == 0) {
             if (reward) reward[o] = (float)rw;
             if (reward64) reward64[o] = rw;
             if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
             if (status_out) status_out[o] = (uint8_t)status;
         }
-        if (autoreset && (E.flags & F_DONE)) reset_env<EXACT_ONLY>(D, S, env, lane, E, n_cams, n_guards);
+        if (autoreset && (E.flags & F_DONE)) reset_env<EXACT_ONLY, LOG2S>(D, S, env, lane, E, n_cams, n_guards);
         if (vis_traj) pack_vis(D, S, lane, vis_traj + o * D.RW);
     }
     store_env(D, S, env, lane, E, status, n_cams, n_guards);
 }
 
-template <bool EXACT_ONLY>
+template <bool EXACT_ONLY, int LOG2S>
 __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_reset(Dev D, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * HEIST_WARPS_PER_CTA + warp;
-    if (env >= D.N) return;
+    const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
+    if (env < 0) return;
     if (mask && !mask[env]) return;
     WarpCtx S = carve_warp_ctx(smem + (size_t)warp * warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg), D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams, n_guards;
     load_env(D, S, env, lane, E, n_cams, n_guards);
-    reset_env<EXACT_ONLY>(D, S, env, lane, E, n_cams, n_guards);
+    reset_env<EXACT_ONLY, LOG2S>(D, S, env, lane, E, n_cams, n_guards);
     store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cost-balanced warp-slot order.  A warp owns one env for a whole launch, and envs differ several-fold
+// in ray-march work, so slots are dealt in "snake" order over the envs sorted by cost: every CTA
+// (4 envs) gets one env from each quartile and all CTAs carry about the same work.
+// ---------------------------------------------------------------------------------------------
+#define ORDER_BINS 1024
+__global__ void __launch_bounds__(1024) k_build_order(Dev D, int n_ctas) {
+    __shared__ int hist[ORDER_BINS];
+    __shared__ int red[32];
+    __shared__ int s_max;
+    const int tid = threadIdx.x;
+    int m = 0;
+    for (int i = tid; i < D.N; i += 1024) m = max(m, D.cost[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5] = m;
+    hist[tid] = 0;
+    __syncthreads();
+    if (tid < 32) {
+        m = red[tid];
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (tid == 0) s_max = max(m, 1);
+    }
+    __syncthreads();
+    const float inv = (float)(ORDER_BINS - 1) / (float)s_max;
+    for (int i = tid; i < D.N; i += 1024) atomicAdd(&hist[min(ORDER_BINS - 1, (int)((float)D.cost[i] * inv))], 1);
+    __syncthreads();
+    // start[b] = number of envs in bins above b (descending cost); serial scan by one warp is fine
+    if (tid == 0) {
+        int acc = 0;
+        for (int b = ORDER_BINS - 1; b >= 0; --b) { int c = hist[b]; hist[b] = acc; acc += c; }
+    }
+    __syncthreads();
+    for (int i = tid; i < D.N; i += 1024) {
+        int b = min(ORDER_BINS - 1, (int)((float)D.cost[i] * inv));
+        int rank = atomicAdd(&hist[b], 1);
+        int rnd = rank / n_ctas, pos = rank - rnd * n_ctas;
+        if (rnd & 1) pos = n_ctas - 1 - pos;
+        D.slot2env[pos * HEIST_WARPS_PER_CTA + rnd] = i;
+    }
 }
