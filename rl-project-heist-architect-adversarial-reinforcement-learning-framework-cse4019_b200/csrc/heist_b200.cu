@@ -132,7 +132,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dx, ndx, sizeof(ndx)));
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
 
-    h->step_smem = HEIST_WARPS_PER_CTA * warp_ctx_bytes(d.R, d.C, d.Kc, d.Kg);
+    h->step_smem = sizeof(CtaCtl) + HEIST_WARPS_PER_CTA * warp_ctx_bytes(d.R, d.C, d.Kc, d.Kg);
     h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
 #define SET_SMEM(L)                                                                                                          \
     CUDA_TRY(cudaFuncSetAttribute(k_step_many<false, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \

@@ -1,4 +1,4 @@
-// heist_step.cuh -- per-step dynamics: reset, step, step_many (one warp per env).
+// heist_step.cuh -- per-step dynamics: reset, step, step_many (a warp owns an env; the CTA marches rays together).
 //
 // Reference: HeistEnvironment.reset / step (environment.py:183-299), Camera.update and
 // get_vision_cone_tiles (security.py:49-101), Guard.update and get_visible_tiles
@@ -46,7 +46,7 @@ struct WarpCtx {
     uint8_t *cell;    // [(R+2)*S] CELL_BLOCK | CELL_VIS
     uint8_t *wall0;   // [(R+2)*S] pristine copy with only CELL_BLOCK (source of the per-tick clear)
     AssetW *asset;    // [Kc+Kg] cameras first, then guards
-    int *pre;         // [Kc+Kg+1] prefix sums of (num_rays+1)
+    int *cpre;        // [Kc+Kg+1] prefix sums of 32-ray chunks per asset
     double *speed;    // [Kc] camera rotation speed
     int4 *g_i;        // [Kg] len, speed, range, num_rays
     int *g_idx;       // [Kg]
@@ -78,7 +78,7 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *p, int R, int C
     S.cell = p;             p += S.map_bytes;
     S.wall0 = p;            p += S.map_bytes;
     S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
-    S.pre = (int *)p;       p += (size_t)(Kc + Kg + 1) * sizeof(int);
+    S.cpre = (int *)p;      p += (size_t)(Kc + Kg + 1) * sizeof(int);
     S.g_idx = (int *)p;
     S.cell_sa = (unsigned)__cvta_generic_to_shared(S.cell);
     return S;
@@ -124,63 +124,101 @@ __device__ __noinline__ void ray_exact(const AssetW *asset, int seg, unsigned ce
     }
 }
 
-// DynamicVisibilityMap.update (visibility.py:31-65): all rays of all assets of the env, flattened
-// over the warp's lanes.
+// ---------------------------------------------------------------------------------------------
+// CTA-cooperative ray-march.  A warp owns one env's scalar state, but the rays of all envs of the CTA
+// are marched by all of its warps: every phase the owners publish how many 32-ray chunks their env
+// needs, and warps grab chunks from one shared counter until none are left.  (Envs differ several-
+// fold in rays per tick -- and a reset doubles a tick's work -- so a one-warp-per-env march leaves
+// most of the SM idle behind its slowest warp.)
+// ---------------------------------------------------------------------------------------------
+struct CtaCtl {
+    int next;                       // chunk counter of the current phase
+    int cnt[HEIST_WARPS_PER_CTA];   // chunks wanted by each env slot this phase (0: none)
+    int pad[3];
+};
+
+// March one 32-ray chunk: rays ri = ray0 + lane of asset A into the cell map at cell_sa.
 template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ void compute_visibility(const Dev &D, const WarpCtx &S, int lane, int n_cams, int n_assets) {
+__device__ __forceinline__ void march_chunk(const AssetW *asset, int k, int ray0, int lane, unsigned cell_sa, int stride,
+                                            double deg2rad) {
+    const AssetW &A = asset[k];
+    const int ri = ray0 + lane;
+    if (ri > A.num_rays) return;
+    if (EXACT_ONLY) { ray_exact(asset, k, cell_sa, stride, deg2rad, ri, 1); return; }
+    const int nsamp = A.nsamp;
+    const unsigned own = A.own;
+    // ---- fast path: direction (error < 1e-7) ----
+    const double a = fma((double)ri, A.step, A.base);                // degrees
+    const double t = fma(a, 1.0 / 90.0, RINT_MAGIC);
+    const int q = __double2loint(t);                                 // nearest quadrant
+    const float r = (float)(fma(t - RINT_MAGIC, -90.0, a) * 0.017453292519943295);  // |r| <= pi/4 (+eps)
+    const float r2 = r * r;
+    float sn = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
+    float cs = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
+                    fmaf(r2, -0.5f, 1.0f));
+    float c_a = (q & 1) ? sn : cs;   // cos(q*90 + r)
+    float s_a = (q & 1) ? cs : sn;   // sin(q*90 + r)
+    if ((q + 1) & 2) c_a = -c_a;
+    if (q & 2) s_a = -s_a;
+    const float scale = (A.shift == 23) ? 8388608.0f : 16777216.0f;
+    const int sx = __float2int_rn(c_a * scale);    // dx =  cos
+    const int sy = __float2int_rn(-s_a * scale);   // dy = -sin
+    // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
+    int x = A.x0, y = A.y0;
+#pragma unroll 2
+    for (int j = 1; j <= nsamp; ++j) {
+        x += sx; y += sy;
+        if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {
+            ray_exact(asset, k, cell_sa, stride, deg2rad, ri, j);
+            break;
+        }
+        unsigned off;
+        if (LOG2S) off = (((unsigned)y >> (FX_BITS - LOG2S)) & (~0u << LOG2S)) | ((unsigned)x >> FX_BITS);
+        else off = (unsigned)((y >> FX_BITS) * stride + (x >> FX_BITS));
+        if (lds_u8(cell_sa + off) == CELL_BLOCK) break;  // blocking cells are never marked, so == suffices
+        if (off != own) sts_u8(cell_sa + off, CELL_VIS);
+    }
+}
+
+// One cooperative phase: all warps of the CTA drain the chunk queue.  Must be entered by every warp
+// after a __syncthreads() that follows the owners' writes to ctl->cnt / ctl->next / their cell maps.
+template <bool EXACT_ONLY, int LOG2S>
+__device__ __forceinline__ void march_phase(const Dev &D, unsigned char *env_base, size_t ctx_bytes, CtaCtl *ctl, int lane) {
+    int pre[HEIST_WARPS_PER_CTA + 1];
+    pre[0] = 0;
+#pragma unroll
+    for (int e = 0; e < HEIST_WARPS_PER_CTA; ++e) pre[e + 1] = pre[e] + ctl->cnt[e];
+    const int total = pre[HEIST_WARPS_PER_CTA];
+    for (;;) {
+        int g = 0;
+        if (lane == 0) g = atomicAdd(&ctl->next, 1);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if (g >= total) break;
+        int e = 0;
+#pragma unroll
+        for (int i = 1; i < HEIST_WARPS_PER_CTA; ++i) e += (g >= pre[i]);
+        int c = g;
+#pragma unroll
+        for (int i = 1; i < HEIST_WARPS_PER_CTA; ++i) if (e == i) c = g - pre[i];
+        const WarpCtx Se = carve_warp_ctx(env_base + (size_t)e * ctx_bytes, D.R, D.C, D.Kc, D.Kg);
+        int k = 0;
+        while (c >= Se.cpre[k + 1]) ++k;
+        march_chunk<EXACT_ONLY, LOG2S>(Se.asset, k, (c - Se.cpre[k]) * 32, lane, Se.cell_sa, Se.S, D.deg2rad);
+    }
+}
+
+// Owner-side preparation of a visibility rebuild (DynamicVisibilityMap.update, visibility.py:31-65):
+// clear the env's cell map and publish the chunk count.
+__device__ __forceinline__ void begin_visibility(const WarpCtx &S, CtaCtl *ctl, int warp, int lane, int n_assets) {
     for (int i = lane * 16; i < S.map_bytes; i += 512)
         *reinterpret_cast<int4 *>(S.cell + i) = *reinterpret_cast<const int4 *>(S.wall0 + i);
-    __syncwarp();
-    const int total = S.pre[n_assets];
-    const unsigned cell_sa = S.cell_sa;
-    const int stride = S.S;
-    int seg = -1, seg_lo = 0, seg_hi = 0;
-    double base = 0.0, step = 0.0;
-    int x0 = 0, y0 = 0, nsamp = 0;
-    unsigned own = ~0u;
-    float scale = 0.0f;
-    for (int i = lane; i < total; i += 32) {
-        if (i >= seg_hi) {
-            do { ++seg; seg_lo = seg_hi; seg_hi = S.pre[seg + 1]; } while (i >= seg_hi);
-            const AssetW &A = S.asset[seg];
-            base = A.base; step = A.step; x0 = A.x0; y0 = A.y0; own = A.own; nsamp = A.nsamp;
-            scale = (A.shift == 23) ? 8388608.0f : 16777216.0f;
-        }
-        const int ri = i - seg_lo;
-        if (EXACT_ONLY) { ray_exact(S.asset, seg, cell_sa, stride, D.deg2rad, ri, 1); continue; }
-        // ---- fast path: direction (error < 1e-7) ----
-        const double a = fma((double)ri, step, base);                   // degrees
-        const double t = fma(a, 1.0 / 90.0, RINT_MAGIC);
-        const int q = __double2loint(t);                                // nearest quadrant
-        const float r = (float)(fma(t - RINT_MAGIC, -90.0, a) * 0.017453292519943295);  // |r| <= pi/4 (+eps)
-        const float r2 = r * r;
-        float sn = fmaf(r * r2, fmaf(r2, fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f), -1.6666654611e-1f), r);
-        float cs = fmaf(r2 * r2, fmaf(r2, fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f), 4.166664568298827e-2f),
-                        fmaf(r2, -0.5f, 1.0f));
-        float c_a = (q & 1) ? sn : cs;   // cos(q*90 + r)
-        float s_a = (q & 1) ? cs : sn;   // sin(q*90 + r)
-        if ((q + 1) & 2) c_a = -c_a;
-        if (q & 2) s_a = -s_a;
-        const int sx = __float2int_rn(c_a * scale);    // dx =  cos
-        const int sy = __float2int_rn(-s_a * scale);   // dy = -sin
-        // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
-        int x = x0, y = y0;
-#pragma unroll 2
-        for (int j = 1; j <= nsamp; ++j) {
-            x += sx; y += sy;
-            if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {
-                ray_exact(S.asset, seg, cell_sa, stride, D.deg2rad, ri, j);
-                break;
-            }
-            unsigned off;
-            if (LOG2S) off = (((unsigned)y >> (FX_BITS - LOG2S)) & (~0u << LOG2S)) | ((unsigned)x >> FX_BITS);
-            else off = (unsigned)((y >> FX_BITS) * stride + (x >> FX_BITS));
-            if (lds_u8(cell_sa + off) == CELL_BLOCK) break;  // blocking cells are never marked, so == suffices
-            if (off != own) sts_u8(cell_sa + off, CELL_VIS);
-        }
-    }
-    __syncwarp();
-    // guard's own tile is always dangerous (visibility.py:59)
+    if (lane == 0) ctl->cnt[warp] = S.cpre[n_assets];
+}
+
+// ... and its owner-side end, after the cooperative march: the guards' own tiles are always lit
+// (visibility.py:59).  Done last because a guard may stand on a WALL tile, which must keep blocking
+// sight (the march tests cell == CELL_BLOCK).
+__device__ __forceinline__ void end_visibility(const WarpCtx &S, int lane, int n_cams, int n_assets) {
     if (lane >= n_cams && lane < n_assets) {
         const AssetW &A = S.asset[lane];
         S.cell[(A.row + 1) * S.S + A.col + 1] |= CELL_VIS;
@@ -246,8 +284,8 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env
     __syncwarp();
     if (lane == 0) {
         int acc = 0;
-        S.pre[0] = 0;
-        for (int k = 0; k < n_cams + n_guards; ++k) { acc += S.asset[k].num_rays + 1; S.pre[k + 1] = acc; }
+        S.cpre[0] = 0;
+        for (int k = 0; k < n_cams + n_guards; ++k) { acc += (S.asset[k].num_rays + 1 + 31) >> 5; S.cpre[k + 1] = acc; }
     }
     __syncwarp();
 }
@@ -279,10 +317,10 @@ __device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, int en
     pack_vis(D, S, lane, D.vis + (size_t)env * D.RW);
 }
 
-// HeistEnvironment.reset (environment.py:183-214): camera and guard headings persist.
-template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ void reset_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
-                                          int n_guards) {
+// HeistEnvironment.reset (environment.py:183-214), owner part: solver to start, guards to waypoint 0;
+// camera and guard headings persist.  The visibility rebuild follows as a cooperative phase.
+__device__ __forceinline__ void reset_state(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
+                                            int n_guards) {
     E.r = D.start_r; E.c = D.start_c; E.tick = 0;
     E.flags = 0;
     E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
@@ -295,21 +333,15 @@ __device__ __forceinline__ void reset_env(const Dev &D, const WarpCtx &S, int en
         refresh_asset(S, A, false);
     }
     __syncwarp();
-    compute_visibility<EXACT_ONLY, LOG2S>(D, S, lane, n_cams, n_cams + n_guards);
 }
 
-// HeistEnvironment.step (environment.py:216-299).  All lanes carry the scalar env state redundantly.
-template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
-                                        int n_guards, int action, double &reward_out) {
-    if (E.flags & F_DONE) { reward_out = 0.0; return HEIST_ALREADY_DONE; }  // :232-233
-    double reward = D.reward_step;                                           // :235
-    int status = HEIST_RUNNING;
-    // 1. move (:239-246) -- blocked only by out-of-bounds (the ring) or WALL
+// HeistEnvironment.step (environment.py:216-299), owner part before the visibility rebuild:
+// move (:239-246), cameras rotate (security.py:49-51), guards advance (security.py:145-159).
+__device__ __forceinline__ void step_begin(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int n_cams,
+                                           int n_guards, int action) {
     int nr = E.r + (action == 2) - (action == 1);
     int nc = E.c + (action == 4) - (action == 3);
-    if (!(S.cell[(nr + 1) * S.S + nc + 1] & CELL_BLOCK)) { E.r = nr; E.c = nc; }
-    // 2. cameras rotate (security.py:49-51), guards advance (security.py:145-159)
+    if (!(S.cell[(nr + 1) * S.S + nc + 1] & CELL_BLOCK)) { E.r = nr; E.c = nc; }  // ring = out of bounds
     if (lane < n_cams) {
         AssetW &A = S.asset[lane];
         A.heading = py_mod360(__dadd_rn(A.heading, S.speed[lane]));
@@ -331,14 +363,16 @@ __device__ __forceinline__ int step_env(const Dev &D, const WarpCtx &S, int env,
         }
     }
     __syncwarp();
-    // 3. visibility (:257-258)
-    compute_visibility<EXACT_ONLY, LOG2S>(D, S, lane, n_cams, n_cams + n_guards);
-    // 4. shaping (:261-269)
+}
+
+// ... and after it: shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297).
+__device__ __forceinline__ int step_finish(const Dev &D, const WarpCtx &S, EnvRegs &E, double &reward_out) {
+    double reward = D.reward_step;  // :235
+    int status = HEIST_RUNNING;
     int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
     reward = __dadd_rn(reward, __dmul_rn((double)(E.prev - curr), 0.1));
     E.prev = curr;
     if (curr <= 3 && E.init > 3) reward = __dadd_rn(reward, __dmul_rn(0.05, (double)(3 - curr)));
-    // 5. detection (:273-281), vault (:284-288), timeout (:291-297)
     if (S.cell[(E.r + 1) * S.S + E.c + 1] & CELL_VIS) {
         E.flags |= F_DETECTED | F_DONE;
         reward = __dadd_rn(reward, D.reward_detection);
@@ -373,28 +407,59 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
             uint32_t *__restrict__ vis_traj) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
+    unsigned char *env_base = smem + sizeof(CtaCtl);
+    const size_t ctx_bytes = warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
-    if (env < 0) return;
-    WarpCtx S = carve_warp_ctx(smem + (size_t)warp * warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg), D.R, D.C, D.Kc, D.Kg);
+    const bool have = env >= 0;
+    const WarpCtx S = carve_warp_ctx(env_base + (size_t)warp * ctx_bytes, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
-    int n_cams, n_guards;
-    load_env(D, S, env, lane, E, n_cams, n_guards);
+    E.flags = F_DONE;
+    int n_cams = 0, n_guards = 0;
+    if (have) load_env(D, S, env, lane, E, n_cams, n_guards);
+    const int n_assets = n_cams + n_guards;
     int status = HEIST_RUNNING;
     for (int t = 0; t < T; ++t) {
-        const size_t o = (size_t)t * D.N + env;
-        int action = actions[o];
-        double rw;
-        status = step_env<EXACT_ONLY, LOG2S>(D, S, env, lane, E, n_cams, n_guards, action, rw);
-        if (lane == 0) {
+        const size_t o = (size_t)t * D.N + (have ? env : 0);
+        // ---- owner: early-out / move / rotate / patrol, then publish the visibility rebuild ----
+        const bool live = have && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
+        if (live) {
+            step_begin(D, S, env, lane, E, n_cams, n_guards, actions[o]);
+            begin_visibility(S, ctl, warp, lane, n_assets);
+        } else if (lane == 0) ctl->cnt[warp] = 0;
+        if (threadIdx.x == 0) ctl->next = 0;
+        __syncthreads();
+        march_phase<EXACT_ONLY, LOG2S>(D, env_base, ctx_bytes, ctl, lane);
+        __syncthreads();
+        // ---- owner: rewards, termination, outputs ----
+        double rw = 0.0;
+        status = HEIST_ALREADY_DONE;
+        if (live) {
+            end_visibility(S, lane, n_cams, n_assets);
+            status = step_finish(D, S, E, rw);
+        }
+        if (have && lane == 0) {
             if (reward) reward[o] = (float)rw;
             if (reward64) reward64[o] = rw;
             if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
             if (status_out) status_out[o] = (uint8_t)status;
         }
-        if (autoreset && (E.flags & F_DONE)) reset_env<EXACT_ONLY, LOG2S>(D, S, env, lane, E, n_cams, n_guards);
-        if (vis_traj) pack_vis(D, S, lane, vis_traj + o * D.RW);
+        // ---- auto-reset (the trainer's `if done: reset()`), second cooperative phase if anyone needs it ----
+        const bool need_reset = autoreset && have && (E.flags & F_DONE);
+        if (__syncthreads_or(need_reset)) {
+            if (need_reset) {
+                reset_state(D, S, env, lane, E, n_cams, n_guards);
+                begin_visibility(S, ctl, warp, lane, n_assets);
+            } else if (lane == 0) ctl->cnt[warp] = 0;
+            if (threadIdx.x == 0) ctl->next = 0;
+            __syncthreads();
+            march_phase<EXACT_ONLY, LOG2S>(D, env_base, ctx_bytes, ctl, lane);
+            __syncthreads();
+            if (need_reset) end_visibility(S, lane, n_cams, n_assets);
+        }
+        if (vis_traj && have) pack_vis(D, S, lane, vis_traj + o * D.RW);
     }
-    store_env(D, S, env, lane, E, status, n_cams, n_guards);
+    if (have) store_env(D, S, env, lane, E, status, n_cams, n_guards);
 }
 
 template <bool EXACT_ONLY, int LOG2S>
@@ -402,15 +467,27 @@ __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_reset(Dev D, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
+    unsigned char *env_base = smem + sizeof(CtaCtl);
+    const size_t ctx_bytes = warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
-    if (env < 0) return;
-    if (mask && !mask[env]) return;
-    WarpCtx S = carve_warp_ctx(smem + (size_t)warp * warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg), D.R, D.C, D.Kc, D.Kg);
+    const bool have = env >= 0 && (!mask || mask[env]);
+    const WarpCtx S = carve_warp_ctx(env_base + (size_t)warp * ctx_bytes, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
-    int n_cams, n_guards;
-    load_env(D, S, env, lane, E, n_cams, n_guards);
-    reset_env<EXACT_ONLY, LOG2S>(D, S, env, lane, E, n_cams, n_guards);
-    store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
+    int n_cams = 0, n_guards = 0;
+    if (have) {
+        load_env(D, S, env, lane, E, n_cams, n_guards);
+        reset_state(D, S, env, lane, E, n_cams, n_guards);
+        begin_visibility(S, ctl, warp, lane, n_cams + n_guards);
+    } else if (lane == 0) ctl->cnt[warp] = 0;
+    if (threadIdx.x == 0) ctl->next = 0;
+    __syncthreads();
+    march_phase<EXACT_ONLY, LOG2S>(D, env_base, ctx_bytes, ctl, lane);
+    __syncthreads();
+    if (have) {
+        end_visibility(S, lane, n_cams, n_cams + n_guards);
+        store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
