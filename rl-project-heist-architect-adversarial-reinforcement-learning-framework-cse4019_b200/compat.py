@@ -59,8 +59,8 @@ class HeistEnvironment:
     ACTION_NAMES = {0: "WAIT", 1: "UP", 2: "DOWN", 3: "LEFT", 4: "RIGHT"}
     NUM_SOLVER_ACTIONS = 5
 
-    def __init__(self, config: Optional[EnvironmentConfig] = None, device=None, max_walls=512, max_cams=32,
-                 max_guards=32, max_path=64):
+    def __init__(self, config: Optional[EnvironmentConfig] = None, device=None, max_walls=512, max_cams=24,
+                 max_guards=8, max_path=64):
         src = config or EnvironmentConfig()
         # accept the reference's own dataclass instance as well
         self.config = src if isinstance(src, EnvironmentConfig) else EnvironmentConfig(

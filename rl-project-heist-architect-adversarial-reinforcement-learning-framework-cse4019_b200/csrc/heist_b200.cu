@@ -85,9 +85,10 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     if (p.start_row < 0 || p.start_row >= p.grid_rows || p.start_col < 0 || p.start_col >= p.grid_cols ||
         p.vault_row < 0 || p.vault_row >= p.grid_rows || p.vault_col < 0 || p.vault_col >= p.grid_cols)
         return fail(-4, "heist_create: start/vault outside the grid");
-    if (p.max_walls < 0 || p.max_cams < 0 || p.max_cams > 32 || p.max_guards < 0 || p.max_guards > 32 ||
-        p.max_path < 1 || p.max_path > 255)
-        return fail(-5, "heist_create: capacities out of range (max_cams, max_guards <= 32; 1 <= max_path <= 255)");
+    if (p.max_walls < 0 || p.max_cams < 0 || p.max_guards < 0 || p.max_cams + p.max_guards > 32 || p.max_path < 1 ||
+        p.max_path > 255)
+        return fail(-5, "heist_create: capacities out of range (max_cams + max_guards <= 32; 1 <= max_path <= 255)");
+    static_assert(HEIST_WARPS_PER_CTA == 4, "pend[] packs the env slot in 2 bits");
     if (p.max_steps < 1) return fail(-6, "heist_create: max_steps must be >= 1");
     CUDA_TRY(cudaSetDevice(device));
 

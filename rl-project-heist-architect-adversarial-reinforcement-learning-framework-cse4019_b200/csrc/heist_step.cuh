@@ -46,7 +46,7 @@ struct WarpCtx {
     uint8_t *cell;    // [(R+2)*S] CELL_BLOCK | CELL_VIS
     uint8_t *wall0;   // [(R+2)*S] pristine copy with only CELL_BLOCK (source of the per-tick clear)
     AssetW *asset;    // [Kc+Kg] cameras first, then guards
-    int *cpre;        // [Kc+Kg+1] prefix sums of 32-ray chunks per asset
+    int *rpre;        // [Kc+Kg+1] prefix sums of rays (num_rays+1) per asset
     double *speed;    // [Kc] camera rotation speed
     int4 *g_i;        // [Kg] len, speed, range, num_rays
     int *g_idx;       // [Kg]
@@ -78,7 +78,7 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *p, int R, int C
     S.cell = p;             p += S.map_bytes;
     S.wall0 = p;            p += S.map_bytes;
     S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
-    S.cpre = (int *)p;      p += (size_t)(Kc + Kg + 1) * sizeof(int);
+    S.rpre = (int *)p;      p += (size_t)(Kc + Kg + 1) * sizeof(int);
     S.g_idx = (int *)p;
     S.cell_sa = (unsigned)__cvta_generic_to_shared(S.cell);
     return S;
@@ -131,20 +131,43 @@ __device__ __noinline__ void ray_exact(const AssetW *asset, int seg, unsigned ce
 // fold in rays per tick -- and a reset doubles a tick's work -- so a one-warp-per-env march leaves
 // most of the SM idle behind its slowest warp.)
 // ---------------------------------------------------------------------------------------------
+#define PEND_CAP 480
 struct CtaCtl {
     int next;                       // chunk counter of the current phase
-    int cnt[HEIST_WARPS_PER_CTA];   // chunks wanted by each env slot this phase (0: none)
-    int pad[3];
+    int pend_n;                     // rays handed to the exact path this phase
+    int cnt[HEIST_WARPS_PER_CTA];   // 32-ray chunks wanted by each env slot this phase (0: none)
+    int pad[2];
+    unsigned pend[PEND_CAP];        // slot:2 | asset:6 | sample j:8 | ray:16
 };
 
-// March one 32-ray chunk: rays ri = ray0 + lane of asset A into the cell map at cell_sa.
+// One ray sample on the fast path.  Returns false when the ray ends (blocked, or handed to the exact path).
+#define HEIST_SAMPLE(CHECK_OWN)                                                                                      \
+    x += sx; y += sy;                                                                                                \
+    if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {      \
+        int slot = (j < 256) ? atomicAdd(&ctl->pend_n, 1) : PEND_CAP;                                                \
+        if (slot < PEND_CAP) ctl->pend[slot] = ((unsigned)e << 30) | ((unsigned)k << 24) | ((unsigned)j << 16) | (unsigned)ri; \
+        else ray_exact(asset, k, cell_sa, stride, deg2rad, ri, j);                                                   \
+        break;                                                                                                       \
+    }                                                                                                                \
+    {                                                                                                                \
+        unsigned off;                                                                                                \
+        if (LOG2S) off = (((unsigned)y >> (FX_BITS - LOG2S)) & (~0u << LOG2S)) | ((unsigned)x >> FX_BITS);           \
+        else off = (unsigned)((y >> FX_BITS) * stride + (x >> FX_BITS));                                             \
+        if (lds_u8(cell_sa + off) == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */        \
+        if (!(CHECK_OWN) || off != own) sts_u8(cell_sa + off, CELL_VIS);                                             \
+    }
+
+// March flattened rays [f0, f0+32) of env slot e (asset table `asset`, ray prefix sums `pre`).
 template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ void march_chunk(const AssetW *asset, int k, int ray0, int lane, unsigned cell_sa, int stride,
-                                            double deg2rad) {
-    const AssetW &A = asset[k];
-    const int ri = ray0 + lane;
-    if (ri > A.num_rays) return;
+__device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *asset, const int *pre, int n_assets, int f0,
+                                            int lane, unsigned cell_sa, int stride, double deg2rad) {
+    const int f = f0 + lane;
+    if (f >= pre[n_assets]) return;
+    int k = 0;
+    while (f >= pre[k + 1]) ++k;
+    const int ri = f - pre[k];
     if (EXACT_ONLY) { ray_exact(asset, k, cell_sa, stride, deg2rad, ri, 1); return; }
+    const AssetW &A = asset[k];
     const int nsamp = A.nsamp;
     const unsigned own = A.own;
     // ---- fast path: direction (error < 1e-7) ----
@@ -165,25 +188,22 @@ __device__ __forceinline__ void march_chunk(const AssetW *asset, int k, int ray0
     const int sy = __float2int_rn(-s_a * scale);   // dy = -sin
     // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
     int x = A.x0, y = A.y0;
+    int j = 1;
+    do {  // only a camera's first sample (dist 0.5) can round to the camera's own tile (security.py:93)
+        if (nsamp < 1) break;
+        HEIST_SAMPLE(true)
 #pragma unroll 2
-    for (int j = 1; j <= nsamp; ++j) {
-        x += sx; y += sy;
-        if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {
-            ray_exact(asset, k, cell_sa, stride, deg2rad, ri, j);
-            break;
-        }
-        unsigned off;
-        if (LOG2S) off = (((unsigned)y >> (FX_BITS - LOG2S)) & (~0u << LOG2S)) | ((unsigned)x >> FX_BITS);
-        else off = (unsigned)((y >> FX_BITS) * stride + (x >> FX_BITS));
-        if (lds_u8(cell_sa + off) == CELL_BLOCK) break;  // blocking cells are never marked, so == suffices
-        if (off != own) sts_u8(cell_sa + off, CELL_VIS);
-    }
+        for (j = 2; j <= nsamp; ++j) { HEIST_SAMPLE(false) }
+    } while (0);
 }
 
-// One cooperative phase: all warps of the CTA drain the chunk queue.  Must be entered by every warp
-// after a __syncthreads() that follows the owners' writes to ctl->cnt / ctl->next / their cell maps.
+// One cooperative phase: all warps of the CTA drain the chunk queue, then (after a barrier) the
+// rays that were handed to the exact path, 128 at a time instead of one or two lanes at a time.
+// Must be entered by every warp after a __syncthreads() that follows the owners' writes to ctl / cell maps;
+// ends with a __syncthreads().
 template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ void march_phase(const Dev &D, unsigned char *env_base, size_t ctx_bytes, CtaCtl *ctl, int lane) {
+__device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, int warp, size_t ctx_bytes, CtaCtl *ctl, int lane,
+                                            const int *n_assets_of) {
     int pre[HEIST_WARPS_PER_CTA + 1];
     pre[0] = 0;
 #pragma unroll
@@ -200,10 +220,23 @@ __device__ __forceinline__ void march_phase(const Dev &D, unsigned char *env_bas
         int c = g;
 #pragma unroll
         for (int i = 1; i < HEIST_WARPS_PER_CTA; ++i) if (e == i) c = g - pre[i];
-        const WarpCtx Se = carve_warp_ctx(env_base + (size_t)e * ctx_bytes, D.R, D.C, D.Kc, D.Kg);
-        int k = 0;
-        while (c >= Se.cpre[k + 1]) ++k;
-        march_chunk<EXACT_ONLY, LOG2S>(Se.asset, k, (c - Se.cpre[k]) * 32, lane, Se.cell_sa, Se.S, D.deg2rad);
+        // every slot's context has the same layout: shift this warp's own pointers by whole contexts
+        const int delta = (e - warp) * (int)ctx_bytes;
+        const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
+        const int *rpre = reinterpret_cast<const int *>(reinterpret_cast<const unsigned char *>(S.rpre) + delta);
+        march_chunk<EXACT_ONLY, LOG2S>(ctl, e, asset, rpre, n_assets_of[e], c * 32, lane, S.cell_sa + delta, S.S, D.deg2rad);
+    }
+    __syncthreads();
+    if (!EXACT_ONLY) {
+        const int P = min(ctl->pend_n, PEND_CAP);
+        for (int i = threadIdx.x; i < P; i += HEIST_WARPS_PER_CTA * 32) {
+            const unsigned p = ctl->pend[i];
+            const int e = p >> 30, k = (p >> 24) & 63, j = (p >> 16) & 255, ri = p & 0xffff;
+            const int delta = (e - warp) * (int)ctx_bytes;
+            const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
+            ray_exact(asset, k, S.cell_sa + delta, S.S, D.deg2rad, ri, j);
+        }
+        if (P > 0) __syncthreads();  // P is CTA-uniform (read after the barrier above)
     }
 }
 
@@ -212,7 +245,7 @@ __device__ __forceinline__ void march_phase(const Dev &D, unsigned char *env_bas
 __device__ __forceinline__ void begin_visibility(const WarpCtx &S, CtaCtl *ctl, int warp, int lane, int n_assets) {
     for (int i = lane * 16; i < S.map_bytes; i += 512)
         *reinterpret_cast<int4 *>(S.cell + i) = *reinterpret_cast<const int4 *>(S.wall0 + i);
-    if (lane == 0) ctl->cnt[warp] = S.cpre[n_assets];
+    if (lane == 0) ctl->cnt[warp] = (S.rpre[n_assets] + 31) >> 5;
 }
 
 // ... and its owner-side end, after the cooperative march: the guards' own tiles are always lit
@@ -284,8 +317,8 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env
     __syncwarp();
     if (lane == 0) {
         int acc = 0;
-        S.cpre[0] = 0;
-        for (int k = 0; k < n_cams + n_guards; ++k) { acc += (S.asset[k].num_rays + 1 + 31) >> 5; S.cpre[k + 1] = acc; }
+        S.rpre[0] = 0;
+        for (int k = 0; k < n_cams + n_guards; ++k) { acc += S.asset[k].num_rays + 1; S.rpre[k + 1] = acc; }
     }
     __syncwarp();
 }
@@ -418,6 +451,8 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     int n_cams = 0, n_guards = 0;
     if (have) load_env(D, S, env, lane, E, n_cams, n_guards);
     const int n_assets = n_cams + n_guards;
+    __shared__ int ctl_nassets[HEIST_WARPS_PER_CTA];
+    if (lane == 0) ctl_nassets[warp] = n_assets;
     int status = HEIST_RUNNING;
     for (int t = 0; t < T; ++t) {
         const size_t o = (size_t)t * D.N + (have ? env : 0);
@@ -427,10 +462,9 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
             step_begin(D, S, env, lane, E, n_cams, n_guards, actions[o]);
             begin_visibility(S, ctl, warp, lane, n_assets);
         } else if (lane == 0) ctl->cnt[warp] = 0;
-        if (threadIdx.x == 0) ctl->next = 0;
+        if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
         __syncthreads();
-        march_phase<EXACT_ONLY, LOG2S>(D, env_base, ctx_bytes, ctl, lane);
-        __syncthreads();
+        march_phase<EXACT_ONLY, LOG2S>(D, S, warp, ctx_bytes, ctl, lane, ctl_nassets);
         // ---- owner: rewards, termination, outputs ----
         double rw = 0.0;
         status = HEIST_ALREADY_DONE;
@@ -451,10 +485,9 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
                 reset_state(D, S, env, lane, E, n_cams, n_guards);
                 begin_visibility(S, ctl, warp, lane, n_assets);
             } else if (lane == 0) ctl->cnt[warp] = 0;
-            if (threadIdx.x == 0) ctl->next = 0;
+            if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
             __syncthreads();
-            march_phase<EXACT_ONLY, LOG2S>(D, env_base, ctx_bytes, ctl, lane);
-            __syncthreads();
+            march_phase<EXACT_ONLY, LOG2S>(D, S, warp, ctx_bytes, ctl, lane, ctl_nassets);
             if (need_reset) end_visibility(S, lane, n_cams, n_assets);
         }
         if (vis_traj && have) pack_vis(D, S, lane, vis_traj + o * D.RW);
@@ -480,10 +513,11 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
         reset_state(D, S, env, lane, E, n_cams, n_guards);
         begin_visibility(S, ctl, warp, lane, n_cams + n_guards);
     } else if (lane == 0) ctl->cnt[warp] = 0;
-    if (threadIdx.x == 0) ctl->next = 0;
+    __shared__ int ctl_nassets[HEIST_WARPS_PER_CTA];
+    if (lane == 0) ctl_nassets[warp] = n_cams + n_guards;
+    if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
     __syncthreads();
-    march_phase<EXACT_ONLY, LOG2S>(D, env_base, ctx_bytes, ctl, lane);
-    __syncthreads();
+    march_phase<EXACT_ONLY, LOG2S>(D, S, warp, ctx_bytes, ctl, lane, ctl_nassets);
     if (have) {
         end_visibility(S, lane, n_cams, n_cams + n_guards);
         store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
