@@ -42,7 +42,6 @@ struct HeistHandle {
     Dev d;
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
-    int log2s;       // row-stride class of the shared-memory cell map (template selector)
     int exact_only;  // heist_set_mode: 1 = every sample through the fp64 reference arithmetic
     void *allocs[64];
     int n_allocs;
@@ -133,16 +132,12 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dx, ndx, sizeof(ndx)));
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
 
-    h->step_smem = sizeof(CtaCtl) + HEIST_WARPS_PER_CTA * warp_ctx_bytes(d.R, d.C, d.Kc, d.Kg);
+    h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
-#define SET_SMEM(L)                                                                                                          \
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<false, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<true, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));  \
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<false, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));     \
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<true, L>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    SET_SMEM(0) SET_SMEM(5) SET_SMEM(6)
-#undef SET_SMEM
-    h->log2s = map_log2s(d.C);
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
     CUDA_TRY(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
 
     // HeistEnvironment.__init__: bordered grid with START/VAULT, solver at start (environment.py:62-96)
@@ -206,10 +201,8 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     CUDA_TRY(cudaSetDevice(h->device));
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
     cudaStream_t s = (cudaStream_t)stream;
-#define GO(E, L) k_reset<E, L><<<grid, block, h->step_smem, s>>>(h->d, mask)
-    if (h->exact_only) { if (h->log2s == 5) GO(true, 5); else if (h->log2s == 6) GO(true, 6); else GO(true, 0); }
-    else { if (h->log2s == 5) GO(false, 5); else if (h->log2s == 6) GO(false, 6); else GO(false, 0); }
-#undef GO
+    if (h->exact_only) k_reset<true><<<grid, block, h->step_smem, s>>>(h->d, mask);
+    else k_reset<false><<<grid, block, h->step_smem, s>>>(h->d, mask);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -217,10 +210,10 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
 static void launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
                         uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
-#define GO(E, L) k_step_many<E, L><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
-    if (h->exact_only) { if (h->log2s == 5) GO(true, 5); else if (h->log2s == 6) GO(true, 6); else GO(true, 0); }
-    else { if (h->log2s == 5) GO(false, 5); else if (h->log2s == 6) GO(false, 6); else GO(false, 0); }
-#undef GO
+    if (h->exact_only)
+        k_step_many<true><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
+    else
+        k_step_many<false><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
 }
 
 extern "C" int heist_set_mode(HeistHandle *h, int exact_only) {

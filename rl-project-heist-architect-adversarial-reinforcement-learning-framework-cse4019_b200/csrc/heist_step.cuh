@@ -1,4 +1,5 @@
-// heist_step.cuh -- per-step dynamics: reset, step, step_many (a warp owns an env; the CTA marches rays together).
+// heist_step.cuh -- per-step dynamics: reset, step, step_many.
+// A warp owns one env's scalar state; the 4 warps of a CTA march the rays of their 4 envs together.
 //
 // Reference: HeistEnvironment.reset / step (environment.py:183-299), Camera.update and
 // get_vision_cone_tiles (security.py:49-101), Guard.update and get_visible_tiles
@@ -6,13 +7,14 @@
 //
 // Visibility is the reference's sample-point ray-march, not a geometric rasterisation.  Every
 // sample is decided by a FILTERED-EXACT scheme:
-//   fast path  - ray direction from an fp32 polynomial sincos of the (fp64-reduced) angle, sample
-//                positions as 8.24 fixed-point integers x_j = x_0 + j*sx.  Its error is bounded by
-//                ~1.3e-6 tile; a sample whose fractional part lies within 2^-16 tile of a rounding
-//                boundary is declared ambiguous;
+//   fast path  - ray direction from an fp32 polynomial sincos of the (fp64-reduced) angle (error
+//                < 1e-7), sample positions as 8.24 fixed-point integers x_j = x_0 + j*sx (total
+//                error < 1.3e-6 tile); a sample whose fractional part lies within 2^-16 tile of a
+//                rounding boundary is declared ambiguous;
 //   exact path - from the first ambiguous sample on, the ray is re-evaluated exactly as the reference
 //                does it: fp64 cos/sin of radians(angle) (host-libm table at multiples of 30 degrees),
-//                separate fp64 multiply and add, round-half-even.
+//                separate fp64 multiply and add, round-half-even.  Such rays are queued and processed
+//                128 at a time after the fast pass (marks are ORs, so the order does not matter).
 // Unambiguous samples round to the same tile in both paths, so the result is bit-identical to the
 // all-fp64 evaluation (heist_set_mode(h, 1) forces the exact path everywhere; tests compare the two).
 #pragma once
@@ -20,19 +22,20 @@
 
 #define FX_BITS 24
 #define FX_ONE (1 << FX_BITS)
-#define FX_MASK (FX_ONE - 1)
 #define FX_EPS 256  // 2^-16 tile
 
 #define CELL_BLOCK 1u  // WALL, or the out-of-bounds ring around the grid
 #define CELL_VIS 2u    // under surveillance this tick
 
-// Per-asset (camera or guard) working record in shared memory.
+#define MAP_STRIDE 256  // bytes per map row: offset = (ytile << 8) | xtile is one PRMT of the 8.24 positions
+
+// Per-asset (camera or guard) working record in shared memory (64 bytes).
 struct __align__(16) AssetW {
     double base;     // heading - fov/2 (refreshed every tick)
     double step;     // fov / num_rays: ray pitch for the fast path
     double fov;      // exact path
     double heading;  // current heading
-    int x0, y0;      // fixed-point origin in the padded map, +0.5 rounding bias included
+    int x0, y0;      // 8.24 origin in the shared cell map (slot column offset, ring, +0.5 rounding bias)
     unsigned own;    // map offset of the asset's tile (cameras: excluded from marking), ~0 for guards
     int nsamp;       // 2*range (cameras, unit 0.5) or range (guards, unit 1)
     int shift;       // 23 for cameras, 24 for guards: sx = dx * 2^shift
@@ -40,48 +43,48 @@ struct __align__(16) AssetW {
     int row, col;
 };
 
-// Per-warp shared-memory working set of one env.  The padded cell map has one byte per tile plus a
-// one-tile ring of blocking cells, so an out-of-bounds sample needs no bounds test.
-struct WarpCtx {
-    uint8_t *cell;    // [(R+2)*S] CELL_BLOCK | CELL_VIS
-    uint8_t *wall0;   // [(R+2)*S] pristine copy with only CELL_BLOCK (source of the per-tick clear)
-    AssetW *asset;    // [Kc+Kg] cameras first, then guards
-    int *rpre;        // [Kc+Kg+1] prefix sums of rays (num_rays+1) per asset
-    double *speed;    // [Kc] camera rotation speed
-    int4 *g_i;        // [Kg] len, speed, range, num_rays
-    int *g_idx;       // [Kg]
-    unsigned cell_sa; // shared-space address of cell[]
-    int S;            // row stride in bytes
-    int map_bytes;    // (R+2)*S rounded up to 16
+// Shared-memory geometry (CTA-uniform).  Cell maps have one byte per tile plus a one-tile ring of
+// blocking cells (so an out-of-bounds sample needs no bounds test) and a 256-byte row stride; the envs
+// of a CTA sit side by side in the rows: slot e uses columns [colbase, colbase + Sx) of map e >> lg_spr.
+struct Geo {
+    int Sx;         // slot width: 32, 64 or 128 bytes (>= C + 2)
+    int lg_spr;     // log2(slots per 256-byte row): 3, 2 or 1
+    int n_maps;     // maps needed for HEIST_WARPS_PER_CTA slots
+    int map_bytes;  // (R + 2) * 256
+    int w0_bytes;   // compact pristine copy per env: (R + 2) * Sx
 };
 
-// Row stride: a power of two when it does not blow up the map (offset = shift+or), else C+2 rounded to 4.
-__host__ __device__ inline int map_log2s(int C) { return C + 2 <= 32 ? 5 : (C + 2 <= 64 ? 6 : 0); }
-__host__ __device__ inline int map_stride(int C) { int l = map_log2s(C); return l ? (1 << l) : ((C + 2 + 3) & ~3); }
-__host__ __device__ inline int map_bytes(int R, int C) { return ((R + 2) * map_stride(C) + 15) & ~15; }
+__host__ __device__ inline Geo make_geo(int R, int C) {
+    Geo g;
+    g.Sx = (C + 2 <= 32) ? 32 : ((C + 2 <= 64) ? 64 : 128);
+    g.lg_spr = (g.Sx == 32) ? 3 : ((g.Sx == 64) ? 2 : 1);
+    const int spr = 1 << g.lg_spr;
+    g.n_maps = (HEIST_WARPS_PER_CTA + spr - 1) / spr;
+    g.map_bytes = (R + 2) * MAP_STRIDE;
+    g.w0_bytes = (R + 2) * g.Sx;
+    return g;
+}
+
+struct WarpCtx {
+    AssetW *asset;    // [Kc+Kg] cameras first, then guards
+    int4 *g_i;        // [Kg] len, speed, range, num_rays
+    double *speed;    // [Kc] camera rotation speed
+    int *rpre;        // [Kc+Kg+1] prefix sums of rays (num_rays+1) per asset
+    int *g_idx;       // [Kg]
+    uint8_t *wall0;   // [(R+2)][Sx] pristine CELL_BLOCK bytes (source of the per-tick clear)
+    uint8_t *cell;    // this slot's window of the shared cell map: cell[(r+1)*256 + c + 1]
+    unsigned cell_sa; // shared-space address of the MAP (not the window): map + (ytile<<8 | xtile)
+    int colbase;      // column offset of this slot inside the map rows
+};
+
 __host__ __device__ inline size_t warp_ctx_bytes(int R, int C, int Kc, int Kg) {
     size_t b = 0;
     b += (size_t)(Kc + Kg) * sizeof(AssetW);
     b += (size_t)Kg * sizeof(int4);
     b += (size_t)Kc * sizeof(double);
-    b += 2 * (size_t)map_bytes(R, C);
-    b += (size_t)(Kc + Kg + 1) * sizeof(int) + (size_t)Kg * sizeof(int);
+    b += ((size_t)(Kc + Kg + 1) * sizeof(int) + (size_t)Kg * sizeof(int) + 15) & ~(size_t)15;
+    b += (size_t)make_geo(R, C).w0_bytes;
     return (b + 15) & ~(size_t)15;
-}
-
-__device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *p, int R, int C, int Kc, int Kg) {
-    WarpCtx S;
-    S.S = map_stride(C);
-    S.map_bytes = map_bytes(R, C);
-    S.asset = (AssetW *)p;  p += (size_t)(Kc + Kg) * sizeof(AssetW);
-    S.g_i = (int4 *)p;      p += (size_t)Kg * sizeof(int4);
-    S.cell = p;             p += S.map_bytes;
-    S.wall0 = p;            p += S.map_bytes;
-    S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
-    S.rpre = (int *)p;      p += (size_t)(Kc + Kg + 1) * sizeof(int);
-    S.g_idx = (int *)p;
-    S.cell_sa = (unsigned)__cvta_generic_to_shared(S.cell);
-    return S;
 }
 
 __device__ __forceinline__ unsigned lds_u8(unsigned sa) {
@@ -92,6 +95,13 @@ __device__ __forceinline__ unsigned lds_u8(unsigned sa) {
 __device__ __forceinline__ void sts_u8(unsigned sa, unsigned v) {
     asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }
+// (ytile << 8) | xtile from the two 8.24 positions (tile = top byte; ytile < 128 so the sign-replicating
+// selector 0xF yields zero bytes)
+__device__ __forceinline__ unsigned tile_offset(unsigned x, unsigned y) {
+    unsigned d;
+    asm("prmt.b32 %0, %1, %2, 0xFF73;" : "=r"(d) : "r"(x), "r"(y));
+    return d;
+}
 
 struct EnvRegs {
     int r, c, tick, prev, init, flags, n_vault, n_detect, n_timeout;
@@ -101,10 +111,10 @@ struct EnvRegs {
 
 __device__ __forceinline__ int rint_even(double x) { return __double2loint(__dadd_rn(x, RINT_MAGIC)); }
 
-// Exact continuation of ray `ri` of asset `seg` from sample j on (security.py:69-99 / 170-190):
+// Exact continuation of ray `ri` of asset `k` from sample j on (security.py:69-99 / 170-190):
 // marks cells until the first out-of-bounds (ring) or WALL sample.
-__device__ __noinline__ void ray_exact(const AssetW *asset, int seg, unsigned cell_sa, int S, double deg2rad, int ri, int j) {
-    const AssetW A = asset[seg];  // private copy: no re-reads of shared memory in the loop
+__device__ __noinline__ void ray_exact(const AssetW *asset, int k, unsigned map_sa, int colbase, double deg2rad, int ri, int j) {
+    const AssetW A = asset[k];  // private copy: no re-reads of shared memory in the loop
     const double half_fov = __ddiv_rn(A.fov, 2.0);
     const double angle_deg =
         __dadd_rn(__dsub_rn(A.heading, half_fov), __ddiv_rn(__dmul_rn(A.fov, (double)ri), (double)A.num_rays));
@@ -112,61 +122,87 @@ __device__ __noinline__ void ray_exact(const AssetW *asset, int seg, unsigned ce
     ray_dir(angle_deg, deg2rad, dx, dy);
     const double unit = (A.shift == 23) ? 0.5 : 1.0;
     const double dcol = (double)A.col, drow = (double)A.row;
-    for (; j <= A.nsamp; ++j) {
-        const double dist = unit * (double)j;  // exact
+    double dist = unit * (double)j;  // exact (multiples of 0.5)
+    for (; j <= A.nsamp; ++j, dist += unit) {
         int c = rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
         int r = rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
         // consecutive samples move by at most one tile per axis, so the first out-of-bounds sample
         // always lands on the blocking ring
-        unsigned off = (unsigned)((r + 1) * S + (c + 1));
-        if (lds_u8(cell_sa + off) == CELL_BLOCK) return;
-        if (off != A.own) sts_u8(cell_sa + off, CELL_VIS);
+        unsigned off = (unsigned)(((r + 1) << 8) + c + 1 + colbase);
+        if (lds_u8(map_sa + off) == CELL_BLOCK) return;
+        if (off != A.own) sts_u8(map_sa + off, CELL_VIS);
     }
 }
 
 // ---------------------------------------------------------------------------------------------
-// CTA-cooperative ray-march.  A warp owns one env's scalar state, but the rays of all envs of the CTA
-// are marched by all of its warps: every phase the owners publish how many 32-ray chunks their env
-// needs, and warps grab chunks from one shared counter until none are left.  (Envs differ several-
-// fold in rays per tick -- and a reset doubles a tick's work -- so a one-warp-per-env march leaves
-// most of the SM idle behind its slowest warp.)
+// CTA-cooperative ray-march.  The rays of all envs of the CTA are marched by all of its warps:
+// every phase the owners publish how many 32-ray chunks their env needs, and warps grab chunks from
+// one shared counter until none are left.  (Envs differ several-fold in rays per tick -- and a reset
+// doubles a tick's work -- so a one-warp-per-env march leaves most of the SM idle behind its slowest
+// warp.)
 // ---------------------------------------------------------------------------------------------
 #define PEND_CAP 480
 struct CtaCtl {
     int next;                       // chunk counter of the current phase
     int pend_n;                     // rays handed to the exact path this phase
     int cnt[HEIST_WARPS_PER_CTA];   // 32-ray chunks wanted by each env slot this phase (0: none)
+    int n_assets[HEIST_WARPS_PER_CTA];
     int pad[2];
     unsigned pend[PEND_CAP];        // slot:2 | asset:6 | sample j:8 | ray:16
 };
 
-// One ray sample on the fast path.  Returns false when the ray ends (blocked, or handed to the exact path).
-#define HEIST_SAMPLE(CHECK_OWN)                                                                                      \
-    x += sx; y += sy;                                                                                                \
-    if ((unsigned)((x + FX_EPS) & FX_MASK) < 2u * FX_EPS || (unsigned)((y + FX_EPS) & FX_MASK) < 2u * FX_EPS) {      \
-        int slot = (j < 256) ? atomicAdd(&ctl->pend_n, 1) : PEND_CAP;                                                \
-        if (slot < PEND_CAP) ctl->pend[slot] = ((unsigned)e << 30) | ((unsigned)k << 24) | ((unsigned)j << 16) | (unsigned)ri; \
-        else ray_exact(asset, k, cell_sa, stride, deg2rad, ri, j);                                                   \
-        break;                                                                                                       \
-    }                                                                                                                \
-    {                                                                                                                \
-        unsigned off;                                                                                                \
-        if (LOG2S) off = (((unsigned)y >> (FX_BITS - LOG2S)) & (~0u << LOG2S)) | ((unsigned)x >> FX_BITS);           \
-        else off = (unsigned)((y >> FX_BITS) * stride + (x >> FX_BITS));                                             \
-        if (lds_u8(cell_sa + off) == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */        \
-        if (!(CHECK_OWN) || off != own) sts_u8(cell_sa + off, CELL_VIS);                                             \
+__host__ __device__ inline size_t cta_smem_bytes(int R, int C, int Kc, int Kg) {
+    const Geo g = make_geo(R, C);
+    return sizeof(CtaCtl) + (size_t)g.n_maps * g.map_bytes + HEIST_WARPS_PER_CTA * warp_ctx_bytes(R, C, Kc, Kg);
+}
+
+// smem layout: [CtaCtl][n_maps cell maps][slot 0 ctx][slot 1 ctx]...
+__device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *smem, const Geo &g, int slot, int R, int C, int Kc, int Kg) {
+    WarpCtx S;
+    unsigned char *maps = smem + sizeof(CtaCtl);
+    unsigned char *p = maps + (size_t)g.n_maps * g.map_bytes + (size_t)slot * warp_ctx_bytes(R, C, Kc, Kg);
+    S.asset = (AssetW *)p;  p += (size_t)(Kc + Kg) * sizeof(AssetW);
+    S.g_i = (int4 *)p;      p += (size_t)Kg * sizeof(int4);
+    S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
+    S.rpre = (int *)p;      S.g_idx = S.rpre + (Kc + Kg + 1);
+    p += ((size_t)(Kc + Kg + 1) * sizeof(int) + (size_t)Kg * sizeof(int) + 15) & ~(size_t)15;
+    S.wall0 = p;
+    unsigned char *map = maps + (size_t)(slot >> g.lg_spr) * g.map_bytes;
+    S.colbase = (slot & ((1 << g.lg_spr) - 1)) * g.Sx;
+    S.cell = map + S.colbase;
+    S.cell_sa = (unsigned)__cvta_generic_to_shared(map);
+    return S;
+}
+
+// One fast-path sample; `J` is the 1-based sample index (a literal in the unrolled variants).
+// `break`s out of the enclosing loop when the ray ends (blocked, or handed to the exact path).
+#define HEIST_SAMPLE(J, CHECK_OWN)                                                                                    \
+    x += sx; y += sy;                                                                                                 \
+    {                                                                                                                 \
+        /* frac within 2^-16 of the rounding boundary <=> ((pos + EPS) << 8) < (2 EPS << 8) as u32 */                \
+        const unsigned ax = x * 256u + (FX_EPS << 8), ay = y * 256u + (FX_EPS << 8);                            \
+        if (min(ax, ay) < (2u * FX_EPS << 8)) {                                                                       \
+            int slot = ((J) < 256) ? atomicAdd(&ctl->pend_n, 1) : PEND_CAP;                                           \
+            if (slot < PEND_CAP)                                                                                      \
+                ctl->pend[slot] = ((unsigned)e << 30) | ((unsigned)k << 24) | ((unsigned)(J) << 16) | (unsigned)ri;   \
+            else ray_exact(asset, k, map_sa, colbase, deg2rad, ri, (J));                                              \
+            break;                                                                                                    \
+        }                                                                                                             \
+        const unsigned off = tile_offset(x, y);                                                                       \
+        if (lds_u8(map_sa + off) == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */          \
+        if (!(CHECK_OWN) || off != own) sts_u8(map_sa + off, CELL_VIS);                                               \
     }
 
-// March flattened rays [f0, f0+32) of env slot e (asset table `asset`, ray prefix sums `pre`).
-template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *asset, const int *pre, int n_assets, int f0,
-                                            int lane, unsigned cell_sa, int stride, double deg2rad) {
+// March flattened rays [f0, f0+32) of env slot e (asset table `asset`, ray prefix sums `rpre`).
+template <bool EXACT_ONLY>
+__device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *asset, const int *rpre, int n_assets, int f0,
+                                            int lane, unsigned map_sa, int colbase, double deg2rad) {
     const int f = f0 + lane;
-    if (f >= pre[n_assets]) return;
+    if (f >= rpre[n_assets]) return;
     int k = 0;
-    while (f >= pre[k + 1]) ++k;
-    const int ri = f - pre[k];
-    if (EXACT_ONLY) { ray_exact(asset, k, cell_sa, stride, deg2rad, ri, 1); return; }
+    while (f >= rpre[k + 1]) ++k;
+    const int ri = f - rpre[k];
+    if (EXACT_ONLY) { ray_exact(asset, k, map_sa, colbase, deg2rad, ri, 1); return; }
     const AssetW &A = asset[k];
     const int nsamp = A.nsamp;
     const unsigned own = A.own;
@@ -184,47 +220,49 @@ __device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *as
     if ((q + 1) & 2) c_a = -c_a;
     if (q & 2) s_a = -s_a;
     const float scale = (A.shift == 23) ? 8388608.0f : 16777216.0f;
-    const int sx = __float2int_rn(c_a * scale);    // dx =  cos
-    const int sy = __float2int_rn(-s_a * scale);   // dy = -sin
+    const unsigned sx = (unsigned)__float2int_rn(c_a * scale);    // dx =  cos
+    const unsigned sy = (unsigned)__float2int_rn(-s_a * scale);   // dy = -sin
     // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
-    int x = A.x0, y = A.y0;
-    int j = 1;
-    do {  // only a camera's first sample (dist 0.5) can round to the camera's own tile (security.py:93)
-        if (nsamp < 1) break;
-        HEIST_SAMPLE(true)
-#pragma unroll 2
-        for (j = 2; j <= nsamp; ++j) { HEIST_SAMPLE(false) }
-    } while (0);
+    // Only a camera's first sample (dist 0.5) can round to the camera's own tile (security.py:93).
+    unsigned x = (unsigned)A.x0, y = (unsigned)A.y0;
+    if (nsamp == 12) {          // camera, vision_range 6 (the Architect's cameras, networks.py:301)
+        do {
+            HEIST_SAMPLE(1, true) HEIST_SAMPLE(2, false) HEIST_SAMPLE(3, false) HEIST_SAMPLE(4, false)
+            HEIST_SAMPLE(5, false) HEIST_SAMPLE(6, false) HEIST_SAMPLE(7, false) HEIST_SAMPLE(8, false)
+            HEIST_SAMPLE(9, false) HEIST_SAMPLE(10, false) HEIST_SAMPLE(11, false) HEIST_SAMPLE(12, false)
+        } while (0);
+    } else if (nsamp == 4) {    // guard, vision_range 4 (networks.py:311)
+        do {
+            HEIST_SAMPLE(1, true) HEIST_SAMPLE(2, false) HEIST_SAMPLE(3, false) HEIST_SAMPLE(4, false)
+        } while (0);
+    } else if (nsamp >= 1) {
+        for (int j = 1; j <= nsamp; ++j) { HEIST_SAMPLE(j, true) }
+    }
 }
 
 // One cooperative phase: all warps of the CTA drain the chunk queue, then (after a barrier) the
-// rays that were handed to the exact path, 128 at a time instead of one or two lanes at a time.
-// Must be entered by every warp after a __syncthreads() that follows the owners' writes to ctl / cell maps;
-// ends with a __syncthreads().
-template <bool EXACT_ONLY, int LOG2S>
-__device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, int warp, size_t ctx_bytes, CtaCtl *ctl, int lane,
-                                            const int *n_assets_of) {
-    int pre[HEIST_WARPS_PER_CTA + 1];
-    pre[0] = 0;
-#pragma unroll
-    for (int e = 0; e < HEIST_WARPS_PER_CTA; ++e) pre[e + 1] = pre[e] + ctl->cnt[e];
-    const int total = pre[HEIST_WARPS_PER_CTA];
+// rays that were handed to the exact path.  Must be entered by every warp after a __syncthreads()
+// that follows the owners' writes to ctl / cell maps; ends with a __syncthreads().
+template <bool EXACT_ONLY>
+__device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, const Geo &geo, int warp, int ctx_bytes,
+                                            CtaCtl *ctl, int lane) {
+    const int p1 = ctl->cnt[0], p2 = p1 + ctl->cnt[1], p3 = p2 + ctl->cnt[2], total = p3 + ctl->cnt[3];
+    const unsigned next_sa = (unsigned)__cvta_generic_to_shared(&ctl->next);
+    const unsigned map0_sa = S.cell_sa - (unsigned)((warp >> geo.lg_spr) * geo.map_bytes);
     for (;;) {
         int g = 0;
-        if (lane == 0) g = atomicAdd(&ctl->next, 1);
+        if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(g) : "r"(next_sa) : "memory");
         g = __shfl_sync(0xffffffffu, g, 0);
         if (g >= total) break;
-        int e = 0;
-#pragma unroll
-        for (int i = 1; i < HEIST_WARPS_PER_CTA; ++i) e += (g >= pre[i]);
-        int c = g;
-#pragma unroll
-        for (int i = 1; i < HEIST_WARPS_PER_CTA; ++i) if (e == i) c = g - pre[i];
+        const int e = (g >= p1) + (g >= p2) + (g >= p3);
+        const int c = g - (e == 0 ? 0 : (e == 1 ? p1 : (e == 2 ? p2 : p3)));
         // every slot's context has the same layout: shift this warp's own pointers by whole contexts
-        const int delta = (e - warp) * (int)ctx_bytes;
+        const int delta = (e - warp) * ctx_bytes;
         const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
         const int *rpre = reinterpret_cast<const int *>(reinterpret_cast<const unsigned char *>(S.rpre) + delta);
-        march_chunk<EXACT_ONLY, LOG2S>(ctl, e, asset, rpre, n_assets_of[e], c * 32, lane, S.cell_sa + delta, S.S, D.deg2rad);
+        const unsigned map_sa = map0_sa + (unsigned)((e >> geo.lg_spr) * geo.map_bytes);
+        const int colbase = (e & ((1 << geo.lg_spr) - 1)) * geo.Sx;
+        march_chunk<EXACT_ONLY>(ctl, e, asset, rpre, ctl->n_assets[e], c * 32, lane, map_sa, colbase, D.deg2rad);
     }
     __syncthreads();
     if (!EXACT_ONLY) {
@@ -232,19 +270,25 @@ __device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, int 
         for (int i = threadIdx.x; i < P; i += HEIST_WARPS_PER_CTA * 32) {
             const unsigned p = ctl->pend[i];
             const int e = p >> 30, k = (p >> 24) & 63, j = (p >> 16) & 255, ri = p & 0xffff;
-            const int delta = (e - warp) * (int)ctx_bytes;
+            const int delta = (e - warp) * ctx_bytes;
             const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
-            ray_exact(asset, k, S.cell_sa + delta, S.S, D.deg2rad, ri, j);
+            const unsigned map_sa = map0_sa + (unsigned)((e >> geo.lg_spr) * geo.map_bytes);
+            ray_exact(asset, k, map_sa, (e & ((1 << geo.lg_spr) - 1)) * geo.Sx, D.deg2rad, ri, j);
         }
         if (P > 0) __syncthreads();  // P is CTA-uniform (read after the barrier above)
     }
 }
 
 // Owner-side preparation of a visibility rebuild (DynamicVisibilityMap.update, visibility.py:31-65):
-// clear the env's cell map and publish the chunk count.
-__device__ __forceinline__ void begin_visibility(const WarpCtx &S, CtaCtl *ctl, int warp, int lane, int n_assets) {
-    for (int i = lane * 16; i < S.map_bytes; i += 512)
-        *reinterpret_cast<int4 *>(S.cell + i) = *reinterpret_cast<const int4 *>(S.wall0 + i);
+// clear the env's window of the cell map from the pristine copy and publish the chunk count.
+__device__ __forceinline__ void begin_visibility(const WarpCtx &S, const Geo &geo, int R, CtaCtl *ctl, int warp, int lane,
+                                                 int n_assets) {
+    const int per_row = geo.Sx >> 4;  // int4 per row
+    for (int i = lane; i < (R + 2) * per_row; i += 32) {
+        const int row = i / per_row, q = i - row * per_row;
+        *reinterpret_cast<int4 *>(S.cell + row * MAP_STRIDE + q * 16) =
+            *reinterpret_cast<const int4 *>(S.wall0 + row * geo.Sx + q * 16);
+    }
     if (lane == 0) ctl->cnt[warp] = (S.rpre[n_assets] + 31) >> 5;
 }
 
@@ -254,7 +298,7 @@ __device__ __forceinline__ void begin_visibility(const WarpCtx &S, CtaCtl *ctl, 
 __device__ __forceinline__ void end_visibility(const WarpCtx &S, int lane, int n_cams, int n_assets) {
     if (lane >= n_cams && lane < n_assets) {
         const AssetW &A = S.asset[lane];
-        S.cell[(A.row + 1) * S.S + A.col + 1] |= CELL_VIS;
+        S.cell[(A.row + 1) * MAP_STRIDE + A.col + 1] |= CELL_VIS;
     }
     __syncwarp();
 }
@@ -262,13 +306,13 @@ __device__ __forceinline__ void end_visibility(const WarpCtx &S, int lane, int n
 // per-tick refresh of an asset record after its heading / position changed
 __device__ __forceinline__ void refresh_asset(const WarpCtx &S, AssetW &A, bool is_cam) {
     A.base = A.heading - A.fov * 0.5;
-    A.x0 = ((A.col + 1) << FX_BITS) + (FX_ONE >> 1);
-    A.y0 = ((A.row + 1) << FX_BITS) + (FX_ONE >> 1);
-    A.own = is_cam ? (unsigned)((A.row + 1) * S.S + A.col + 1) : ~0u;
+    A.x0 = (int)(((unsigned)(A.col + 1 + S.colbase) << FX_BITS) + (FX_ONE >> 1));
+    A.y0 = (int)(((unsigned)(A.row + 1) << FX_BITS) + (FX_ONE >> 1));
+    A.own = is_cam ? (unsigned)(((A.row + 1) << 8) + A.col + 1 + S.colbase) : ~0u;
 }
 
-__device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env, int lane, EnvRegs &E, int &n_cams,
-                                         int &n_guards) {
+__device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, const Geo &geo, int env, int lane, EnvRegs &E,
+                                         int &n_cams, int &n_guards) {
     const int4 es = *reinterpret_cast<const int4 *>(D.env_s + (size_t)env * 4);
     n_cams = es.x;
     n_guards = es.y;
@@ -276,18 +320,19 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env
     const int4 d1 = *reinterpret_cast<const int4 *>(D.env_d + (size_t)env * 8 + 4);
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    // cell map with a blocking ring: CELL_BLOCK from the wall bitmap, CELL_VIS from the stored visibility
+    // cell window with a blocking ring: CELL_BLOCK from the wall bitmap, CELL_VIS from the stored visibility
     const uint32_t *wall = D.wall + (size_t)env * D.RW, *vis = D.vis + (size_t)env * D.RW;
-    for (int i = lane; i < S.map_bytes; i += 32) {
-        int rr = i / S.S - 1, cc = i - (rr + 1) * S.S - 1;
-        bool inside = rr >= 0 && rr < D.R && cc >= 0 && cc < D.C;
+    for (int i = lane; i < (D.R + 2) * geo.Sx; i += 32) {
+        const int row = i / geo.Sx, col = i - row * geo.Sx;
+        const int rr = row - 1, cc = col - 1;
+        const bool inside = rr >= 0 && rr < D.R && cc >= 0 && cc < D.C;
         unsigned w = CELL_BLOCK, v = 0;
         if (inside) {
             w = (wall[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
             v = ((vis[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u) << 1;
         }
         S.wall0[i] = (uint8_t)w;
-        S.cell[i] = (uint8_t)(w | v);
+        S.cell[row * MAP_STRIDE + col] = (uint8_t)(w | v);
     }
     if (lane < n_cams) {
         size_t o = (size_t)env * D.Kc + lane;
@@ -323,12 +368,12 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, int env
     __syncwarp();
 }
 
-// row bitmaps of the visibility bits of the cell map -> dst[RW]
+// row bitmaps of the visibility bits of the cell window -> dst[RW]
 __device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, int lane, uint32_t *dst) {
     for (int r = 0; r < D.R; ++r)
         for (int w = 0; w < D.W; ++w) {
             int c = w * 32 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, c < D.C && (S.cell[(r + 1) * S.S + c + 1] & CELL_VIS));
+            unsigned m = __ballot_sync(0xffffffffu, c < D.C && (S.cell[(r + 1) * MAP_STRIDE + c + 1] & CELL_VIS));
             if (lane == 0) dst[r * D.W + w] = m;
         }
 }
@@ -374,7 +419,7 @@ __device__ __forceinline__ void step_begin(const Dev &D, const WarpCtx &S, int e
                                            int n_guards, int action) {
     int nr = E.r + (action == 2) - (action == 1);
     int nc = E.c + (action == 4) - (action == 3);
-    if (!(S.cell[(nr + 1) * S.S + nc + 1] & CELL_BLOCK)) { E.r = nr; E.c = nc; }  // ring = out of bounds
+    if (!(S.cell[(nr + 1) * MAP_STRIDE + nc + 1] & CELL_BLOCK)) { E.r = nr; E.c = nc; }  // ring = out of bounds
     if (lane < n_cams) {
         AssetW &A = S.asset[lane];
         A.heading = py_mod360(__dadd_rn(A.heading, S.speed[lane]));
@@ -406,7 +451,7 @@ __device__ __forceinline__ int step_finish(const Dev &D, const WarpCtx &S, EnvRe
     reward = __dadd_rn(reward, __dmul_rn((double)(E.prev - curr), 0.1));
     E.prev = curr;
     if (curr <= 3 && E.init > 3) reward = __dadd_rn(reward, __dmul_rn(0.05, (double)(3 - curr)));
-    if (S.cell[(E.r + 1) * S.S + E.c + 1] & CELL_VIS) {
+    if (S.cell[(E.r + 1) * MAP_STRIDE + E.c + 1] & CELL_VIS) {
         E.flags |= F_DETECTED | F_DONE;
         reward = __dadd_rn(reward, D.reward_detection);
         status = HEIST_DETECTED;
@@ -433,7 +478,7 @@ __device__ __forceinline__ int step_finish(const Dev &D, const WarpCtx &S, EnvRe
 
 // T steps per launch; T = 1 with vis_traj = NULL is HeistEnvironment.step for the batch.
 // Warp slot -> env through D.slot2env (cost-balanced order built after every set_layout).
-template <bool EXACT_ONLY, int LOG2S>
+template <bool EXACT_ONLY>
 __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
             double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
@@ -441,18 +486,17 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
-    unsigned char *env_base = smem + sizeof(CtaCtl);
-    const size_t ctx_bytes = warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
+    const Geo geo = make_geo(D.R, D.C);
+    const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
     const bool have = env >= 0;
-    const WarpCtx S = carve_warp_ctx(env_base + (size_t)warp * ctx_bytes, D.R, D.C, D.Kc, D.Kg);
+    const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     E.flags = F_DONE;
     int n_cams = 0, n_guards = 0;
-    if (have) load_env(D, S, env, lane, E, n_cams, n_guards);
+    if (have) load_env(D, S, geo, env, lane, E, n_cams, n_guards);
     const int n_assets = n_cams + n_guards;
-    __shared__ int ctl_nassets[HEIST_WARPS_PER_CTA];
-    if (lane == 0) ctl_nassets[warp] = n_assets;
+    if (lane == 0) ctl->n_assets[warp] = n_assets;
     int status = HEIST_RUNNING;
     for (int t = 0; t < T; ++t) {
         const size_t o = (size_t)t * D.N + (have ? env : 0);
@@ -460,11 +504,11 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
         const bool live = have && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
         if (live) {
             step_begin(D, S, env, lane, E, n_cams, n_guards, actions[o]);
-            begin_visibility(S, ctl, warp, lane, n_assets);
+            begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets);
         } else if (lane == 0) ctl->cnt[warp] = 0;
         if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
         __syncthreads();
-        march_phase<EXACT_ONLY, LOG2S>(D, S, warp, ctx_bytes, ctl, lane, ctl_nassets);
+        march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
         // ---- owner: rewards, termination, outputs ----
         double rw = 0.0;
         status = HEIST_ALREADY_DONE;
@@ -483,11 +527,11 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
         if (__syncthreads_or(need_reset)) {
             if (need_reset) {
                 reset_state(D, S, env, lane, E, n_cams, n_guards);
-                begin_visibility(S, ctl, warp, lane, n_assets);
+                begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets);
             } else if (lane == 0) ctl->cnt[warp] = 0;
             if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
             __syncthreads();
-            march_phase<EXACT_ONLY, LOG2S>(D, S, warp, ctx_bytes, ctl, lane, ctl_nassets);
+            march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
             if (need_reset) end_visibility(S, lane, n_cams, n_assets);
         }
         if (vis_traj && have) pack_vis(D, S, lane, vis_traj + o * D.RW);
@@ -495,29 +539,28 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     if (have) store_env(D, S, env, lane, E, status, n_cams, n_guards);
 }
 
-template <bool EXACT_ONLY, int LOG2S>
+template <bool EXACT_ONLY>
 __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_reset(Dev D, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
-    unsigned char *env_base = smem + sizeof(CtaCtl);
-    const size_t ctx_bytes = warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
+    const Geo geo = make_geo(D.R, D.C);
+    const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
     const bool have = env >= 0 && (!mask || mask[env]);
-    const WarpCtx S = carve_warp_ctx(env_base + (size_t)warp * ctx_bytes, D.R, D.C, D.Kc, D.Kg);
+    const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams = 0, n_guards = 0;
     if (have) {
-        load_env(D, S, env, lane, E, n_cams, n_guards);
+        load_env(D, S, geo, env, lane, E, n_cams, n_guards);
         reset_state(D, S, env, lane, E, n_cams, n_guards);
-        begin_visibility(S, ctl, warp, lane, n_cams + n_guards);
+        begin_visibility(S, geo, D.R, ctl, warp, lane, n_cams + n_guards);
     } else if (lane == 0) ctl->cnt[warp] = 0;
-    __shared__ int ctl_nassets[HEIST_WARPS_PER_CTA];
-    if (lane == 0) ctl_nassets[warp] = n_cams + n_guards;
+    if (lane == 0) ctl->n_assets[warp] = n_cams + n_guards;
     if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
     __syncthreads();
-    march_phase<EXACT_ONLY, LOG2S>(D, S, warp, ctx_bytes, ctl, lane, ctl_nassets);
+    march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
     if (have) {
         end_visibility(S, lane, n_cams, n_cams + n_guards);
         store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
@@ -525,9 +568,9 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Cost-balanced warp-slot order.  A warp owns one env for a whole launch, and envs differ several-fold
-// in ray-march work, so slots are dealt in "snake" order over the envs sorted by cost: every CTA
-// (4 envs) gets one env from each quartile and all CTAs carry about the same work.
+// Cost-balanced warp-slot order.  Envs differ several-fold in ray-march work, so slots are dealt in
+// "snake" order over the envs sorted by cost: every CTA (4 envs) gets one env from each quartile and
+// all CTAs carry about the same work.
 // ---------------------------------------------------------------------------------------------
 #define ORDER_BINS 1024
 __global__ void __launch_bounds__(1024) k_build_order(Dev D, int n_ctas) {
@@ -550,7 +593,7 @@ __global__ void __launch_bounds__(1024) k_build_order(Dev D, int n_ctas) {
     const float inv = (float)(ORDER_BINS - 1) / (float)s_max;
     for (int i = tid; i < D.N; i += 1024) atomicAdd(&hist[min(ORDER_BINS - 1, (int)((float)D.cost[i] * inv))], 1);
     __syncthreads();
-    // start[b] = number of envs in bins above b (descending cost); serial scan by one warp is fine
+    // start[b] = number of envs in bins above b (descending cost)
     if (tid == 0) {
         int acc = 0;
         for (int b = ORDER_BINS - 1; b >= 0; --b) { int c = hist[b]; hist[b] = acc; acc += c; }
