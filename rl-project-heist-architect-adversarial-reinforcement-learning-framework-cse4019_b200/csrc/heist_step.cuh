@@ -175,19 +175,14 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *smem, const Geo
 }
 
 // One fast-path sample; `J` is the 1-based sample index (a literal in the unrolled variants).
-// `break`s out of the enclosing loop when the ray ends (blocked, or handed to the exact path).
+// `break`s out of the enclosing loop when the ray ends: blocked, or ambiguous (amb_j = J; the rare
+// hand-over to the exact path is done once, after the loop, to keep the unrolled code small).
 #define HEIST_SAMPLE(J, CHECK_OWN)                                                                                    \
     x += sx; y += sy;                                                                                                 \
     {                                                                                                                 \
         /* frac within 2^-16 of the rounding boundary <=> ((pos + EPS) << 8) < (2 EPS << 8) as u32 */                \
-        const unsigned ax = x * 256u + (FX_EPS << 8), ay = y * 256u + (FX_EPS << 8);                            \
-        if (min(ax, ay) < (2u * FX_EPS << 8)) {                                                                       \
-            int slot = ((J) < 256) ? atomicAdd(&ctl->pend_n, 1) : PEND_CAP;                                           \
-            if (slot < PEND_CAP)                                                                                      \
-                ctl->pend[slot] = ((unsigned)e << 30) | ((unsigned)k << 24) | ((unsigned)(J) << 16) | (unsigned)ri;   \
-            else ray_exact(asset, k, map_sa, colbase, deg2rad, ri, (J));                                              \
-            break;                                                                                                    \
-        }                                                                                                             \
+        const unsigned ax = x * 256u + (FX_EPS << 8), ay = y * 256u + (FX_EPS << 8);                                  \
+        if (min(ax, ay) < (2u * FX_EPS << 8)) { amb_j = (J); break; }                                                 \
         const unsigned off = tile_offset(x, y);                                                                       \
         if (lds_u8(map_sa + off) == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */          \
         if (!(CHECK_OWN) || off != own) sts_u8(map_sa + off, CELL_VIS);                                               \
@@ -225,6 +220,7 @@ __device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *as
     // ---- samples: 8.24 fixed point, tile = floor(pos + 0.5) unless within 2^-16 of a boundary ----
     // Only a camera's first sample (dist 0.5) can round to the camera's own tile (security.py:93).
     unsigned x = (unsigned)A.x0, y = (unsigned)A.y0;
+    int amb_j = 0;
     if (nsamp == 12) {          // camera, vision_range 6 (the Architect's cameras, networks.py:301)
         do {
             HEIST_SAMPLE(1, true) HEIST_SAMPLE(2, false) HEIST_SAMPLE(3, false) HEIST_SAMPLE(4, false)
@@ -237,6 +233,12 @@ __device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *as
         } while (0);
     } else if (nsamp >= 1) {
         for (int j = 1; j <= nsamp; ++j) { HEIST_SAMPLE(j, true) }
+    }
+    if (amb_j) {  // queue the rest of the ray for the exact path (processed 128 rays at a time after the barrier)
+        int slot = (amb_j < 256) ? atomicAdd(&ctl->pend_n, 1) : PEND_CAP;
+        if (slot < PEND_CAP)
+            ctl->pend[slot] = ((unsigned)e << 30) | ((unsigned)k << 24) | ((unsigned)amb_j << 16) | (unsigned)ri;
+        else ray_exact(asset, k, map_sa, colbase, deg2rad, ri, amb_j);
     }
 }
 
@@ -500,39 +502,40 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     int status = HEIST_RUNNING;
     for (int t = 0; t < T; ++t) {
         const size_t o = (size_t)t * D.N + (have ? env : 0);
-        // ---- owner: early-out / move / rotate / patrol, then publish the visibility rebuild ----
         const bool live = have && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
-        if (live) {
-            step_begin(D, S, env, lane, E, n_cams, n_guards, actions[o]);
-            begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets);
-        } else if (lane == 0) ctl->cnt[warp] = 0;
-        if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
-        __syncthreads();
-        march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
-        // ---- owner: rewards, termination, outputs ----
-        double rw = 0.0;
-        status = HEIST_ALREADY_DONE;
-        if (live) {
-            end_visibility(S, lane, n_cams, n_assets);
-            status = step_finish(D, S, E, rw);
-        }
-        if (have && lane == 0) {
-            if (reward) reward[o] = (float)rw;
-            if (reward64) reward64[o] = rw;
-            if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
-            if (status_out) status_out[o] = (uint8_t)status;
-        }
-        // ---- auto-reset (the trainer's `if done: reset()`), second cooperative phase if anyone needs it ----
-        const bool need_reset = autoreset && have && (E.flags & F_DONE);
-        if (__syncthreads_or(need_reset)) {
-            if (need_reset) {
-                reset_state(D, S, env, lane, E, n_cams, n_guards);
-                begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets);
-            } else if (lane == 0) ctl->cnt[warp] = 0;
+        // Two cooperative phases per tick through ONE copy of the march code (instruction cache):
+        // phase 0 = the step's visibility rebuild, phase 1 = the rebuild after an auto-reset
+        // (the trainer's `if done: reset()`), entered only if some env of the CTA needs it.
+#pragma unroll 1
+        for (int phase = 0; phase < 2; ++phase) {
+            bool mine;
+            if (phase == 0) {
+                // ---- owner: move / rotate / patrol ----
+                mine = live;
+                if (live) step_begin(D, S, env, lane, E, n_cams, n_guards, actions[o]);
+            } else {
+                mine = autoreset && have && (E.flags & F_DONE);
+                if (!__syncthreads_or(mine)) break;
+                if (mine) reset_state(D, S, env, lane, E, n_cams, n_guards);
+            }
+            if (mine) begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets);
+            else if (lane == 0) ctl->cnt[warp] = 0;
             if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
             __syncthreads();
             march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
-            if (need_reset) end_visibility(S, lane, n_cams, n_assets);
+            if (mine) end_visibility(S, lane, n_cams, n_assets);
+            if (phase == 0) {
+                // ---- owner: rewards, termination, outputs ----
+                double rw = 0.0;
+                status = HEIST_ALREADY_DONE;
+                if (live) status = step_finish(D, S, E, rw);
+                if (have && lane == 0) {
+                    if (reward) reward[o] = (float)rw;
+                    if (reward64) reward64[o] = rw;
+                    if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
+                    if (status_out) status_out[o] = (uint8_t)status;
+                }
+            }
         }
         if (vis_traj && have) pack_vis(D, S, lane, vis_traj + o * D.RW);
     }
