@@ -180,11 +180,14 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *smem, const Geo
 #define HEIST_SAMPLE(J, CHECK_OWN)                                                                                    \
     x += sx; y += sy;                                                                                                 \
     {                                                                                                                 \
+        /* the load is issued first so that its latency overlaps the ambiguity test: the address is always   */      \
+        /* inside the map because the previous sample was in bounds and not blocking (ring argument above)   */      \
+        const unsigned off = tile_offset(x, y);                                                                       \
+        const unsigned cellv = lds_u8(map_sa + off);                                                                  \
         /* frac within 2^-16 of the rounding boundary <=> ((pos + EPS) << 8) < (2 EPS << 8) as u32 */                \
         const unsigned ax = x * 256u + (FX_EPS << 8), ay = y * 256u + (FX_EPS << 8);                                  \
         if (min(ax, ay) < (2u * FX_EPS << 8)) { amb_j = (J); break; }                                                 \
-        const unsigned off = tile_offset(x, y);                                                                       \
-        if (lds_u8(map_sa + off) == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */          \
+        if (cellv == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */                         \
         if (!(CHECK_OWN) || off != own) sts_u8(map_sa + off, CELL_VIS);                                               \
     }
 
