@@ -173,9 +173,11 @@ def run_ours(args, rank, world, local_rank):
     # memory (e2e)
     acts_host = [torch.from_numpy(synthetic.sample_actions(rng, T, N)).pin_memory() for _ in range(n_iter)]
     acts_dev = [a.to(dev) for a in acts_host]
+    # every env step writes its packed observable state to HBM: reward, done, status and the visibility bitmap
     out = {"reward": torch.empty((T, N), dtype=torch.float32, device=dev),
            "done": torch.empty((T, N), dtype=torch.uint8, device=dev),
-           "status": torch.empty((T, N), dtype=torch.uint8, device=dev)}
+           "status": torch.empty((T, N), dtype=torch.uint8, device=dev),
+           "vis_bits": torch.empty((T, N, env.R, env.W), dtype=torch.int32, device=dev)}
     rew_host = torch.empty((T, N), dtype=torch.float32).pin_memory()
     done_host = torch.empty((T, N), dtype=torch.uint8).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

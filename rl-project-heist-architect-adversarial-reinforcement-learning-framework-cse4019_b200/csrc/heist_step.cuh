@@ -373,18 +373,36 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, const G
     __syncwarp();
 }
 
-// row bitmaps of the visibility bits of the cell window -> dst[RW]
-__device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, int lane, uint32_t *dst) {
-    for (int r = 0; r < D.R; ++r)
-        for (int w = 0; w < D.W; ++w) {
-            int c = w * 32 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, c < D.C && (S.cell[(r + 1) * MAP_STRIDE + c + 1] & CELL_VIS));
-            if (lane == 0) dst[r * D.W + w] = m;
-        }
+// bit i of the result = CELL_VIS of byte p[i], i < 32 (p 16-byte aligned)
+__device__ __forceinline__ unsigned pack32(const uint8_t *p) {
+    const uint4 a = *reinterpret_cast<const uint4 *>(p), b = *reinterpret_cast<const uint4 *>(p + 16);
+    unsigned m = 0;
+    // (w >> 1) & 0x01010101 isolates the CELL_VIS bit of 4 cells; * 0x01020408 gathers them into the top nibble
+#define HEIST_NIB(w, sh) m |= (((((w) >> 1) & 0x01010101u) * 0x01020408u) >> 24) << (sh);
+    HEIST_NIB(a.x, 0) HEIST_NIB(a.y, 4) HEIST_NIB(a.z, 8) HEIST_NIB(a.w, 12)
+    HEIST_NIB(b.x, 16) HEIST_NIB(b.y, 20) HEIST_NIB(b.z, 24) HEIST_NIB(b.w, 28)
+#undef HEIST_NIB
+    return m;
 }
 
-__device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, int env, int lane, const EnvRegs &E, int status,
-                                          int n_cams, int n_guards) {
+// row bitmaps of the visibility bits of the cell window -> dst[RW]; lane = grid row, coalesced store.
+// (The window's first byte is the ring, so the packed row is shifted down by one; ring and padding
+// bytes never carry CELL_VIS.)
+__device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, const Geo &geo, int lane, uint32_t *dst) {
+    for (int r = lane; r < D.R; r += 32) {
+        const uint8_t *row = S.cell + (r + 1) * MAP_STRIDE;
+        const unsigned lo = pack32(row);
+        const unsigned mid = geo.Sx > 32 ? pack32(row + 32) : 0u;
+        dst[r * D.W] = (lo >> 1) | (mid << 31);
+        if (D.W > 1) {
+            const unsigned hi = geo.Sx > 64 ? pack32(row + 64) : 0u;
+            dst[r * D.W + 1] = (mid >> 1) | (hi << 31);
+        }
+    }
+}
+
+__device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, const Geo &geo, int env, int lane,
+                                          const EnvRegs &E, int status, int n_cams, int n_guards) {
     if (lane == 0) {
         int4 d0 = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
         int4 d1 = make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
@@ -397,7 +415,7 @@ __device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, int en
         D.guard_heading[o] = S.asset[n_cams + lane].heading;
         D.guard_idx[o] = S.g_idx[lane];
     }
-    pack_vis(D, S, lane, D.vis + (size_t)env * D.RW);
+    pack_vis(D, S, geo, lane, D.vis + (size_t)env * D.RW);
 }
 
 // HeistEnvironment.reset (environment.py:183-214), owner part: solver to start, guards to waypoint 0;
@@ -540,9 +558,9 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
                 }
             }
         }
-        if (vis_traj && have) pack_vis(D, S, lane, vis_traj + o * D.RW);
+        if (vis_traj && have) pack_vis(D, S, geo, lane, vis_traj + o * D.RW);
     }
-    if (have) store_env(D, S, env, lane, E, status, n_cams, n_guards);
+    if (have) store_env(D, S, geo, env, lane, E, status, n_cams, n_guards);
 }
 
 template <bool EXACT_ONLY>
@@ -569,7 +587,7 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
     march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
     if (have) {
         end_visibility(S, lane, n_cams, n_cams + n_guards);
-        store_env(D, S, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
+        store_env(D, S, geo, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
     }
 }
 
