@@ -239,6 +239,12 @@ extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int
     CUDA_TRY(cudaSetDevice(h->device));
     launch_step(h, actions, T, autoreset, reward, nullptr, done, status, vis_traj, (cudaStream_t)stream);
     CUDA_TRY(cudaGetLastError());
+    if (T >= 8) {  // re-deal the warp slots by the work each env actually did (its reset rate included)
+        CUDA_TRY(cudaMemsetAsync(h->d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(h->N) * HEIST_WARPS_PER_CTA,
+                                 (cudaStream_t)stream));
+        k_build_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d, env_blocks(h->N));
+        CUDA_TRY(cudaGetLastError());
+    }
     return 0;
 }
 

@@ -521,6 +521,8 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     const int n_assets = n_cams + n_guards;
     if (lane == 0) ctl->n_assets[warp] = n_assets;
     int status = HEIST_RUNNING;
+    int work = 0;  // 32-ray chunks this env asked for during the launch (measured load-balance cost)
+    const int chunks = have ? (S.rpre[n_assets] + 31) >> 5 : 0;
     for (int t = 0; t < T; ++t) {
         const size_t o = (size_t)t * D.N + (have ? env : 0);
         const bool live = have && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
@@ -539,7 +541,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
                 if (!__syncthreads_or(mine)) break;
                 if (mine) reset_state(D, S, env, lane, E, n_cams, n_guards);
             }
-            if (mine) begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets);
+            if (mine) { begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets); work += chunks; }
             else if (lane == 0) ctl->cnt[warp] = 0;
             if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
             __syncthreads();
@@ -560,7 +562,11 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
         }
         if (vis_traj && have) pack_vis(D, S, geo, lane, vis_traj + o * D.RW);
     }
-    if (have) store_env(D, S, geo, env, lane, E, status, n_cams, n_guards);
+    if (have) {
+        store_env(D, S, geo, env, lane, E, status, n_cams, n_guards);
+        // feed the measured work (resets included) back into the slot order of the next launch
+        if (lane == 0 && T >= 8) D.cost[env] = (int)(((long long)work * 256) / T) + 16;
+    }
 }
 
 template <bool EXACT_ONLY>
