@@ -41,6 +41,14 @@ def b_step_bytes(rows, cols, kc, kg):
     return 1 + (g + 32 * kc + 40 * kg + 16) + (8 * kc + 12 * kg + 16) + g + 5
 
 
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (or None)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -213,7 +221,6 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
 
     # (1) kernel-resident throughput: inputs already in HBM
-    live_before = int(env.env_dyn[:, 1].sum().item())  # not used for counting; auto-reset keeps every step live
     ms_value = timed_loop(lambda i: env.step_many(acts_dev[i], autoreset=True, out=out))
     steps_per_iter = T * N  # auto-reset: every (tick, env) is a live env step
     total_steps = steps_per_iter * args.steps * world
@@ -229,7 +236,6 @@ def run_ours(args, rank, world, local_rank):
     ms_e2e = timed_loop(e2e_body)
     e2e_value = total_steps / (ms_e2e * 1e-3)
     clocks = sampler.stop() if sampler else None
-    _ = live_before
 
     # (3) secondary HBM-streaming kernels of the path, timed alone (reported, not the headline)
     def time_kernel(fn, reps=20):
@@ -269,11 +275,12 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T * N, "d2h_bytes_per_step": 5 * T * N,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": args.steps,
+            "gpu_launches": 2 * args.steps,  # k_step_many + k_build_order per step
             "roofline": {"bound": "hbm", "kernel": "k_step_many", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": measured_traffic("k_step_many"), "peak_source": peak_src,
                          "bytes_per_env_step": bstep, "mean_cams": kc, "mean_guards": kg,
-                         "note": "ray-march is issue/fp64-bound, not HBM-bound (SURVEY 8d); see DESIGN.md"},
+                         "note": "the ray-march is instruction-issue bound, not HBM bound (SURVEY 8d, DESIGN.md 5): "
+                                 "frac is honest and small; see profiles/ for issue-slot utilisation"},
             "clocks": clocks, "other_kernels": extra}
     if not args.no_cpu_baseline and world == 1:
         rate, threads, sample, _, _ = cpu_rollout_rate(args, 256, args.cpu_seconds, seed)
@@ -297,6 +304,11 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
+    if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "ours":
+        # convenience: the driver launches torchrun itself; a bare `python bench.py --gpus N` re-launches under it
+        os.execvp(sys.executable, [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                                   f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1", "--master-port",
+                                   "29533", os.path.abspath(__file__)] + sys.argv[1:])
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
