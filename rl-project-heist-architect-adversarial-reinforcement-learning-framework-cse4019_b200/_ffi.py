@@ -50,7 +50,8 @@ EXPORTS = {
 
 
 def lib_path():
-    return _build.LIB_PATH
+    """HEIST_B200_DEBUG=1 selects the range-checked debug build of the same sources."""
+    return _build.DBG_LIB_PATH if os.environ.get("HEIST_B200_DEBUG") == "1" else _build.LIB_PATH
 
 
 def load():

@@ -7,6 +7,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_DIR = os.path.join(_HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libheist_b200.so")
+DBG_LIB_PATH = os.path.join(LIB_DIR, "libheist_b200_dbg.so")  # -DHEIST_DEBUG_BOUNDS: range-checked cell-map accesses
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -28,28 +29,30 @@ def sources():
         [os.path.join(os.path.dirname(_HERE), "include", "heist_b200.h")]
 
 
-def is_stale():
-    if not os.path.exists(LIB_PATH):
+def is_stale(path=None):
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         return True
-    t = os.path.getmtime(LIB_PATH)
+    t = os.path.getmtime(path)
     return any(os.path.getmtime(s) > t for s in sources())
 
 
 def build(force=False, verbose=False):
     """Compile csrc/heist_b200.cu -> lib/libheist_b200.so (cross-compiles without a GPU)."""
-    if not force and not is_stale():
-        return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-        ["-o", LIB_PATH, os.path.join(CSRC, "heist_b200.cu")]
     env = dict(os.environ)
     env.pop("CC", None)   # the image's $CC wrapper is not a usable nvcc host compiler
     env.pop("CXX", None)
-    res = subprocess.run(cmd, capture_output=True, text=True, env=env)
-    if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+    for path, extra in ((LIB_PATH, []), (DBG_LIB_PATH, ["-DHEIST_DEBUG_BOUNDS"])):
+        if not force and not is_stale(path):
+            continue
+        cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+            ["-o", path, os.path.join(CSRC, "heist_b200.cu")]
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+        if verbose:
+            print(res.stderr)
     return LIB_PATH
 
 

@@ -315,10 +315,11 @@ extern "C" int heist_check_errors(HeistHandle *h, void *stream) {
     CUDA_TRY(cudaMemcpy(&flags, h->d.err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
         CUDA_TRY(cudaMemset(h->d.err, 0, sizeof(int)));
-        return fail(-100 - flags, "device-side layout error:%s%s%s",
+        return fail(-100 - flags, "device-side error:%s%s%s%s",
                     (flags & ERR_CAPACITY) ? " capacity exceeded (max_walls/max_cams/max_guards/max_path)" : "",
                     (flags & ERR_WAYPOINT) ? " guard waypoint outside the grid" : "",
-                    (flags & ERR_RAYS) ? " fov/vision_range too large" : "");
+                    (flags & ERR_RAYS) ? " fov/vision_range too large" : "",
+                    (flags & ERR_BOUNDS) ? " cell-map access out of range (debug build)" : "");
     }
     return 0;
 }

@@ -87,13 +87,28 @@ __host__ __device__ inline size_t warp_ctx_bytes(int R, int C, int Kc, int Kg) {
     return (b + 15) & ~(size_t)15;
 }
 
+#ifdef HEIST_DEBUG_BOUNDS
+// Debug build (lib/libheist_b200_dbg.so): every cell-map access of the march is range-checked against the
+// CTA's dynamic shared memory; a violation raises the sticky ERR_BOUNDS flag instead of touching memory.
+// (compute-sanitizer is not available on the GPU pool; tests/test_gpu_parity.py runs this build.)
+__device__ int *g_dbg_err;
+__device__ unsigned g_dbg_smem_lo, g_dbg_smem_hi;
+__device__ __forceinline__ bool dbg_ok(unsigned sa) {
+    if (sa >= g_dbg_smem_lo && sa < g_dbg_smem_hi) return true;
+    atomicOr(g_dbg_err, ERR_BOUNDS);
+    return false;
+}
+#else
+__device__ __forceinline__ bool dbg_ok(unsigned) { return true; }
+#endif
+
 __device__ __forceinline__ unsigned lds_u8(unsigned sa) {
-    unsigned v;
-    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
+    unsigned v = CELL_BLOCK;
+    if (dbg_ok(sa)) asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(sa) : "memory");
     return v;
 }
 __device__ __forceinline__ void sts_u8(unsigned sa, unsigned v) {
-    asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
+    if (dbg_ok(sa)) asm volatile("st.shared.u8 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
 }
 // (ytile << 8) | xtile from the two 8.24 positions (tile = top byte; ytile < 128 so the sign-replicating
 // selector 0xF yields zero bytes)
@@ -172,6 +187,17 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *smem, const Geo
     S.cell = map + S.colbase;
     S.cell_sa = (unsigned)__cvta_generic_to_shared(map);
     return S;
+}
+
+__device__ __forceinline__ void dbg_init(const Dev &D, unsigned char *smem, const Geo &geo) {
+#ifdef HEIST_DEBUG_BOUNDS
+    if (threadIdx.x == 0) {  // every CTA writes the same values (shared-window addresses are CTA-independent)
+        g_dbg_err = D.err;
+        g_dbg_smem_lo = (unsigned)__cvta_generic_to_shared(smem) + (unsigned)sizeof(CtaCtl);
+        g_dbg_smem_hi = g_dbg_smem_lo + (unsigned)(geo.n_maps * geo.map_bytes);
+    }
+    __syncthreads();
+#endif
 }
 
 // One fast-path sample; `J` is the 1-based sample index (a literal in the unrolled variants).
@@ -511,6 +537,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
     const Geo geo = make_geo(D.R, D.C);
     const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
+    dbg_init(D, smem, geo);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
     const bool have = env >= 0;
     const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
@@ -576,6 +603,7 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
     const Geo geo = make_geo(D.R, D.C);
+    dbg_init(D, smem, geo);
     const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
     const bool have = env >= 0 && (!mask || mask[env]);

@@ -439,3 +439,17 @@ def test_filtered_fast_path_equals_all_fp64_path(R, C, N, T, counts, nice):
         assert torch.equal(res[0][1][k], res[1][1][k]), k
     assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
     assert res[0][1]["vis_bits"].ne(0).any()
+
+
+def test_debug_bounds_build_reports_no_out_of_range_access():
+    """compute-sanitizer is closed on the GPU pool, so the march is also run from a -DHEIST_DEBUG_BOUNDS build that
+    range-checks every cell-map access (tests/sanitizer_small.py: four grid classes, resets, exact-path rays)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, HEIST_B200_DEBUG="1")
+    res = subprocess.run([sys.executable, os.path.join(root, "tests", "sanitizer_small.py")], env=env,
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 4
