@@ -254,10 +254,11 @@ extern "C" int heist_observe(HeistHandle *h, float *state, void *stream) {
     const Dev &d = h->d;
     cudaStream_t s = (cudaStream_t)stream;
     if (d.C % 4 == 0 && ((uintptr_t)state & 15) == 0) {
-        long long total = (long long)d.N * 3 * (d.RC / 4);
-        long long blocks = (total + 255) / 256;
-        if (blocks > 148LL * 32) blocks = 148LL * 32;
-        k_observe_vec4<<<(int)blocks, 256, 0, s>>>(d, (float4 *)state);
+        const int nq = 3 * (d.RC / 4);
+        const int bx = (nq + 255) / 256;                     // blocks per env, each <= 256 threads ...
+        const int bdx = ((nq + bx - 1) / bx + 31) & ~31;     // ... evenly split and rounded up to a warp
+        const int by = d.N < 148 * 16 ? d.N : 148 * 16;      // grid-stride over envs beyond that
+        k_observe_vec4<<<dim3(bx, by), bdx, 0, s>>>(d, (float4 *)state);
     } else {
         long long total = (long long)d.N * 3 * d.RC;
         long long blocks = (total + 255) / 256;
@@ -294,7 +295,14 @@ extern "C" int heist_gae(const float *rew, const float *val, const uint8_t *done
     CUDA_TRY(cudaSetDevice(device));
     const float g = (float)gamma;                  // torch casts the Python scalar to the tensor dtype
     const float gl = (float)(gamma * gae_lambda);  // self.gamma * self.gae_lambda is a Python double product
-    k_gae<8><<<(n_cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
+    // Columns are the only parallelism (the scan is sequential in t for bit-exactness).  With few columns use
+    // one warp per CTA spread over all SMs and a deep load prefetch; with many, wider CTAs and less prefetch.
+    if (n_cols <= 32768)
+        k_gae<32, 32><<<(n_cols + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
+    else if (n_cols <= 131072)
+        k_gae<16, 64><<<(n_cols + 63) / 64, 64, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
+    else
+        k_gae<8, 128><<<(n_cols + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

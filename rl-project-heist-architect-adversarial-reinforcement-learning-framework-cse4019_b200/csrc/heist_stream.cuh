@@ -17,38 +17,40 @@ __global__ void k_pos_table(Dev D) {
 }
 
 // state[N][3][R][C] float32.  One thread per 4 consecutive cells of one channel (C % 4 == 0)
-// -> one 16-byte store; inputs are bytes / bits and stay in L1/L2.
-__global__ void __launch_bounds__(256) k_observe_vec4(Dev D, float4 *__restrict__ out) {
+// -> one 16-byte store; inputs are bytes / bits and stay in L1/L2.  blockIdx.y strides over envs,
+// blockIdx.x * blockDim.x + tid over the 3 * R*C/4 quads of one env (32-bit index math only; the block
+// width is 3*R*C/4 rounded up to a warp so that small grids do not idle half a block).
+__global__ void __launch_bounds__(1024) k_observe_vec4(Dev D, float4 *__restrict__ out) {
     const int quads = D.RC >> 2;
-    const long long total = (long long)D.N * 3 * quads;
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        int env = (int)(idx / (3 * quads));
-        int rem = (int)(idx - (long long)env * 3 * quads);
-        int ch = rem / quads;
-        int cell = (rem - ch * quads) << 2;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 3 * quads) return;
+    const int ch = (q >= quads) + (q >= 2 * quads);
+    const int cell = (q - ch * quads) << 2;
+    const int r = cell / D.C, c = cell - r * D.C;
+    const int vcell = D.vault_r * D.C + D.vault_c;
+    float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ch == 2) g = *reinterpret_cast<const float4 *>(D.pos_tab + cell);
+#pragma unroll 4
+    for (int env = blockIdx.y; env < D.N; env += gridDim.y) {
         float4 v;
         if (ch == 0) {  // occupancy = grid.astype(float32) / 5   (:319)
             uchar4 t = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + cell);
             v.x = __fdiv_rn((float)t.x, 5.0f); v.y = __fdiv_rn((float)t.y, 5.0f);
             v.z = __fdiv_rn((float)t.z, 5.0f); v.w = __fdiv_rn((float)t.w, 5.0f);
         } else if (ch == 1) {  // visibility (:322)
-            int r = cell / D.C, c = cell - r * D.C;
             uint32_t bits = D.vis[(size_t)env * D.RW + r * D.W + (c >> 5)] >> (c & 31);
             v.x = (float)(bits & 1u); v.y = (float)((bits >> 1) & 1u);
             v.z = (float)((bits >> 2) & 1u); v.w = (float)((bits >> 3) & 1u);
         } else {  // position channel (:356-365): solver +1, vault -1 (vault wins), plus gradient
             int pos = D.env_d[(size_t)env * 8];
             int scell = (pos & 0xffff) * D.C + (pos >> 16);
-            int vcell = D.vault_r * D.C + D.vault_c;
-            float4 g = *reinterpret_cast<const float4 *>(D.pos_tab + cell);
             float b0 = (cell + 0 == vcell) ? -1.0f : ((cell + 0 == scell) ? 1.0f : 0.0f);
             float b1 = (cell + 1 == vcell) ? -1.0f : ((cell + 1 == scell) ? 1.0f : 0.0f);
             float b2 = (cell + 2 == vcell) ? -1.0f : ((cell + 2 == scell) ? 1.0f : 0.0f);
             float b3 = (cell + 3 == vcell) ? -1.0f : ((cell + 3 == scell) ? 1.0f : 0.0f);
             v.x = __fadd_rn(b0, g.x); v.y = __fadd_rn(b1, g.y); v.z = __fadd_rn(b2, g.z); v.w = __fadd_rn(b3, g.w);
         }
-        out[idx] = v;
+        __stcs(out + (size_t)env * 3 * quads + q, v);  // write-once stream: do not keep it in L2
     }
 }
 
@@ -94,8 +96,8 @@ __global__ void k_obs_vectors(Dev D, float *__restrict__ out) {
 // GAE + returns, one thread per time-major column, fp32 ops in the reference's order, no FMA:
 //   delta = r + (g * next_v) * (1 - d) - v ;  A = delta + (gl * (1 - d)) * A ;  ret = A + v
 // Loads do not depend on the recurrence, so each thread prefetches CH timesteps at a time.
-template <int CH>
-__global__ void __launch_bounds__(128)
+template <int CH, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 k_gae(const float *__restrict__ rew, const float *__restrict__ val, const uint8_t *__restrict__ done, int T, int n,
       float g, float gl, float *__restrict__ adv, float *__restrict__ ret) {
     int j = blockIdx.x * blockDim.x + threadIdx.x;
