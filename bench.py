@@ -28,8 +28,9 @@ FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
 
 
 def workload_config(args, world):
-    return {"workload": f"config2: {args.rows}x{args.cols} grid, {args.envs} envs/GPU, random valid layouts "
-                        f"(budget {args.budget}), Solver-only rollout T={args.ticks}, auto-reset, uniform actions",
+    return {"workload": f"config{args.config}: {args.rows}x{args.cols} grid, {args.envs} envs/GPU, random valid layouts "
+                        f"(budget {args.budget}{', walls/cameras/guards = %d/%d/%d' % args.exact_counts if args.exact_counts else ''}), "
+                        f"Solver-only rollout T={args.ticks}, auto-reset, uniform actions",
             "grid": [args.rows, args.cols], "envs_per_gpu": args.envs, "ticks_per_step": args.ticks,
             "budget": args.budget, "max_steps": 200, "parallelism": f"env-shard x{world} (no data-path collective)",
             "l2": "flushed between timed iterations (256 MiB write)"}
@@ -114,7 +115,8 @@ def cpu_rollout_rate(args, n_envs, budget_s, seed, n_threads=0, min_rounds=1):
     rng = np.random.default_rng(seed)
     envs = []
     while len(envs) < n_envs:  # random VALID layouts: resample invalid ones (validity from the oracle's BFS)
-        am = synthetic.sample_asset_maps(rng, 1, args.rows, args.cols)[0]
+        am = (synthetic.sample_asset_maps_exact(rng, 1, args.rows, args.cols, *args.exact_counts)[0]
+              if args.exact_counts else synthetic.sample_asset_maps(rng, 1, args.rows, args.cols)[0])
         cp = synthetic.sample_cam_params(rng, 1)[0]
         walls, cams, guards, _ = ho.decode_layout(am, args.budget, *cp)
         e = ho.OracleEnv(args.rows, args.cols, max_steps=200, budget=args.budget)
@@ -170,7 +172,7 @@ def run_ours(args, rank, world, local_rank):
                                        architect_budget=args.budget)
     env = heist_b200.BatchedHeistEnv(cfg, args.envs, device=dev)
     seed = synthetic.BASE_SEED + rank
-    synthetic.make_valid_workload(env, seed, args.budget)
+    synthetic.make_valid_workload(env, seed, args.budget, exact_counts=args.exact_counts)
     env.reset()
     kc = float(env.env_static[:, 0].float().mean().item())
     kg = float(env.env_static[:, 1].float().mean().item())
@@ -299,10 +301,20 @@ def main():
     ap.add_argument("--cols", type=int, default=20)
     ap.add_argument("--ticks", type=int, default=200)
     ap.add_argument("--budget", type=int, default=15)
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
+                    help="BASELINE.json configs[] index: 2 = 20x20/4096 envs (default, the headline), 3 = 32x32/65536 "
+                         "envs, 4 cameras + 2 guards, 4 = 64x64/262144 envs split over the GPUs")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    args.exact_counts = None
+    if args.config == 3:
+        args.rows = args.cols = 32
+        args.envs, args.budget, args.exact_counts = 65536, 22, (2, 4, 2)
+    elif args.config == 4:
+        args.rows = args.cols = 64
+        args.envs, args.budget, args.exact_counts = 262144 // max(1, int(os.environ.get("WORLD_SIZE", "1"))), 22, (2, 4, 2)
 
     if args.gpus > 1 and "WORLD_SIZE" not in os.environ and args.impl == "ours":
         # convenience: the driver launches torchrun itself; a bare `python bench.py --gpus N` re-launches under it
