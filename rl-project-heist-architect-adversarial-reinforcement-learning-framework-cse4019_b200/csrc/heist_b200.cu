@@ -134,10 +134,11 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+#define SET_SMEM(E, B)                                                                                                    \
+    CUDA_TRY(cudaFuncSetAttribute(k_step_many<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_reset<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    SET_SMEM(false, false) SET_SMEM(false, true) SET_SMEM(true, false) SET_SMEM(true, true)
+#undef SET_SMEM
     CUDA_TRY(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
 
     // HeistEnvironment.__init__: bordered grid with START/VAULT, solver at start (environment.py:62-96)
@@ -201,8 +202,11 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     CUDA_TRY(cudaSetDevice(h->device));
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
     cudaStream_t s = (cudaStream_t)stream;
-    if (h->exact_only) k_reset<true><<<grid, block, h->step_smem, s>>>(h->d, mask);
-    else k_reset<false><<<grid, block, h->step_smem, s>>>(h->d, mask);
+    const bool big = h->d.R > 32;
+#define GO(E, B) k_reset<E, B><<<grid, block, h->step_smem, s>>>(h->d, mask)
+    if (h->exact_only) { if (big) GO(true, true); else GO(true, false); }
+    else { if (big) GO(false, true); else GO(false, false); }
+#undef GO
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -210,10 +214,11 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
 static void launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
                         uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
-    if (h->exact_only)
-        k_step_many<true><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
-    else
-        k_step_many<false><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj);
+    const bool big = h->d.R > 32;
+#define GO(E, B) k_step_many<E, B><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
+    if (h->exact_only) { if (big) GO(true, true); else GO(true, false); }
+    else { if (big) GO(false, true); else GO(false, false); }
+#undef GO
 }
 
 extern "C" int heist_set_mode(HeistHandle *h, int exact_only) {

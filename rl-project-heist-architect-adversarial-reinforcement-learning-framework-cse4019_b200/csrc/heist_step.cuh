@@ -51,7 +51,6 @@ struct Geo {
     int lg_spr;     // log2(slots per 256-byte row): 3, 2 or 1
     int n_maps;     // maps needed for HEIST_WARPS_PER_CTA slots
     int map_bytes;  // (R + 2) * 256
-    int w0_bytes;   // compact pristine copy per env: (R + 2) * Sx
 };
 
 __host__ __device__ inline Geo make_geo(int R, int C) {
@@ -61,7 +60,6 @@ __host__ __device__ inline Geo make_geo(int R, int C) {
     const int spr = 1 << g.lg_spr;
     g.n_maps = (HEIST_WARPS_PER_CTA + spr - 1) / spr;
     g.map_bytes = (R + 2) * MAP_STRIDE;
-    g.w0_bytes = (R + 2) * g.Sx;
     return g;
 }
 
@@ -71,7 +69,6 @@ struct WarpCtx {
     double *speed;    // [Kc] camera rotation speed
     int *rpre;        // [Kc+Kg+1] prefix sums of rays (num_rays+1) per asset
     int *g_idx;       // [Kg]
-    uint8_t *wall0;   // [(R+2)][Sx] pristine CELL_BLOCK bytes (source of the per-tick clear)
     uint8_t *cell;    // this slot's window of the shared cell map: cell[(r+1)*256 + c + 1]
     unsigned cell_sa; // shared-space address of the MAP (not the window): map + (ytile<<8 | xtile)
     int colbase;      // column offset of this slot inside the map rows
@@ -83,7 +80,6 @@ __host__ __device__ inline size_t warp_ctx_bytes(int R, int C, int Kc, int Kg) {
     b += (size_t)Kg * sizeof(int4);
     b += (size_t)Kc * sizeof(double);
     b += ((size_t)(Kc + Kg + 1) * sizeof(int) + (size_t)Kg * sizeof(int) + 15) & ~(size_t)15;
-    b += (size_t)make_geo(R, C).w0_bytes;
     return (b + 15) & ~(size_t)15;
 }
 
@@ -181,7 +177,6 @@ __device__ __forceinline__ WarpCtx carve_warp_ctx(unsigned char *smem, const Geo
     S.speed = (double *)p;  p += (size_t)Kc * sizeof(double);
     S.rpre = (int *)p;      S.g_idx = S.rpre + (Kc + Kg + 1);
     p += ((size_t)(Kc + Kg + 1) * sizeof(int) + (size_t)Kg * sizeof(int) + 15) & ~(size_t)15;
-    S.wall0 = p;
     unsigned char *map = maps + (size_t)(slot >> g.lg_spr) * g.map_bytes;
     S.colbase = (slot & ((1 << g.lg_spr) - 1)) * g.Sx;
     S.cell = map + S.colbase;
@@ -310,16 +305,38 @@ __device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, cons
     }
 }
 
-// Owner-side preparation of a visibility rebuild (DynamicVisibilityMap.update, visibility.py:31-65):
-// clear the env's window of the cell map from the pristine copy and publish the chunk count.
-__device__ __forceinline__ void begin_visibility(const WarpCtx &S, const Geo &geo, int R, CtaCtl *ctl, int warp, int lane,
-                                                 int n_assets) {
-    const int per_row = geo.Sx >> 4;  // int4 per row
-    for (int i = lane; i < (R + 2) * per_row; i += 32) {
-        const int row = i / per_row, q = i - row * per_row;
-        *reinterpret_cast<int4 *>(S.cell + row * MAP_STRIDE + q * 16) =
-            *reinterpret_cast<const int4 *>(S.wall0 + row * geo.Sx + q * 16);
+// Rows an env's rays can touch this rebuild: |row - asset row| <= vision range (a sample at distance d
+// moves at most d rows).  Bit r of the mask = grid row r.
+__device__ __forceinline__ unsigned long long dirty_rows(const WarpCtx &S, int R, int lane, int n_assets) {
+    unsigned lo = 0, hi = 0;
+    if (lane < n_assets) {
+        const AssetW &A = S.asset[lane];
+        const int rr = (A.shift == 23) ? (A.nsamp + 1) >> 1 : A.nsamp;
+        const int r0 = max(A.row - rr, 0), r1 = min(A.row + rr, R - 1);
+        const unsigned long long m = ((r1 - r0 + 1 >= 64) ? ~0ull : ((1ull << (r1 - r0 + 1)) - 1ull)) << r0;
+        lo = (unsigned)m; hi = (unsigned)(m >> 32);
     }
+    lo = __reduce_or_sync(0xffffffffu, lo);
+    hi = __reduce_or_sync(0xffffffffu, hi);
+    return ((unsigned long long)hi << 32) | lo;
+}
+
+// Owner-side preparation of a visibility rebuild (DynamicVisibilityMap.update, visibility.py:31-65):
+// strip CELL_VIS from the rows the previous rebuild could have marked (`dirty`, in/out: replaced by the rows
+// of this rebuild) and publish the chunk count.
+template <bool BIG>
+__device__ __forceinline__ void begin_visibility(const WarpCtx &S, const Geo &geo, int R, CtaCtl *ctl, int warp, int lane,
+                                                 int n_assets, unsigned long long &dirty) {
+    const int per_row = geo.Sx >> 4;  // int4 per window row
+    for (int i = lane; i < R * per_row; i += 32) {
+        const int row = i / per_row, q = i - row * per_row;
+        if (BIG && !((dirty >> row) & 1ull)) continue;
+        int4 *p = reinterpret_cast<int4 *>(S.cell + (row + 1) * MAP_STRIDE + q * 16);
+        int4 v = *p;
+        v.x &= 0x01010101; v.y &= 0x01010101; v.z &= 0x01010101; v.w &= 0x01010101;
+        *p = v;
+    }
+    if (BIG) dirty = dirty_rows(S, R, lane, n_assets);  // grids up to 32 rows: nearly every row is in range anyway
     if (lane == 0) ctl->cnt[warp] = (S.rpre[n_assets] + 31) >> 5;
 }
 
@@ -362,7 +379,6 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, const G
             w = (wall[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
             v = ((vis[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u) << 1;
         }
-        S.wall0[i] = (uint8_t)w;
         S.cell[row * MAP_STRIDE + col] = (uint8_t)(w | v);
     }
     if (lane < n_cams) {
@@ -413,22 +429,30 @@ __device__ __forceinline__ unsigned pack32(const uint8_t *p) {
 
 // row bitmaps of the visibility bits of the cell window -> dst[RW]; lane = grid row, coalesced store.
 // (The window's first byte is the ring, so the packed row is shifted down by one; ring and padding
-// bytes never carry CELL_VIS.)
-__device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, const Geo &geo, int lane, uint32_t *dst) {
+// bytes never carry CELL_VIS.)  Rows outside `dirty` cannot be lit and are written as zero unread.
+template <bool BIG>
+__device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, const Geo &geo, int lane, uint32_t *dst,
+                                         unsigned long long dirty) {
     for (int r = lane; r < D.R; r += 32) {
-        const uint8_t *row = S.cell + (r + 1) * MAP_STRIDE;
-        const unsigned lo = pack32(row);
-        const unsigned mid = geo.Sx > 32 ? pack32(row + 32) : 0u;
-        dst[r * D.W] = (lo >> 1) | (mid << 31);
-        if (D.W > 1) {
-            const unsigned hi = geo.Sx > 64 ? pack32(row + 64) : 0u;
-            dst[r * D.W + 1] = (mid >> 1) | (hi << 31);
+        unsigned w0 = 0, w1 = 0;
+        if (!BIG || ((dirty >> r) & 1ull)) {
+            const uint8_t *row = S.cell + (r + 1) * MAP_STRIDE;
+            const unsigned lo = pack32(row);
+            const unsigned mid = geo.Sx > 32 ? pack32(row + 32) : 0u;
+            w0 = (lo >> 1) | (mid << 31);
+            if (D.W > 1) {
+                const unsigned hi = geo.Sx > 64 ? pack32(row + 64) : 0u;
+                w1 = (mid >> 1) | (hi << 31);
+            }
         }
+        dst[r * D.W] = w0;
+        if (D.W > 1) dst[r * D.W + 1] = w1;
     }
 }
 
+template <bool BIG>
 __device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, const Geo &geo, int env, int lane,
-                                          const EnvRegs &E, int status, int n_cams, int n_guards) {
+                                          const EnvRegs &E, int status, int n_cams, int n_guards, unsigned long long dirty) {
     if (lane == 0) {
         int4 d0 = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
         int4 d1 = make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
@@ -441,7 +465,7 @@ __device__ __forceinline__ void store_env(const Dev &D, const WarpCtx &S, const 
         D.guard_heading[o] = S.asset[n_cams + lane].heading;
         D.guard_idx[o] = S.g_idx[lane];
     }
-    pack_vis(D, S, geo, lane, D.vis + (size_t)env * D.RW);
+    pack_vis<BIG>(D, S, geo, lane, D.vis + (size_t)env * D.RW, dirty);
 }
 
 // HeistEnvironment.reset (environment.py:183-214), owner part: solver to start, guards to waypoint 0;
@@ -527,7 +551,7 @@ __device__ __forceinline__ int step_finish(const Dev &D, const WarpCtx &S, EnvRe
 
 // T steps per launch; T = 1 with vis_traj = NULL is HeistEnvironment.step for the batch.
 // Warp slot -> env through D.slot2env (cost-balanced order built after every set_layout).
-template <bool EXACT_ONLY>
+template <bool EXACT_ONLY, bool BIG>  // BIG: more than 32 grid rows (dirty-row tracking pays off)
 __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
             double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
@@ -548,6 +572,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     const int n_assets = n_cams + n_guards;
     if (lane == 0) ctl->n_assets[warp] = n_assets;
     int status = HEIST_RUNNING;
+    unsigned long long dirty = ~0ull;  // rows that may carry CELL_VIS (everything, for the map loaded from HBM)
     int work = 0;  // 32-ray chunks this env asked for during the launch (measured load-balance cost)
     const int chunks = have ? (S.rpre[n_assets] + 31) >> 5 : 0;
     for (int t = 0; t < T; ++t) {
@@ -568,7 +593,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
                 if (!__syncthreads_or(mine)) break;
                 if (mine) reset_state(D, S, env, lane, E, n_cams, n_guards);
             }
-            if (mine) { begin_visibility(S, geo, D.R, ctl, warp, lane, n_assets); work += chunks; }
+            if (mine) { begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_assets, dirty); work += chunks; }
             else if (lane == 0) ctl->cnt[warp] = 0;
             if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
             __syncthreads();
@@ -587,16 +612,16 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
                 }
             }
         }
-        if (vis_traj && have) pack_vis(D, S, geo, lane, vis_traj + o * D.RW);
+        if (vis_traj && have) pack_vis<BIG>(D, S, geo, lane, vis_traj + o * D.RW, dirty);
     }
     if (have) {
-        store_env(D, S, geo, env, lane, E, status, n_cams, n_guards);
+        store_env<BIG>(D, S, geo, env, lane, E, status, n_cams, n_guards, dirty);
         // feed the measured work (resets included) back into the slot order of the next launch
         if (lane == 0 && T >= 8) D.cost[env] = (int)(((long long)work * 256) / T) + 16;
     }
 }
 
-template <bool EXACT_ONLY>
+template <bool EXACT_ONLY, bool BIG>
 __global__ void __launch_bounds__(HEIST_WARPS_PER_CTA * 32, 8)
 k_reset(Dev D, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -610,10 +635,11 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
     const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams = 0, n_guards = 0;
+    unsigned long long dirty = ~0ull;
     if (have) {
         load_env(D, S, geo, env, lane, E, n_cams, n_guards);
         reset_state(D, S, env, lane, E, n_cams, n_guards);
-        begin_visibility(S, geo, D.R, ctl, warp, lane, n_cams + n_guards);
+        begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_cams + n_guards, dirty);
     } else if (lane == 0) ctl->cnt[warp] = 0;
     if (lane == 0) ctl->n_assets[warp] = n_cams + n_guards;
     if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
@@ -621,7 +647,7 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
     march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
     if (have) {
         end_visibility(S, lane, n_cams, n_cams + n_guards);
-        store_env(D, S, geo, env, lane, E, HEIST_RUNNING, n_cams, n_guards);
+        store_env<BIG>(D, S, geo, env, lane, E, HEIST_RUNNING, n_cams, n_guards, dirty);
     }
 }
 
