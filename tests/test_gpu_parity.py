@@ -453,3 +453,87 @@ def test_debug_bounds_build_reports_no_out_of_range_access():
                          capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout + res.stderr
     assert res.stdout.count("ok") == 4
+
+
+def _wild_layout(rng, R, C):
+    """Explicit layouts far outside the Architect's ranges: wide/narrow fov, long ranges, negative and
+    fractional speeds, many cameras, long custom patrols with strides, guards on walls/borders."""
+    walls = [(int(rng.integers(0, R)), int(rng.integers(0, C))) for _ in range(int(rng.integers(0, 40)))]
+    cams = []
+    for _ in range(int(rng.integers(0, 13))):
+        kind = rng.integers(0, 4)
+        fov = [float(rng.uniform(1, 359)), float(rng.choice([10, 15, 180, 270, 359, 360])), float(np.float32(rng.uniform(30, 120))),
+               float(rng.choice([60, 90, 120]))][kind]
+        cams.append({"row": int(rng.integers(-1, R + 1)), "col": int(rng.integers(-1, C + 1)), "fov_angle": fov,
+                     "heading": float(rng.choice([0, 90, 45.5, -30, 725.25, float(rng.uniform(-400, 800))])),
+                     "rotation_speed": float(rng.choice([0, 15, -15, 0.1, 359.9, -720.5, float(rng.uniform(-50, 50))])),
+                     "vision_range": int(rng.choice([0, 1, 2, 3, 6, 6, 9, 13]))})
+    guards = []
+    for _ in range(int(rng.integers(0, 5))):
+        L = int(rng.integers(1, 17))
+        path = [(int(rng.integers(0, R)), int(rng.integers(0, C))) for _ in range(L)]
+        guards.append({"patrol_path": path, "speed": int(rng.choice([1, 1, 2, 3, 5, -1, -2, 0])),
+                       "vision_range": int(rng.choice([0, 1, 4, 4, 7, 10])),
+                       "fov_angle": float(rng.choice([90.0, 90.0, 45.0, 200.0, 13.7, 360.0]))})
+    return walls, cams, guards
+
+
+@pytest.mark.parametrize("R,C,N,T,seed", [(20, 20, 96, 60, 1), (33, 47, 48, 40, 2), (64, 64, 32, 30, 3), (7, 64, 32, 40, 4),
+                                           (64, 5, 32, 40, 5)])
+def test_wild_explicit_layouts_match_oracle(R, C, N, T, seed):
+    rng = np.random.default_rng(1000 + seed)
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=17, start_pos=(1, 1))
+    env = BatchedHeistEnv(cfg, N, max_walls=64, max_cams=16, max_guards=8, max_path=16)
+    lays = [_wild_layout(rng, R, C) for _ in range(N)]
+    budgets = rng.choice([3, 15, 40, 200], N).astype(np.int32)
+    valid = env.set_layout_explicit(lays, budget=budgets).cpu().numpy()
+    env.check_errors()
+    oenvs = []
+    for (w, c, g), b in zip(lays, budgets):
+        e = ho.OracleEnv(R, C, max_steps=17, budget=int(b))
+        oenvs.append(e)
+        assert e.set_layout(w, c, g) == valid[len(oenvs) - 1], len(oenvs) - 1
+    assert np.array_equal(env.tile_codes.cpu().numpy(), np.stack([e.grid for e in oenvs]).astype(np.uint8))
+    assert env.budget_spent.cpu().tolist() == [e.info()["spent"] for e in oenvs]
+    env.reset()
+    ho.reset_all(oenvs)
+    assert np.array_equal(u32(env.visibility_bits), np.stack([ho.pack_bits(e.visibility) for e in oenvs]))
+    acts = synthetic.sample_actions(rng, T, N)
+    res = []
+    for exact in (False, True):
+        env.set_exact_only(exact)
+        env.set_layout_explicit(lays, budget=budgets)
+        env.reset()
+        out = env.step_many(acts, autoreset=True, want_vis=True)
+        res.append({k: v.clone() for k, v in out.items()})
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    for out in res:
+        assert np.array_equal(out["done"].cpu().numpy(), ref["done"])
+        assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
+        assert np.array_equal(out["reward"].cpu().numpy(), ref["reward"])
+        assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+    info = [e.info() for e in oenvs]
+    ch, gh, gx = env.cam_heading.cpu().numpy(), env.guard_heading.cpu().numpy(), env.guard_idx.cpu().numpy()
+    for j, e in enumerate(oenvs):
+        assert np.array_equal(ch[j, :info[j]["n_cams"]], e.cam_headings()), j
+        gs, ghead = e.guards_state()
+        assert np.array_equal(gx[j, :info[j]["n_guards"]], gs[:, 2]) and np.array_equal(gh[j, :info[j]["n_guards"]], ghead), j
+    assert np.array_equal(env.observe().cpu().numpy(), np.stack([e.state_tensor() for e in oenvs]))
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 7, 130])
+def test_env_counts_not_multiple_of_cta(N):
+    cfg = EnvironmentConfig(max_steps=40)
+    env = BatchedHeistEnv(cfg, N)
+    rng = np.random.default_rng(N)
+    am, cp = synthetic.sample_asset_maps(rng, N, 20, 20), synthetic.sample_cam_params(rng, N)
+    env.set_layout_from_asset_map(am, cp, 15)
+    oenvs, _ = oracle_envs(am, cp, cfg, 15)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, 70, N)
+    out = env.step_many(acts, autoreset=True, want_vis=True)
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
+    assert np.array_equal(out["reward"].cpu().numpy(), ref["reward"])
+    assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
