@@ -154,6 +154,23 @@ int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int autoreset,
 int heist_observe(HeistHandle *h, float *state, void *stream);
 
 /*
+ * One tick plus the dense state the policy needs next, in one call: HeistEnvironment.step followed by
+ * get_state_tensor (the trainer's inner loop, training.py:523-529), with the optional `if done: reset()`
+ * applied before the state is built.  state [N][3][R][C] float32.
+ */
+int heist_step_observe(HeistHandle *h, const int8_t *actions, int autoreset, float *reward, uint8_t *done,
+                       uint8_t *status, float *state, void *stream);
+
+/*
+ * Dense states for a PPO minibatch from a PACKED rollout buffer (agents/solver.py:134,165 keep and gather dense
+ * (3,R,C) float32 states; here a transition is its visibility bitmap + solver position).  For m < M:
+ * vis_bits [M][R*W], pos [M] = row | col << 16, env_idx [M] = env whose layout (tile codes) applies
+ * -> state [M][3][R][C], identical to what heist_observe produced when the transition was recorded.
+ */
+int heist_expand_states(HeistHandle *h, const uint32_t *vis_bits, const int32_t *pos, const int32_t *env_idx, int M,
+                        float *state, void *stream);
+
+/*
  * HeistEnvironment._get_observation small vectors (environment.py:324-337):
  * obs_vec [N][5] float32 = solver_position(2), vault_direction(2), time_feature(1).
  * occupancy_grid and visibility_map are channels 0 and 1 of heist_observe.

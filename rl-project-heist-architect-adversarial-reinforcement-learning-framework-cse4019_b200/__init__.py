@@ -15,3 +15,4 @@ build = _build_mod.build
 __all__ = ["BatchedHeistEnv", "EnvironmentConfig", "HeistEnvironment", "RolloutBuffer", "compute_gae",
            "normalize_advantages", "STATUS_NAMES", "dist", "build", "load_library", "lib_path"]
 from . import synthetic  # noqa: F401,E402
+from . import ppo  # noqa: F401,E402

@@ -41,6 +41,8 @@ EXPORTS = {
     "heist_step_many": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "heist_observe": (C.c_int, [c_vp, c_vp, c_vp]),
     "heist_observation_vectors": (C.c_int, [c_vp, c_vp, c_vp]),
+    "heist_step_observe": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "heist_expand_states": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, c_vp, c_vp]),
     "heist_get_state": (C.c_int, [c_vp, C.POINTER(HeistStateView)]),
     "heist_gae": (C.c_int, [c_vp, c_vp, c_vp, C.c_int, C.c_int, C.c_double, C.c_double, c_vp, c_vp, C.c_int, c_vp]),
     "heist_architect_reward": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),

@@ -270,6 +270,33 @@ class BatchedHeistEnv:
         self._keep_a = a
         return out
 
+    def step_observe(self, actions, autoreset=True, state_out=None):
+        """One tick + the dense state for the next policy forward (training.py:523-529 for the batch).
+        -> reward [N] f32, done [N] bool, status [N] u8, state [N,3,R,C] f32 (after the auto-reset, if any)."""
+        a = self._dev(actions, torch.int8)
+        N = self.num_envs
+        reward = torch.empty(N, dtype=torch.float32, device=self.device)
+        done = torch.empty(N, dtype=torch.uint8, device=self.device)
+        status = torch.empty(N, dtype=torch.uint8, device=self.device)
+        if state_out is None:
+            state_out = torch.empty((N, 3, self.R, self.C), dtype=torch.float32, device=self.device)
+        _ffi.check(self._lib.heist_step_observe(self._h, _ptr(a), int(autoreset), _ptr(reward), _ptr(done), _ptr(status),
+                                                _ptr(state_out), self._stream()), "heist_step_observe")
+        return reward, done.bool(), status, state_out
+
+    def expand_states(self, vis_bits, pos, env_idx, out=None):
+        """Dense [M,3,R,C] states from packed transitions (visibility bitmap, row|col<<16, env index)."""
+        vb = vis_bits.contiguous().view(-1, self.R, self.W)
+        M = vb.shape[0]
+        p = pos.contiguous().view(-1).to(torch.int32)
+        e = env_idx.contiguous().view(-1).to(torch.int32)
+        assert p.numel() == M and e.numel() == M and vb.dtype == torch.int32
+        if out is None:
+            out = torch.empty((M, 3, self.R, self.C), dtype=torch.float32, device=self.device)
+        _ffi.check(self._lib.heist_expand_states(self._h, _ptr(vb), _ptr(p), _ptr(e), M, _ptr(out), self._stream()),
+                   "heist_expand_states")
+        return out
+
     # ------------------------------------------------------------------ observations
     def observe(self, out=None):
         """get_state_tensor for the batch: [N,3,R,C] float32 (environment.py:347-374)."""

@@ -274,6 +274,29 @@ extern "C" int heist_observe(HeistHandle *h, float *state, void *stream) {
     return 0;
 }
 
+extern "C" int heist_step_observe(HeistHandle *h, const int8_t *actions, int autoreset, float *reward, uint8_t *done,
+                                  uint8_t *status, float *state, void *stream) {
+    if (!h || !actions || !state) return fail(-1, "heist_step_observe: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    launch_step(h, actions, 1, autoreset, reward, nullptr, done, status, nullptr, (cudaStream_t)stream);
+    CUDA_TRY(cudaGetLastError());
+    return heist_observe(h, state, stream);
+}
+
+extern "C" int heist_expand_states(HeistHandle *h, const uint32_t *vis_bits, const int32_t *pos, const int32_t *env_idx,
+                                   int M, float *state, void *stream) {
+    if (!h || !vis_bits || !pos || !env_idx || !state) return fail(-1, "heist_expand_states: null argument");
+    if (M < 0) return fail(-9, "heist_expand_states: negative M");
+    if (M == 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const Dev &d = h->d;
+    const int bx = (3 * d.RC + 255) / 256;
+    const int by = M < 148 * 16 ? M : 148 * 16;
+    k_expand_states<<<dim3(bx, by), 256, 0, (cudaStream_t)stream>>>(d, vis_bits, pos, env_idx, M, state);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int heist_observation_vectors(HeistHandle *h, float *obs_vec, void *stream) {
     if (!h || !obs_vec) return fail(-1, "heist_observation_vectors: null argument");
     CUDA_TRY(cudaSetDevice(h->device));

@@ -54,6 +54,33 @@ __global__ void __launch_bounds__(1024) k_observe_vec4(Dev D, float4 *__restrict
     }
 }
 
+// Minibatch assembly from a packed rollout buffer (agents/solver.py:155-169 gathers dense states; here the
+// buffer keeps 4*R*W + 4 bytes per transition and the dense [M][3][R][C] states are rebuilt on demand):
+// transition m = (visibility bitmap vis[m], solver position pos[m] = row | col << 16, env env_idx[m] whose
+// static tile codes give channel 0).  Same arithmetic as k_observe_*; one thread per cell.
+__global__ void __launch_bounds__(256)
+k_expand_states(Dev D, const uint32_t *__restrict__ vis, const int32_t *__restrict__ pos, const int32_t *__restrict__ env_idx,
+                int M, float *__restrict__ out) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= 3 * D.RC) return;
+    const int ch = (q >= D.RC) + (q >= 2 * D.RC);
+    const int cell = q - ch * D.RC;
+    const int r = cell / D.C, c = cell - r * D.C;
+    const int vcell = D.vault_r * D.C + D.vault_c;
+    const float g = D.pos_tab[cell];
+    for (int m = blockIdx.y; m < M; m += gridDim.y) {
+        float v;
+        if (ch == 0) v = __fdiv_rn((float)D.tile[(size_t)env_idx[m] * D.RC + cell], 5.0f);
+        else if (ch == 1) v = (float)((vis[(size_t)m * D.RW + r * D.W + (c >> 5)] >> (c & 31)) & 1u);
+        else {
+            const int p = pos[m];
+            const int scell = (p & 0xffff) * D.C + (p >> 16);
+            v = __fadd_rn((cell == vcell) ? -1.0f : ((cell == scell) ? 1.0f : 0.0f), g);
+        }
+        __stcs(out + (size_t)m * 3 * D.RC + q, v);
+    }
+}
+
 // Scalar fallback for C % 4 != 0.
 __global__ void __launch_bounds__(256) k_observe_scalar(Dev D, float *__restrict__ out) {
     const long long total = (long long)D.N * 3 * D.RC;

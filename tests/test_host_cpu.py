@@ -150,3 +150,18 @@ def test_gloo_world_size_2(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_ppo_host_helpers_on_cpu():
+    from heist_b200 import ppo
+    logits = torch.full((2, 4, 5, 6), -1e4)
+    want = torch.randint(0, 4, (2, 5, 6))
+    logits.scatter_(1, want[:, None], 1e4)
+    am, logp = ppo.architect_sample(logits, temperature=0.7)
+    assert am.dtype == torch.int8 and torch.equal(am.long(), want) and logp.abs().max() < 1e-3
+    h = (torch.ones(1, 3, 4), torch.ones(1, 3, 4))
+    kept = ppo._mask_hidden(h, torch.tensor([True, False, True]))
+    assert kept[0][0, 1].sum() == 0 and kept[1][0, 0].sum() == 4
+    cp = ppo.camera_params_tensor({"fov": torch.tensor([[60.0]]), "speed": torch.tensor([[15.0]]),
+                                   "heading": torch.tensor([[90.0]])})
+    assert cp.tolist() == [[60.0, 15.0, 90.0]]
