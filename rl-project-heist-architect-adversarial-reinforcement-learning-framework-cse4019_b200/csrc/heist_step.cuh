@@ -147,14 +147,14 @@ __device__ __noinline__ void ray_exact(const AssetW *asset, int k, unsigned map_
 
 // ---------------------------------------------------------------------------------------------
 // CTA-cooperative ray-march.  The rays of all envs of the CTA are marched by all of its warps:
-// every phase the owners publish how many 32-ray chunks their env needs, and warps grab chunks from
-// one shared counter until none are left.  (Envs differ several-fold in rays per tick -- and a reset
+// every phase the owners publish how many 32-ray chunks their env needs, and the chunks of every env are
+// dealt round-robin over the warps.  (Envs differ several-fold in rays per tick -- and a reset
 // doubles a tick's work -- so a one-warp-per-env march leaves most of the SM idle behind its slowest
 // warp.)
 // ---------------------------------------------------------------------------------------------
 #define PEND_CAP 480
 struct CtaCtl {
-    int next;                       // chunk counter of the current phase
+    int spare;
     int pend_n;                     // rays handed to the exact path this phase
     int cnt[HEIST_WARPS_PER_CTA];   // 32-ray chunks wanted by each env slot this phase (0: none)
     int n_assets[HEIST_WARPS_PER_CTA];
@@ -213,12 +213,12 @@ __device__ __forceinline__ void dbg_init(const Dev &D, unsigned char *smem, cons
     }
 
 // March flattened rays [f0, f0+32) of env slot e (asset table `asset`, ray prefix sums `rpre`).
+// `k` is the lane's asset cursor: a warp walks an env's chunks in increasing order, so the scan resumes.
 template <bool EXACT_ONLY>
-__device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *asset, const int *rpre, int n_assets, int f0,
-                                            int lane, unsigned map_sa, int colbase, double deg2rad) {
+__device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *asset, const int *rpre, int total_rays, int f0,
+                                            int lane, unsigned map_sa, int colbase, double deg2rad, int &k) {
     const int f = f0 + lane;
-    if (f >= rpre[n_assets]) return;
-    int k = 0;
+    if (f >= total_rays) return;
     while (f >= rpre[k + 1]) ++k;
     const int ri = f - rpre[k];
     if (EXACT_ONLY) { ray_exact(asset, k, map_sa, colbase, deg2rad, ri, 1); return; }
@@ -272,23 +272,24 @@ __device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *as
 template <bool EXACT_ONLY>
 __device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, const Geo &geo, int warp, int ctx_bytes,
                                             CtaCtl *ctl, int lane) {
-    const int p1 = ctl->cnt[0], p2 = p1 + ctl->cnt[1], p3 = p2 + ctl->cnt[2], total = p3 + ctl->cnt[3];
-    const unsigned next_sa = (unsigned)__cvta_generic_to_shared(&ctl->next);
     const unsigned map0_sa = S.cell_sa - (unsigned)((warp >> geo.lg_spr) * geo.map_bytes);
-    for (;;) {
-        int g = 0;
-        if (lane == 0) asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(g) : "r"(next_sa) : "memory");
-        g = __shfl_sync(0xffffffffu, g, 0);
-        if (g >= total) break;
-        const int e = (g >= p1) + (g >= p2) + (g >= p3);
-        const int c = g - (e == 0 ? 0 : (e == 1 ? p1 : (e == 2 ? p2 : p3)));
+    // Static deal: chunk c of env slot e goes to warp (c + e) & 3.  No shared counter (ptxas turns a
+    // shared atomicAdd into a ~20-instruction aggregate), no per-chunk slot decode, and the per-env pointers
+    // and the lanes' asset cursors are set up once per env instead of once per chunk.
+#pragma unroll 1
+    for (int e = 0; e < HEIST_WARPS_PER_CTA; ++e) {
+        const int cnt = ctl->cnt[e];
+        if (cnt == 0) continue;
         // every slot's context has the same layout: shift this warp's own pointers by whole contexts
         const int delta = (e - warp) * ctx_bytes;
         const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
         const int *rpre = reinterpret_cast<const int *>(reinterpret_cast<const unsigned char *>(S.rpre) + delta);
         const unsigned map_sa = map0_sa + (unsigned)((e >> geo.lg_spr) * geo.map_bytes);
         const int colbase = (e & ((1 << geo.lg_spr) - 1)) * geo.Sx;
-        march_chunk<EXACT_ONLY>(ctl, e, asset, rpre, ctl->n_assets[e], c * 32, lane, map_sa, colbase, D.deg2rad);
+        const int total_rays = rpre[ctl->n_assets[e]];
+        int k = 0;
+        for (int c = (warp - e) & (HEIST_WARPS_PER_CTA - 1); c < cnt; c += HEIST_WARPS_PER_CTA)
+            march_chunk<EXACT_ONLY>(ctl, e, asset, rpre, total_rays, c * 32, lane, map_sa, colbase, D.deg2rad, k);
     }
     __syncthreads();
     if (!EXACT_ONLY) {
@@ -595,7 +596,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
             }
             if (mine) { begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_assets, dirty); work += chunks; }
             else if (lane == 0) ctl->cnt[warp] = 0;
-            if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
+            if (threadIdx.x == 0) ctl->pend_n = 0;
             __syncthreads();
             march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
             if (mine) end_visibility(S, lane, n_cams, n_assets);
@@ -642,7 +643,7 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
         begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_cams + n_guards, dirty);
     } else if (lane == 0) ctl->cnt[warp] = 0;
     if (lane == 0) ctl->n_assets[warp] = n_cams + n_guards;
-    if (threadIdx.x == 0) { ctl->next = 0; ctl->pend_n = 0; }
+    if (threadIdx.x == 0) ctl->pend_n = 0;
     __syncthreads();
     march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
     if (have) {
