@@ -158,6 +158,7 @@ struct CtaCtl {
     int pend_n;                     // rays handed to the exact path this phase
     int cnt[HEIST_WARPS_PER_CTA];   // 32-ray chunks wanted by each env slot this phase (0: none)
     int n_assets[HEIST_WARPS_PER_CTA];
+    int active[HEIST_WARPS_PER_CTA];  // owner still has ticks to run (step_many)
     int pad[2];
     unsigned pend[PEND_CAP];        // slot:2 | asset:6 | sample j:8 | ray:16
 };
@@ -576,44 +577,51 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     unsigned long long dirty = ~0ull;  // rows that may carry CELL_VIS (everything, for the map loaded from HBM)
     int work = 0;  // 32-ray chunks this env asked for during the launch (measured load-balance cost)
     const int chunks = have ? (S.rpre[n_assets] + 31) >> 5 : 0;
-    for (int t = 0; t < T; ++t) {
-        const size_t o = (size_t)t * D.N + (have ? env : 0);
-        const bool live = have && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
-        // Two cooperative phases per tick through ONE copy of the march code (instruction cache):
-        // phase 0 = the step's visibility rebuild, phase 1 = the rebuild after an auto-reset
-        // (the trainer's `if done: reset()`), entered only if some env of the CTA needs it.
-#pragma unroll 1
-        for (int phase = 0; phase < 2; ++phase) {
-            bool mine;
-            if (phase == 0) {
-                // ---- owner: move / rotate / patrol ----
-                mine = live;
-                if (live) step_begin(D, S, env, lane, E, n_cams, n_guards, actions[o]);
-            } else {
-                mine = autoreset && have && (E.flags & F_DONE);
-                if (!__syncthreads_or(mine)) break;
-                if (mine) reset_state(D, S, env, lane, E, n_cams, n_guards);
+    // Every loop iteration is one cooperative visibility rebuild for the whole CTA, but the envs of a CTA are
+    // NOT in lock-step: each owner advances its own tick `t` and asks for whatever rebuild it needs next -- the
+    // one of its next step, or the one of the auto-reset that follows a finished episode (the trainer's
+    // `if done: reset()`).  Iterations per launch = max over the CTA's envs of (T + resets) instead of
+    // T + (ticks in which any of them resets), and the march code exists once (instruction cache).
+    int t = 0;
+    bool pending_reset = false;
+    for (;;) {
+        const bool active = have && t < T;
+        int kind = 0;  // 0: no rebuild (env already done / finished), 1: step, 2: reset
+        if (active) {
+            if (pending_reset) { reset_state(D, S, env, lane, E, n_cams, n_guards); kind = 2; }
+            else if (!(E.flags & F_DONE)) {  // a done env is not mutated (:232-233)
+                step_begin(D, S, env, lane, E, n_cams, n_guards, actions[(size_t)t * D.N + env]);
+                kind = 1;
             }
-            if (mine) { begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_assets, dirty); work += chunks; }
-            else if (lane == 0) ctl->cnt[warp] = 0;
-            if (threadIdx.x == 0) ctl->pend_n = 0;
-            __syncthreads();
-            march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
-            if (mine) end_visibility(S, lane, n_cams, n_assets);
-            if (phase == 0) {
-                // ---- owner: rewards, termination, outputs ----
+        }
+        if (kind) { begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_assets, dirty); work += chunks; }
+        else if (lane == 0) ctl->cnt[warp] = 0;
+        if (lane == 0) ctl->active[warp] = active;
+        if (threadIdx.x == 0) ctl->pend_n = 0;
+        __syncthreads();
+        if (!(ctl->active[0] | ctl->active[1] | ctl->active[2] | ctl->active[3])) break;  // CTA-uniform
+        march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
+        if (active) {
+            const size_t o = (size_t)t * D.N + env;
+            if (kind) end_visibility(S, lane, n_cams, n_assets);
+            if (kind != 2) {
+                // ---- owner: rewards, termination, outputs of step t ----
                 double rw = 0.0;
                 status = HEIST_ALREADY_DONE;
-                if (live) status = step_finish(D, S, E, rw);
-                if (have && lane == 0) {
+                if (kind == 1) status = step_finish(D, S, E, rw);
+                if (lane == 0) {
                     if (reward) reward[o] = (float)rw;
                     if (reward64) reward64[o] = rw;
                     if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
                     if (status_out) status_out[o] = (uint8_t)status;
                 }
+                pending_reset = autoreset && (E.flags & F_DONE);
+            } else pending_reset = false;
+            if (!pending_reset) {  // tick t is complete: its visibility map is final
+                if (vis_traj) pack_vis<BIG>(D, S, geo, lane, vis_traj + o * D.RW, dirty);
+                ++t;
             }
         }
-        if (vis_traj && have) pack_vis<BIG>(D, S, geo, lane, vis_traj + o * D.RW, dirty);
     }
     if (have) {
         store_env<BIG>(D, S, geo, env, lane, E, status, n_cams, n_guards, dirty);
