@@ -154,7 +154,7 @@ __device__ __noinline__ void ray_exact(const AssetW *asset, int k, unsigned map_
 // ---------------------------------------------------------------------------------------------
 #define PEND_CAP 480
 struct CtaCtl {
-    int spare;
+    int taken;                      // exact-path queue entries already claimed by a draining warp
     int pend_n;                     // rays handed to the exact path this phase
     int cnt[HEIST_WARPS_PER_CTA];   // 32-ray chunks wanted by each env slot this phase (0: none)
     int n_assets[HEIST_WARPS_PER_CTA];
@@ -267,6 +267,22 @@ __device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *as
     }
 }
 
+#define PEND_EMPTY 0xffffffffu
+// Take queue entry i (spin until its producer has written it), hand it back as empty, run the exact path.
+template <bool EXACT_ONLY>
+__device__ __forceinline__ void drain_one(const Dev &D, const WarpCtx &S, const Geo &geo, int warp, int ctx_bytes,
+                                          CtaCtl *ctl, unsigned map0_sa, int i) {
+    volatile unsigned *pe = &ctl->pend[i];
+    unsigned p;
+    while ((p = *pe) == PEND_EMPTY) {}
+    *pe = PEND_EMPTY;
+    const int e = p >> 30, k = (p >> 24) & 63, j = (p >> 16) & 255, ri = p & 0xffff;
+    const int delta = (e - warp) * ctx_bytes;
+    const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
+    const unsigned map_sa = map0_sa + (unsigned)((e >> geo.lg_spr) * geo.map_bytes);
+    ray_exact(asset, k, map_sa, (e & ((1 << geo.lg_spr) - 1)) * geo.Sx, D.deg2rad, ri, j);
+}
+
 // One cooperative phase: all warps of the CTA drain the chunk queue, then (after a barrier) the
 // rays that were handed to the exact path.  Must be entered by every warp after a __syncthreads()
 // that follows the owners' writes to ctl / cell maps; ends with a __syncthreads().
@@ -292,18 +308,30 @@ __device__ __forceinline__ void march_phase(const Dev &D, const WarpCtx &S, cons
         for (int c = (warp - e) & (HEIST_WARPS_PER_CTA - 1); c < cnt; c += HEIST_WARPS_PER_CTA)
             march_chunk<EXACT_ONLY>(ctl, e, asset, rpre, total_rays, c * 32, lane, map_sa, colbase, D.deg2rad, k);
     }
+    if (!EXACT_ONLY) {
+        // Opportunistic drain of the exact-path queue by warps that ran out of chunks: the long fp64 dependency
+        // chains of ray_exact overlap the other warps' marching instead of sitting between two barriers.
+        // An entry is its own ready flag (PEND_EMPTY until the producer's store lands).
+        for (;;) {
+            int old = 0, cnt = 0;
+            if (lane == 0) {
+                old = *(volatile int *)&ctl->taken;
+                cnt = min(32, min(*(volatile int *)&ctl->pend_n, PEND_CAP) - old);
+                if (cnt > 0 && atomicCAS(&ctl->taken, old, old + cnt) != old) cnt = -1;  // lost the race: retry
+            }
+            old = __shfl_sync(0xffffffffu, old, 0);
+            cnt = __shfl_sync(0xffffffffu, cnt, 0);
+            if (cnt == 0) break;
+            if (cnt > 0 && lane < cnt) drain_one<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, map0_sa, old + lane);
+        }
+    }
     __syncthreads();
     if (!EXACT_ONLY) {
-        const int P = min(ctl->pend_n, PEND_CAP);
-        for (int i = threadIdx.x; i < P; i += HEIST_WARPS_PER_CTA * 32) {
-            const unsigned p = ctl->pend[i];
-            const int e = p >> 30, k = (p >> 24) & 63, j = (p >> 16) & 255, ri = p & 0xffff;
-            const int delta = (e - warp) * ctx_bytes;
-            const AssetW *asset = reinterpret_cast<const AssetW *>(reinterpret_cast<const unsigned char *>(S.asset) + delta);
-            const unsigned map_sa = map0_sa + (unsigned)((e >> geo.lg_spr) * geo.map_bytes);
-            ray_exact(asset, k, map_sa, (e & ((1 << geo.lg_spr) - 1)) * geo.Sx, D.deg2rad, ri, j);
-        }
-        if (P > 0) __syncthreads();  // P is CTA-uniform (read after the barrier above)
+        // entries pushed after the last look above (CTA-uniform values: read after the barrier)
+        const int P = min(ctl->pend_n, PEND_CAP), T0 = ctl->taken;
+        for (int i = T0 + threadIdx.x; i < P; i += HEIST_WARPS_PER_CTA * 32)
+            drain_one<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, map0_sa, i);
+        if (P > T0) __syncthreads();
     }
 }
 
@@ -564,6 +592,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     const Geo geo = make_geo(D.R, D.C);
     const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     dbg_init(D, smem, geo);
+    for (int i = threadIdx.x; i < PEND_CAP; i += HEIST_WARPS_PER_CTA * 32) ctl->pend[i] = PEND_EMPTY;
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
     const bool have = env >= 0;
     const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
@@ -597,7 +626,7 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
         if (kind) { begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_assets, dirty); work += chunks; }
         else if (lane == 0) ctl->cnt[warp] = 0;
         if (lane == 0) ctl->active[warp] = active;
-        if (threadIdx.x == 0) ctl->pend_n = 0;
+        if (threadIdx.x == 0) { ctl->pend_n = 0; ctl->taken = 0; }
         __syncthreads();
         if (!(ctl->active[0] | ctl->active[1] | ctl->active[2] | ctl->active[3])) break;  // CTA-uniform
         march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
@@ -638,6 +667,7 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
     CtaCtl *ctl = reinterpret_cast<CtaCtl *>(smem);
     const Geo geo = make_geo(D.R, D.C);
     dbg_init(D, smem, geo);
+    for (int i = threadIdx.x; i < PEND_CAP; i += HEIST_WARPS_PER_CTA * 32) ctl->pend[i] = PEND_EMPTY;
     const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
     const bool have = env >= 0 && (!mask || mask[env]);
@@ -651,7 +681,7 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
         begin_visibility<BIG>(S, geo, D.R, ctl, warp, lane, n_cams + n_guards, dirty);
     } else if (lane == 0) ctl->cnt[warp] = 0;
     if (lane == 0) ctl->n_assets[warp] = n_cams + n_guards;
-    if (threadIdx.x == 0) ctl->pend_n = 0;
+    if (threadIdx.x == 0) { ctl->pend_n = 0; ctl->taken = 0; }
     __syncthreads();
     march_phase<EXACT_ONLY>(D, S, geo, warp, ctx_bytes, ctl, lane);
     if (have) {
