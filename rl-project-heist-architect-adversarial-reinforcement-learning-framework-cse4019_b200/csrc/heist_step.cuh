@@ -28,6 +28,7 @@
 #define CELL_VIS 2u    // under surveillance this tick
 
 #define MAP_STRIDE 256  // bytes per map row: offset = (ytile << 8) | xtile is one PRMT of the 8.24 positions
+#define RING 2          // blocking cells around the grid: 1 ends every ray, the 2nd keeps the load of the NEXT sample in the map
 
 // Per-asset (camera or guard) working record in shared memory (64 bytes).
 struct __align__(16) AssetW {
@@ -47,19 +48,19 @@ struct __align__(16) AssetW {
 // blocking cells (so an out-of-bounds sample needs no bounds test) and a 256-byte row stride; the envs
 // of a CTA sit side by side in the rows: slot e uses columns [colbase, colbase + Sx) of map e >> lg_spr.
 struct Geo {
-    int Sx;         // slot width: 32, 64 or 128 bytes (>= C + 2)
+    int Sx;         // slot width: 32, 64 or 128 bytes (>= C + 2 * RING)
     int lg_spr;     // log2(slots per 256-byte row): 3, 2 or 1
     int n_maps;     // maps needed for HEIST_WARPS_PER_CTA slots
-    int map_bytes;  // (R + 2) * 256
+    int map_bytes;  // (R + 2 * RING) * 256
 };
 
 __host__ __device__ inline Geo make_geo(int R, int C) {
     Geo g;
-    g.Sx = (C + 2 <= 32) ? 32 : ((C + 2 <= 64) ? 64 : 128);
+    g.Sx = (C + 2 * RING <= 32) ? 32 : ((C + 2 * RING <= 64) ? 64 : 128);
     g.lg_spr = (g.Sx == 32) ? 3 : ((g.Sx == 64) ? 2 : 1);
     const int spr = 1 << g.lg_spr;
     g.n_maps = (HEIST_WARPS_PER_CTA + spr - 1) / spr;
-    g.map_bytes = (R + 2) * MAP_STRIDE;
+    g.map_bytes = (R + 2 * RING) * MAP_STRIDE;
     return g;
 }
 
@@ -69,7 +70,7 @@ struct WarpCtx {
     double *speed;    // [Kc] camera rotation speed
     int *rpre;        // [Kc+Kg+1] prefix sums of rays (num_rays+1) per asset
     int *g_idx;       // [Kg]
-    uint8_t *cell;    // this slot's window of the shared cell map: cell[(r+1)*256 + c + 1]
+    uint8_t *cell;    // this slot's window of the shared cell map: cell[(r+RING)*256 + c + RING]
     unsigned cell_sa; // shared-space address of the MAP (not the window): map + (ytile<<8 | xtile)
     int colbase;      // column offset of this slot inside the map rows
 };
@@ -139,7 +140,7 @@ __device__ __noinline__ void ray_exact(const AssetW *asset, int k, unsigned map_
         int r = rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
         // consecutive samples move by at most one tile per axis, so the first out-of-bounds sample
         // always lands on the blocking ring
-        unsigned off = (unsigned)(((r + 1) << 8) + c + 1 + colbase);
+        unsigned off = (unsigned)(((r + RING) << 8) + c + RING + colbase);
         if (lds_u8(map_sa + off) == CELL_BLOCK) return;
         if (off != A.own) sts_u8(map_sa + off, CELL_VIS);
     }
@@ -196,21 +197,26 @@ __device__ __forceinline__ void dbg_init(const Dev &D, unsigned char *smem, cons
 #endif
 }
 
-// One fast-path sample; `J` is the 1-based sample index (a literal in the unrolled variants).
-// `break`s out of the enclosing loop when the ray ends: blocked, or ambiguous (amb_j = J; the rare
-// hand-over to the exact path is done once, after the loop, to keep the unrolled code small).
-#define HEIST_SAMPLE(J, CHECK_OWN)                                                                                    \
+// One fast-path sample, software-pipelined by one: the tile offset, the cell byte and the ambiguity key of sample J
+// were produced one step earlier (offn / celln / ambn); this step first issues the same for sample J+1 -- the
+// second ring of blocking cells keeps that speculative load inside the map even when sample J is the one that
+// ends the ray -- and only then decides sample J, so the shared-memory latency overlaps the decision.
+// `J` is the 1-based sample index (a literal in the unrolled variants).  `break`s out of the enclosing loop when
+// the ray ends: blocked, or ambiguous (amb_j = J; the rare hand-over to the exact path is done once, after the
+// loop, to keep the unrolled code small).
+#define HEIST_ADVANCE()                                                                                               \
     x += sx; y += sy;                                                                                                 \
+    offn = tile_offset(x, y);                                                                                         \
+    celln = lds_u8(map_sa + offn);                                                                                    \
+    /* frac within 2^-16 of the rounding boundary <=> ((pos + EPS) << 8) < (2 EPS << 8) as u32 */                    \
+    ambn = min(x * 256u + (FX_EPS << 8), y * 256u + (FX_EPS << 8));
+#define HEIST_SAMPLE(J, CHECK_OWN, LAST)                                                                              \
     {                                                                                                                 \
-        /* the load is issued first so that its latency overlaps the ambiguity test: the address is always   */      \
-        /* inside the map because the previous sample was in bounds and not blocking (ring argument above)   */      \
-        const unsigned off = tile_offset(x, y);                                                                       \
-        const unsigned cellv = lds_u8(map_sa + off);                                                                  \
-        /* frac within 2^-16 of the rounding boundary <=> ((pos + EPS) << 8) < (2 EPS << 8) as u32 */                \
-        const unsigned ax = x * 256u + (FX_EPS << 8), ay = y * 256u + (FX_EPS << 8);                                  \
-        if (min(ax, ay) < (2u * FX_EPS << 8)) { amb_j = (J); break; }                                                 \
-        if (cellv == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */                         \
-        if (!(CHECK_OWN) || off != own) sts_u8(map_sa + off, CELL_VIS);                                               \
+        const unsigned offc = offn, cellc = celln, ambc = ambn;                                                       \
+        if (!(LAST)) { HEIST_ADVANCE() }                                                                              \
+        if (ambc < (2u * FX_EPS << 8)) { amb_j = (J); break; }                                                        \
+        if (cellc == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */                         \
+        if (!(CHECK_OWN) || offc != own) sts_u8(map_sa + offc, CELL_VIS);                                             \
     }
 
 // March flattened rays [f0, f0+32) of env slot e (asset table `asset`, ray prefix sums `rpre`).
@@ -246,18 +252,22 @@ __device__ __forceinline__ void march_chunk(CtaCtl *ctl, int e, const AssetW *as
     // Only a camera's first sample (dist 0.5) can round to the camera's own tile (security.py:93).
     unsigned x = (unsigned)A.x0, y = (unsigned)A.y0;
     int amb_j = 0;
+    unsigned offn, celln, ambn;
+    if (nsamp >= 1) { HEIST_ADVANCE() }   // sample 1
     if (nsamp == 12) {          // camera, vision_range 6 (the Architect's cameras, networks.py:301)
         do {
-            HEIST_SAMPLE(1, true) HEIST_SAMPLE(2, false) HEIST_SAMPLE(3, false) HEIST_SAMPLE(4, false)
-            HEIST_SAMPLE(5, false) HEIST_SAMPLE(6, false) HEIST_SAMPLE(7, false) HEIST_SAMPLE(8, false)
-            HEIST_SAMPLE(9, false) HEIST_SAMPLE(10, false) HEIST_SAMPLE(11, false) HEIST_SAMPLE(12, false)
+            HEIST_SAMPLE(1, true, false) HEIST_SAMPLE(2, false, false) HEIST_SAMPLE(3, false, false)
+            HEIST_SAMPLE(4, false, false) HEIST_SAMPLE(5, false, false) HEIST_SAMPLE(6, false, false)
+            HEIST_SAMPLE(7, false, false) HEIST_SAMPLE(8, false, false) HEIST_SAMPLE(9, false, false)
+            HEIST_SAMPLE(10, false, false) HEIST_SAMPLE(11, false, false) HEIST_SAMPLE(12, false, true)
         } while (0);
     } else if (nsamp == 4) {    // guard, vision_range 4 (networks.py:311)
         do {
-            HEIST_SAMPLE(1, true) HEIST_SAMPLE(2, false) HEIST_SAMPLE(3, false) HEIST_SAMPLE(4, false)
+            HEIST_SAMPLE(1, true, false) HEIST_SAMPLE(2, false, false) HEIST_SAMPLE(3, false, false)
+            HEIST_SAMPLE(4, false, true)
         } while (0);
     } else if (nsamp >= 1) {
-        for (int j = 1; j <= nsamp; ++j) { HEIST_SAMPLE(j, true) }
+        for (int j = 1; j <= nsamp; ++j) { HEIST_SAMPLE(j, true, j == nsamp) }
     }
     if (amb_j) {  // queue the rest of the ray for the exact path (processed 128 rays at a time after the barrier)
         int slot = (amb_j < 256) ? atomicAdd(&ctl->pend_n, 1) : PEND_CAP;
@@ -361,7 +371,7 @@ __device__ __forceinline__ void begin_visibility(const WarpCtx &S, const Geo &ge
     for (int i = lane; i < R * per_row; i += 32) {
         const int row = i / per_row, q = i - row * per_row;
         if (BIG && !((dirty >> row) & 1ull)) continue;
-        int4 *p = reinterpret_cast<int4 *>(S.cell + (row + 1) * MAP_STRIDE + q * 16);
+        int4 *p = reinterpret_cast<int4 *>(S.cell + (row + RING) * MAP_STRIDE + q * 16);
         int4 v = *p;
         v.x &= 0x01010101; v.y &= 0x01010101; v.z &= 0x01010101; v.w &= 0x01010101;
         *p = v;
@@ -376,7 +386,7 @@ __device__ __forceinline__ void begin_visibility(const WarpCtx &S, const Geo &ge
 __device__ __forceinline__ void end_visibility(const WarpCtx &S, int lane, int n_cams, int n_assets) {
     if (lane >= n_cams && lane < n_assets) {
         const AssetW &A = S.asset[lane];
-        S.cell[(A.row + 1) * MAP_STRIDE + A.col + 1] |= CELL_VIS;
+        S.cell[(A.row + RING) * MAP_STRIDE + A.col + RING] |= CELL_VIS;
     }
     __syncwarp();
 }
@@ -384,9 +394,9 @@ __device__ __forceinline__ void end_visibility(const WarpCtx &S, int lane, int n
 // per-tick refresh of an asset record after its heading / position changed
 __device__ __forceinline__ void refresh_asset(const WarpCtx &S, AssetW &A, bool is_cam) {
     A.base = A.heading - A.fov * 0.5;
-    A.x0 = (int)(((unsigned)(A.col + 1 + S.colbase) << FX_BITS) + (FX_ONE >> 1));
-    A.y0 = (int)(((unsigned)(A.row + 1) << FX_BITS) + (FX_ONE >> 1));
-    A.own = is_cam ? (unsigned)(((A.row + 1) << 8) + A.col + 1 + S.colbase) : ~0u;
+    A.x0 = (int)(((unsigned)(A.col + RING + S.colbase) << FX_BITS) + (FX_ONE >> 1));
+    A.y0 = (int)(((unsigned)(A.row + RING) << FX_BITS) + (FX_ONE >> 1));
+    A.own = is_cam ? (unsigned)(((A.row + RING) << 8) + A.col + RING + S.colbase) : ~0u;
 }
 
 __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, const Geo &geo, int env, int lane, EnvRegs &E,
@@ -400,9 +410,9 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, const G
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
     // cell window with a blocking ring: CELL_BLOCK from the wall bitmap, CELL_VIS from the stored visibility
     const uint32_t *wall = D.wall + (size_t)env * D.RW, *vis = D.vis + (size_t)env * D.RW;
-    for (int i = lane; i < (D.R + 2) * geo.Sx; i += 32) {
+    for (int i = lane; i < (D.R + 2 * RING) * geo.Sx; i += 32) {
         const int row = i / geo.Sx, col = i - row * geo.Sx;
-        const int rr = row - 1, cc = col - 1;
+        const int rr = row - RING, cc = col - RING;
         const bool inside = rr >= 0 && rr < D.R && cc >= 0 && cc < D.C;
         unsigned w = CELL_BLOCK, v = 0;
         if (inside) {
@@ -466,13 +476,13 @@ __device__ __forceinline__ void pack_vis(const Dev &D, const WarpCtx &S, const G
     for (int r = lane; r < D.R; r += 32) {
         unsigned w0 = 0, w1 = 0;
         if (!BIG || ((dirty >> r) & 1ull)) {
-            const uint8_t *row = S.cell + (r + 1) * MAP_STRIDE;
+            const uint8_t *row = S.cell + (r + RING) * MAP_STRIDE;
             const unsigned lo = pack32(row);
             const unsigned mid = geo.Sx > 32 ? pack32(row + 32) : 0u;
-            w0 = (lo >> 1) | (mid << 31);
+            w0 = (lo >> RING) | (mid << (32 - RING));
             if (D.W > 1) {
                 const unsigned hi = geo.Sx > 64 ? pack32(row + 64) : 0u;
-                w1 = (mid >> 1) | (hi << 31);
+                w1 = (mid >> RING) | (hi << (32 - RING));
             }
         }
         dst[r * D.W] = w0;
@@ -522,7 +532,7 @@ __device__ __forceinline__ void step_begin(const Dev &D, const WarpCtx &S, int e
                                            int n_guards, int action) {
     int nr = E.r + (action == 2) - (action == 1);
     int nc = E.c + (action == 4) - (action == 3);
-    if (!(S.cell[(nr + 1) * MAP_STRIDE + nc + 1] & CELL_BLOCK)) { E.r = nr; E.c = nc; }  // ring = out of bounds
+    if (!(S.cell[(nr + RING) * MAP_STRIDE + nc + RING] & CELL_BLOCK)) { E.r = nr; E.c = nc; }  // ring = out of bounds
     if (lane < n_cams) {
         AssetW &A = S.asset[lane];
         A.heading = py_mod360(__dadd_rn(A.heading, S.speed[lane]));
@@ -554,7 +564,7 @@ __device__ __forceinline__ int step_finish(const Dev &D, const WarpCtx &S, EnvRe
     reward = __dadd_rn(reward, __dmul_rn((double)(E.prev - curr), 0.1));
     E.prev = curr;
     if (curr <= 3 && E.init > 3) reward = __dadd_rn(reward, __dmul_rn(0.05, (double)(3 - curr)));
-    if (S.cell[(E.r + 1) * MAP_STRIDE + E.c + 1] & CELL_VIS) {
+    if (S.cell[(E.r + RING) * MAP_STRIDE + E.c + RING] & CELL_VIS) {
         E.flags |= F_DETECTED | F_DONE;
         reward = __dadd_rn(reward, D.reward_detection);
         status = HEIST_DETECTED;
