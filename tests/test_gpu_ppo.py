@@ -116,3 +116,31 @@ def test_architect_sampling_feeds_the_decode_kernel(golden):
     s, _ = ppo.architect_sample(lg, temperature=2.0)
     freq = torch.bincount(s.flatten().long(), minlength=4).float() / s.numel()
     assert torch.allclose(freq, torch.softmax(torch.tensor([0.0, 1.0, 2.0, -1.0]) / 2.0, 0).cuda(), atol=0.01)
+
+
+def test_calls_are_cuda_graph_capturable():
+    """No host sync or allocation inside the ABI calls: a tick + observe + GAE replays from a CUDA graph."""
+    env, _, _, _ = _env(N=64)
+    acts = torch.randint(0, 5, (64,), dtype=torch.int8, device="cuda")
+    state = torch.empty(64, 3, 20, 20, device="cuda")
+    snap = {k: getattr(env, k).clone() for k in ("env_dyn", "visibility_bits", "cam_heading", "guard_heading", "guard_idx")}
+    r0, d0, s0, st0 = env.step_observe(acts, True)
+    for k, v in snap.items():               # rewind, then run the same tick from a graph
+        getattr(env, k).copy_(v)
+    rew = torch.zeros(1, 64, device="cuda")
+    done = torch.zeros(1, 64, dtype=torch.uint8, device="cuda")
+    stat = torch.zeros(1, 64, dtype=torch.uint8, device="cuda")
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=side):
+            env.step_many(acts.view(1, 64), autoreset=True, out={"reward": rew, "done": done, "status": stat})
+            env.observe(out=state)
+            adv, ret = heist_b200.compute_gae(rew, torch.zeros_like(rew), done)
+    for k, v in snap.items():
+        getattr(env, k).copy_(v)
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(rew[0], r0) and torch.equal(done[0].bool(), d0) and torch.equal(stat[0], s0)
+    assert torch.equal(state, st0) and torch.equal(ret, rew)
