@@ -214,8 +214,8 @@ __device__ __forceinline__ void dbg_init(const Dev &D, unsigned char *smem, cons
     {                                                                                                                 \
         const unsigned offc = offn, cellc = celln, ambc = ambn;                                                       \
         if (!(LAST)) { HEIST_ADVANCE() }                                                                              \
-        if (ambc < (2u * FX_EPS << 8)) { amb_j = (J); break; }                                                        \
-        if (cellc == CELL_BLOCK) break; /* blocking cells are never marked, so == suffices */                         \
+        /* one exit branch per sample; blocking cells are never marked, so == suffices */                            \
+        if ((ambc < (2u * FX_EPS << 8)) | (cellc == CELL_BLOCK)) { if (ambc < (2u * FX_EPS << 8)) amb_j = (J); break; } \
         if (!(CHECK_OWN) || offc != own) sts_u8(map_sa + offc, CELL_VIS);                                             \
     }
 
