@@ -133,7 +133,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
-    h->layout_smem = HEIST_WARPS_PER_CTA * ((((size_t)d.RC + 15) & ~(size_t)15) + (size_t)d.RW * 4);
+    h->layout_smem = HEIST_WARPS_PER_CTA * layout_warp_bytes(d.RC, d.RW);
 #define SET_SMEM(E, B)                                                                                                    \
     CUDA_TRY(cudaFuncSetAttribute(k_step_many<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
     CUDA_TRY(cudaFuncSetAttribute(k_reset<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));

@@ -11,6 +11,11 @@
 #define COST_CAMERA 3
 #define COST_GUARD 5
 
+// k_set_layout shared memory per warp: tile codes [RC] (16-byte aligned) + wall row bitmaps [RW]
+__host__ __device__ inline size_t layout_warp_bytes(int RC, int RW) {
+    return ((((size_t)RC + 15) & ~(size_t)15) + (size_t)RW * 4 + 15) & ~(size_t)15;
+}
+
 // Mutable device copy of HeistLayoutArrays (decode output == set_layout input).
 struct LayoutDev {
     int32_t *n_walls;  int16_t *wall_rc;
@@ -105,6 +110,17 @@ k_decode(Dev D, LayoutDev Lz, const int8_t *__restrict__ asset_map, const float 
 // ---------------------------------------------------------------------------------------------
 // Bit-parallel flood fill, lane = grid row (rows lane and lane+32), 64-bit row words.
 // ---------------------------------------------------------------------------------------------
+// All cells reachable from the seeds s (s within pass) along runs of passable bits of one row.  Adding the
+// seeds to the run mask ripples a carry from the lowest seed of a run to the run's top bit: the bits that
+// flip are that stretch (plus the wall bit above, masked off); the other seeds of the run are OR-ed back.
+// The downward direction is the same on the bit-reversed row.
+__device__ __forceinline__ unsigned long long hfill(unsigned long long s, unsigned long long pass, unsigned long long rpass) {
+    s &= pass;
+    const unsigned long long up = (((pass + s) ^ pass) & pass) | s;
+    const unsigned long long rs = __brevll(s);
+    const unsigned long long dn = (((rpass + rs) ^ rpass) & rpass) | rs;
+    return up | __brevll(dn);
+}
 __device__ __forceinline__ bool bfs_warp(const uint32_t *wallrows, int R, int C, int W, int lane, int sr, int sc,
                                          int gr, int gc) {
     if (sr == gr && sc == gc) return true;  // utils.py:65-66
@@ -123,24 +139,23 @@ __device__ __forceinline__ bool bfs_warp(const uint32_t *wallrows, int R, int C,
     unsigned long long reach0 = (lane == sr) ? (1ull << sc) : 0ull;
     unsigned long long reach1 = (lane + 32 == sr) ? (1ull << sc) : 0ull;
     const unsigned long long gbit = 1ull << gc;
+    const unsigned long long rpass0 = __brevll(pass0), rpass1 = __brevll(pass1);
     for (;;) {
-        // flood along the row first (a few cheap rounds), then exchange with the rows above/below
-        unsigned long long n0 = reach0, n1 = reach1;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            n0 |= ((n0 << 1) | (n0 >> 1)) & pass0;
-            n1 |= ((n1 << 1) | (n1 >> 1)) & pass1;
+        // complete flood along each row in one shot (carry trick), then a few cheap vertical exchanges
+        unsigned long long n0 = hfill(reach0, pass0, rpass0), n1 = hfill(reach1, pass1, rpass1);
+#pragma unroll 1
+        for (int k = 0; k < 8; ++k) {
+            unsigned long long up0 = __shfl_up_sync(0xffffffffu, n0, 1);
+            unsigned long long dn0 = __shfl_down_sync(0xffffffffu, n0, 1);
+            unsigned long long up1 = __shfl_up_sync(0xffffffffu, n1, 1);
+            unsigned long long dn1 = __shfl_down_sync(0xffffffffu, n1, 1);
+            unsigned long long n0_last = __shfl_sync(0xffffffffu, n0, 31);
+            unsigned long long n1_first = __shfl_sync(0xffffffffu, n1, 0);
+            if (lane == 0) { up0 = 0ull; up1 = n0_last; }
+            if (lane == 31) { dn0 = n1_first; dn1 = 0ull; }
+            n0 |= (up0 | dn0) & pass0;
+            n1 |= (up1 | dn1) & pass1;
         }
-        unsigned long long up0 = __shfl_up_sync(0xffffffffu, n0, 1);
-        unsigned long long dn0 = __shfl_down_sync(0xffffffffu, n0, 1);
-        unsigned long long up1 = __shfl_up_sync(0xffffffffu, n1, 1);
-        unsigned long long dn1 = __shfl_down_sync(0xffffffffu, n1, 1);
-        unsigned long long n0_last = __shfl_sync(0xffffffffu, n0, 31);
-        unsigned long long n1_first = __shfl_sync(0xffffffffu, n1, 0);
-        if (lane == 0) { up0 = 0ull; up1 = n0_last; }
-        if (lane == 31) { dn0 = n1_first; dn1 = 0ull; }
-        n0 |= (up0 | dn0) & pass0;
-        n1 |= (up1 | dn1) & pass1;
         bool changed = (n0 != reach0) || (n1 != reach1);
         reach0 = n0; reach1 = n1;
         bool hit = (lane == gr && (reach0 & gbit)) || (lane + 32 == gr && (reach1 & gbit));
@@ -161,14 +176,25 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
     const int env = blockIdx.x * HEIST_WARPS_PER_CTA + warp;
     if (env >= D.N) return;
     const int R = D.R, C = D.C, W = D.W;
-    const size_t per_warp = ((size_t)D.RC + 15 & ~(size_t)15) + (size_t)D.RW * 4;
+    const size_t per_warp = layout_warp_bytes(D.RC, D.RW);
     uint8_t *tile = smem + (size_t)warp * per_warp;
     uint32_t *wallrows = (uint32_t *)(tile + (((size_t)D.RC + 15) & ~(size_t)15));
 
     // _reset_layout (:169-177) / create_empty_grid (utils.py:131-139)
-    for (int i = lane; i < D.RC; i += 32) {
-        int r = i / C, c = i - r * C;
-        tile[i] = (r == 0 || r == R - 1 || c == 0 || c == C - 1) ? HEIST_WALL : HEIST_EMPTY;
+    if ((C & 3) == 0) {  // 4 cells per store
+        const int qpr = C >> 2;
+        for (int i = lane; i < (D.RC >> 2); i += 32) {
+            const int r = i / qpr, q = i - r * qpr;
+            unsigned v = (r == 0 || r == R - 1) ? 0x01010101u : 0u;
+            if (q == 0) v |= 0x00000001u;
+            if (q == qpr - 1) v |= 0x01000000u;
+            reinterpret_cast<unsigned *>(tile)[i] = v;
+        }
+    } else {
+        for (int i = lane; i < D.RC; i += 32) {
+            int r = i / C, c = i - r * C;
+            tile[i] = (r == 0 || r == R - 1 || c == 0 || c == C - 1) ? HEIST_WALL : HEIST_EMPTY;
+        }
     }
     __syncwarp();
     int n_cams = 0, n_guards = 0, spent = 0, cost = 0;
@@ -263,7 +289,12 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
     __syncwarp();
     bool valid = bfs_warp(wallrows, R, C, W, lane, D.start_r, D.start_c, D.vault_r, D.vault_c);
     // stores
-    for (int i = lane; i < D.RC; i += 32) D.tile[(size_t)env * D.RC + i] = tile[i];
+    if ((D.RC & 15) == 0) {  // 16-byte stores (the per-env tile block is then 16-byte aligned too)
+        int4 *dst = reinterpret_cast<int4 *>(D.tile + (size_t)env * D.RC);
+        for (int i = lane; i < (D.RC >> 4); i += 32) dst[i] = reinterpret_cast<const int4 *>(tile)[i];
+    } else {
+        for (int i = lane; i < D.RC; i += 32) D.tile[(size_t)env * D.RC + i] = tile[i];
+    }
     for (int i = lane; i < D.RW; i += 32) D.wall[(size_t)env * D.RW + i] = wallrows[i];
     if (lane == 0) {
         *reinterpret_cast<int4 *>(D.env_s + (size_t)env * 4) = make_int4(n_cams, n_guards, valid ? 1 : 0, spent);

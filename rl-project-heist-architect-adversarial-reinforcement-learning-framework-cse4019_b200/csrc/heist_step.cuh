@@ -408,18 +408,38 @@ __device__ __forceinline__ void load_env(const Dev &D, const WarpCtx &S, const G
     const int4 d1 = *reinterpret_cast<const int4 *>(D.env_d + (size_t)env * 8 + 4);
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    // cell window with a blocking ring: CELL_BLOCK from the wall bitmap, CELL_VIS from the stored visibility
+    // cell window with a blocking ring: CELL_BLOCK from the wall bitmap (everything outside the grid blocks),
+    // CELL_VIS from the stored visibility.  One lane expands 32 window bytes at a time: the row bitmaps are
+    // shifted by the ring width, cut into nibbles, and each nibble becomes 4 cell bytes with one multiply.
     const uint32_t *wall = D.wall + (size_t)env * D.RW, *vis = D.vis + (size_t)env * D.RW;
-    for (int i = lane; i < (D.R + 2 * RING) * geo.Sx; i += 32) {
-        const int row = i / geo.Sx, col = i - row * geo.Sx;
-        const int rr = row - RING, cc = col - RING;
-        const bool inside = rr >= 0 && rr < D.R && cc >= 0 && cc < D.C;
-        unsigned w = CELL_BLOCK, v = 0;
-        if (inside) {
-            w = (wall[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u;
-            v = ((vis[rr * D.W + (cc >> 5)] >> (cc & 31)) & 1u) << 1;
+    const int gpr = geo.Sx >> 5;  // 32-byte groups per window row
+    for (int u = lane; u < (D.R + 2 * RING) * gpr; u += 32) {
+        const int row = u / gpr, g = u - row * gpr;
+        const int rr = row - RING;
+        uint32_t wbits = 0xffffffffu, vbits = 0u;
+        if (rr >= 0 && rr < D.R) {
+            unsigned long long w64 = wall[rr * D.W], v64 = vis[rr * D.W];
+            if (D.W > 1) { w64 |= (unsigned long long)wall[rr * D.W + 1] << 32; v64 |= (unsigned long long)vis[rr * D.W + 1] << 32; }
+            // 128-bit (hi:lo) = bitmap << RING, then bits outside [RING, RING + C) forced to "blocking, not visible"
+            const unsigned long long wlo = w64 << RING, whi = w64 >> (64 - RING), vlo = v64 << RING, vhi = v64 >> (64 - RING);
+            const int lo_bit = g * 32;  // window bytes [lo_bit, lo_bit + 32)
+            const uint32_t wsel = lo_bit == 0 ? (uint32_t)wlo : lo_bit == 32 ? (uint32_t)(wlo >> 32) : lo_bit == 64 ? (uint32_t)whi : (uint32_t)(whi >> 32);
+            const uint32_t vsel = lo_bit == 0 ? (uint32_t)vlo : lo_bit == 32 ? (uint32_t)(vlo >> 32) : lo_bit == 64 ? (uint32_t)vhi : (uint32_t)(vhi >> 32);
+            // inside mask for this group: window positions p with RING <= p < RING + C
+            const int a0 = max(RING - lo_bit, 0), a1 = min(RING + D.C - lo_bit, 32);
+            const uint32_t inside = a1 > a0 ? ((a1 - a0 >= 32 ? 0xffffffffu : ((1u << (a1 - a0)) - 1u)) << a0) : 0u;
+            wbits = (wsel & inside) | ~inside;
+            vbits = vsel & inside;
         }
-        S.cell[row * MAP_STRIDE + col] = (uint8_t)(w | v);
+        uint32_t out[8];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const uint32_t wn = (wbits >> (4 * n)) & 15u, vn = (vbits >> (4 * n)) & 15u;
+            out[n] = ((wn * 0x00204081u) & 0x01010101u) | (((vn * 0x00204081u) & 0x01010101u) << 1);
+        }
+        uint4 *dst = reinterpret_cast<uint4 *>(S.cell + row * MAP_STRIDE + g * 32);
+        dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
     }
     if (lane < n_cams) {
         size_t o = (size_t)env * D.Kc + lane;
