@@ -280,12 +280,24 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
     }
     __syncwarp();
     // wall_mask = (grid == WALL) as row bitmaps (environment.py:211,257)
-    for (int r = 0; r < R; ++r)
-        for (int w = 0; w < W; ++w) {
-            int c = w * 32 + lane;
-            unsigned m = __ballot_sync(0xffffffffu, c < C && tile[r * C + c] == HEIST_WALL);
-            if (lane == 0) wallrows[r * W + w] = m;
-        }
+    if ((C & 31) == 0) {  // lane = row: per-byte compare (__vcmpeq4) + multiply-gather, 4 tiles per step
+        for (int r = lane; r < R; r += 32)
+            for (int w = 0; w < W; ++w) {
+                const unsigned *src = reinterpret_cast<const unsigned *>(tile + r * C + w * 32);
+                unsigned m = 0;
+#pragma unroll
+                for (int n = 0; n < 8; ++n)
+                    m |= (((__vcmpeq4(src[n], 0x01010101u) & 0x01010101u) * 0x01020408u) >> 24) << (4 * n);
+                wallrows[r * W + w] = m;
+            }
+    } else {
+        for (int r = 0; r < R; ++r)
+            for (int w = 0; w < W; ++w) {
+                int c = w * 32 + lane;
+                unsigned m = __ballot_sync(0xffffffffu, c < C && tile[r * C + c] == HEIST_WALL);
+                if (lane == 0) wallrows[r * W + w] = m;
+            }
+    }
     __syncwarp();
     bool valid = bfs_warp(wallrows, R, C, W, lane, D.start_r, D.start_c, D.vault_r, D.vault_c);
     // stores
