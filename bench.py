@@ -50,6 +50,13 @@ def measured_traffic(kernel):
         return None
 
 
+def measured_inst(kernel):
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["warp_inst_per_launch"]
+    except Exception:
+        return None
+
+
 def hbm_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -284,6 +291,15 @@ def run_ours(args, rank, world, local_rank):
                          "note": "the ray-march is instruction-issue bound, not HBM bound (SURVEY 8d, DESIGN.md 5): "
                                  "frac is honest and small; see profiles/ for issue-slot utilisation"},
             "clocks": clocks, "other_kernels": extra}
+    inst = measured_inst("k_step_many")
+    if inst and args.config == 2 and args.envs == 4096 and args.ticks == 200 and clocks and clocks.get("sm_mhz"):
+        # informational: the bound that actually applies.  Warp-instructions per launch from the committed ncu
+        # capture, issue peak = 148 SMs x 4 schedulers x 1 instruction/clock at the SM clock sampled during the run.
+        peak_issue = 148 * 4 * clocks["sm_mhz"] * 1e6
+        ach = inst / (ms_kernel * 1e-3)
+        line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": ach, "peak": peak_issue,
+                                  "unit": "warp-inst/s", "frac": ach / peak_issue,
+                                  "warp_inst_per_env_step": inst / steps_per_iter}
     if not args.no_cpu_baseline and world == 1:
         rate, threads, sample, _, _ = cpu_rollout_rate(args, 256, args.cpu_seconds, seed)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
