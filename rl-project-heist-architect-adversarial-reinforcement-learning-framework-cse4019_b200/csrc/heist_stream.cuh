@@ -35,8 +35,10 @@ __global__ void __launch_bounds__(1024) k_observe_vec4(Dev D, float4 *__restrict
         float4 v;
         if (ch == 0) {  // occupancy = grid.astype(float32) / 5   (:319)
             uchar4 t = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + cell);
-            v.x = __fdiv_rn((float)t.x, 5.0f); v.y = __fdiv_rn((float)t.y, 5.0f);
-            v.z = __fdiv_rn((float)t.z, 5.0f); v.w = __fdiv_rn((float)t.w, 5.0f);
+            // float32(code) / 5 == float32(code) * 0.2f bit-for-bit for the six tile codes 0..5 (checked
+            // exhaustively; the parity tests compare every code): one multiply instead of an IEEE division
+            v.x = __fmul_rn((float)t.x, 0.2f); v.y = __fmul_rn((float)t.y, 0.2f);
+            v.z = __fmul_rn((float)t.z, 0.2f); v.w = __fmul_rn((float)t.w, 0.2f);
         } else if (ch == 1) {  // visibility (:322)
             uint32_t bits = D.vis[(size_t)env * D.RW + r * D.W + (c >> 5)] >> (c & 31);
             v.x = (float)(bits & 1u); v.y = (float)((bits >> 1) & 1u);
@@ -70,7 +72,7 @@ k_expand_states(Dev D, const uint32_t *__restrict__ vis, const int32_t *__restri
     const float g = D.pos_tab[cell];
     for (int m = blockIdx.y; m < M; m += gridDim.y) {
         float v;
-        if (ch == 0) v = __fdiv_rn((float)D.tile[(size_t)env_idx[m] * D.RC + cell], 5.0f);
+        if (ch == 0) v = __fmul_rn((float)D.tile[(size_t)env_idx[m] * D.RC + cell], 0.2f);  // == / 5 for codes 0..5
         else if (ch == 1) v = (float)((vis[(size_t)m * D.RW + r * D.W + (c >> 5)] >> (c & 31)) & 1u);
         else {
             const int p = pos[m];
@@ -91,7 +93,7 @@ __global__ void __launch_bounds__(256) k_observe_scalar(Dev D, float *__restrict
         int ch = rem / D.RC;
         int cell = rem - ch * D.RC;
         float v;
-        if (ch == 0) v = __fdiv_rn((float)D.tile[(size_t)env * D.RC + cell], 5.0f);
+        if (ch == 0) v = __fmul_rn((float)D.tile[(size_t)env * D.RC + cell], 0.2f);  // == / 5 for codes 0..5
         else if (ch == 1) {
             int r = cell / D.C, c = cell - r * D.C;
             v = (float)((D.vis[(size_t)env * D.RW + r * D.W + (c >> 5)] >> (c & 31)) & 1u);
