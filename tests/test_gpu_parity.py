@@ -537,3 +537,56 @@ def test_env_counts_not_multiple_of_cta(N):
     assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
     assert np.array_equal(out["reward"].cpu().numpy(), ref["reward"])
     assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+
+
+def test_errors_are_reported_not_swallowed():
+    import ctypes as C
+    from heist_b200 import _ffi
+    lib = _ffi.load()
+    # bad construction parameters -> negative code + message
+    p = _ffi.HeistParams(grid_rows=80, grid_cols=20, max_steps=200, start_row=1, start_col=1, vault_row=18, vault_col=18,
+                         architect_budget=15, max_walls=8, max_cams=8, max_guards=4, max_path=8,
+                         reward_vault=10.0, reward_detection=-1.0, reward_step=-0.01)
+    h = C.c_void_p()
+    assert lib.heist_create(C.byref(p), 4, 0, C.byref(h)) == -3 and b"outside" in lib.heist_last_error()
+    p.grid_rows, p.max_cams, p.max_guards = 20, 30, 8
+    assert lib.heist_create(C.byref(p), 4, 0, C.byref(h)) == -5
+    with pytest.raises(RuntimeError, match="heist_create"):
+        BatchedHeistEnv(EnvironmentConfig(grid_rows=2, grid_cols=2), 1)
+    # device-side capacity overflow in the decode (budget buys more walls than max_walls): sticky flag, no truncation
+    env = BatchedHeistEnv(EnvironmentConfig(), 8, max_walls=4)
+    am = np.zeros((8, 20, 20), np.int8)
+    am[:, 5, 2:12] = 1
+    env.set_layout_from_asset_map(am, np.tile(np.float32([60, 15, 0]), (8, 1)), budget=15)
+    with pytest.raises(RuntimeError, match="capacity"):
+        env.check_errors()
+    env.check_errors()  # the flag is cleared once reported
+    # host-side validation of explicit layouts
+    with pytest.raises(ValueError, match="capacity"):
+        env.set_layout_explicit([([(1, 1)] * 5, [], [])] * 8)
+    with pytest.raises(ValueError, match="outside"):
+        env.set_layout_explicit([([], [], [{"patrol_path": [(25, 3)]}])] * 8)
+    with pytest.raises(KeyError):
+        heist_b200.HeistEnvironment(EnvironmentConfig(grid_rows=10, grid_cols=10)).step(7)
+
+
+def test_single_tick_api_with_masked_resets_matches_oracle():
+    """heist_step + heist_reset(mask) at batch scale, the pattern of a policy-in-the-loop driver."""
+    cfg = EnvironmentConfig(max_steps=25)
+    N, T = 512, 60
+    env = BatchedHeistEnv(cfg, N)
+    rng = np.random.default_rng(2718)
+    am, cp = synthetic.sample_asset_maps(rng, N, 20, 20), synthetic.sample_cam_params(rng, N, nice=True)
+    env.set_layout_from_asset_map(am, cp, 15)
+    oenvs, _ = oracle_envs(am, cp, cfg, 15)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, T, N)
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    for t in range(T):
+        rew, done, status = env.step(acts[t])
+        assert np.array_equal(rew.cpu().numpy(), ref["reward"][t]) and np.array_equal(status.cpu().numpy(), ref["status"][t])
+        if t % 7 == 0:  # un-reset state of finished envs is observable too: done flag stays until reset
+            assert torch.equal(env.done, done)
+        env.reset(mask=done)
+        assert np.array_equal(u32(env.visibility_bits), ref["vis_bits"][t]), t
