@@ -196,10 +196,17 @@ int heist_gae(const float *rew, const float *val, const uint8_t *done, int T, in
 int heist_architect_reward(HeistHandle *h, double *reward_out, double *solve_rate_out, void *stream);
 
 /*
- * Verification knob: exact_only != 0 routes every ray sample through the fp64 reference arithmetic
- * (no fixed-point fast path).  Results are bit-identical either way; tests compare the two modes.
+ * Verification knob.  All three modes produce bit-identical results; tests compare them.
+ *   HEIST_MODE_DEFAULT  visibility from the per-layout angular cache (table-driven kernel); envs whose assets the
+ *                       cache does not cover (vision_range > 7, fov outside (0, 180], ...) are ray-marched
+ *   HEIST_MODE_EXACT    every ray sample through the fp64 reference arithmetic (security.py:69-99)
+ *   HEIST_MODE_MARCH    filtered fixed-point ray-march with exact fallback for every env (no cache)
+ * Setting HEIST_NO_VIS_CACHE=1 in the environment before heist_create makes DEFAULT behave like MARCH.
  */
-int heist_set_mode(HeistHandle *h, int exact_only);
+#define HEIST_MODE_DEFAULT 0
+#define HEIST_MODE_EXACT 1
+#define HEIST_MODE_MARCH 2
+int heist_set_mode(HeistHandle *h, int mode);
 
 /* Synchronises `stream` and reports sticky device-side errors (capacity overflow, bad waypoint). */
 int heist_check_errors(HeistHandle *h, void *stream);

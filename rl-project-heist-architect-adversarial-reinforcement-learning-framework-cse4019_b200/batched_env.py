@@ -139,9 +139,16 @@ class BatchedHeistEnv:
             t = torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
         return t.contiguous()
 
+    MODE_DEFAULT, MODE_EXACT, MODE_MARCH = 0, 1, 2
+
+    def set_mode(self, mode):
+        """Verification knob (include/heist_b200.h): 0 = angular visibility cache + ray-march for what it does not
+        cover, 1 = all-fp64 ray-march, 2 = filtered ray-march everywhere.  All modes are bit-identical."""
+        _ffi.check(self._lib.heist_set_mode(self._h, int(mode)), "heist_set_mode")
+
     def set_exact_only(self, flag):
-        """Verification knob: force the all-fp64 ray-march (bit-identical to the default filtered path)."""
-        _ffi.check(self._lib.heist_set_mode(self._h, int(bool(flag))), "heist_set_mode")
+        """Force the all-fp64 ray-march (True) or go back to the default mode (False)."""
+        self.set_mode(self.MODE_EXACT if flag else self.MODE_DEFAULT)
 
     def check_errors(self):
         _ffi.check(self._lib.heist_check_errors(self._h, self._stream()), "heist_check_errors")

@@ -11,11 +11,14 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 
 #include "heist_common.cuh"
 #include "heist_layout.cuh"
 #include "heist_step.cuh"
+#include "heist_cache.cuh"
+#include "heist_fast.cuh"
 #include "heist_stream.cuh"
 
 static thread_local std::string g_err;
@@ -42,8 +45,11 @@ struct HeistHandle {
     Dev d;
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
-    int exact_only;  // heist_set_mode: 1 = every sample through the fp64 reference arithmetic
-    void *allocs[64];
+    int mode;        // heist_set_mode: HEIST_MODE_*
+    size_t camvis_smem, dyn_smem;
+    double *heads;      size_t heads_cap;     // k_heads output, grow-only [blocks][N][Kc]
+    uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
+    void *allocs[96];
     int n_allocs;
 };
 
@@ -61,6 +67,7 @@ static cudaError_t dalloc(HeistHandle *h, T **ptr, size_t count) {
     return cudaSuccess;
 }
 
+static cudaError_t build_cache(HeistHandle *h, cudaStream_t s);
 static inline int env_blocks(int N) { return (N + HEIST_WARPS_PER_CTA - 1) / HEIST_WARPS_PER_CTA; }
 
 extern "C" int heist_abi_version(void) { return HEIST_ABI_VERSION; }
@@ -71,6 +78,8 @@ extern "C" int heist_destroy(HeistHandle *h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
+    if (h->heads) cudaFree(h->heads);
+    if (h->scratch) cudaFree(h->scratch);
     delete h;
     return 0;
 }
@@ -118,8 +127,26 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     A(z.cam_f, N * d.Kc * 3); A(z.cam_range, N * d.Kc); A(z.n_guards, N); A(z.guard_len, N * d.Kg);
     A(z.guard_path, N * d.Kg * d.L * 2); A(z.guard_head, N * d.Kg * d.L); A(z.guard_speed, N * d.Kg);
     A(z.guard_range, N * d.Kg); A(z.guard_fov, N * d.Kg);
-#undef A
+    A(d.env_cached, N); A(d.n_uncached, (size_t)1);
     if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc: %s", cudaGetErrorString(e)); }
+    // Visibility cache (heist_cache.cuh): ~25 KB per camera slot.  Optional: when it does not fit, every env
+    // stays on the ray-march kernel.
+    {
+        const char *off = getenv("HEIST_NO_VIS_CACHE");
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t HS = (size_t)d.L + 1;
+        const size_t need = N * d.Kc * ((size_t)VC_POINTS * 8 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
+                            N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
+        if (!(off && off[0] == '1') && need < free_b / 2) {
+            A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
+            A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc);
+            A(d.vg_mask, N * d.Kg * d.L * HS * VC_ROWS); A(d.vg_hval, N * d.Kg * HS);
+            A(d.vg_hslot, N * d.Kg * d.L); A(d.vg_nh, N * d.Kg);
+            if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc (visibility cache): %s", cudaGetErrorString(e)); }
+        }
+    }
+#undef A
 
     // cos / -sin of exact multiples of 30 degrees from the host libm (see heist_common.cuh)
     double ndx[NICE_N], ndy[NICE_N];
@@ -133,6 +160,18 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
+    h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);
+    h->dyn_smem = FAST_WARPS * dyn_warp_bytes(d.RW, d.Kg);
+#define SET_FAST(RPL, W)                                                                                                  \
+    CUDA_TRY(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem)); \
+    CUDA_TRY(cudaFuncSetAttribute(k_dyn<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
+#undef SET_FAST
+    if (d.vc_p) {   // single-tick buffers up front, so that step / reset never allocate (CUDA-graph capture)
+        h->heads_cap = N * d.Kc; h->scratch_cap = N * d.RW;
+        CUDA_TRY(cudaMalloc(&h->heads, h->heads_cap * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->scratch, h->scratch_cap * sizeof(uint32_t)));
+    }
     h->layout_smem = HEIST_WARPS_PER_CTA * layout_warp_bytes(d.RC, d.RW);
 #define SET_SMEM(E, B)                                                                                                    \
     CUDA_TRY(cudaFuncSetAttribute(k_step_many<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
@@ -147,6 +186,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     LayoutDev none;
     memset(&none, 0, sizeof(none));
     k_set_layout<<<env_blocks(num_envs), HEIST_WARPS_PER_CTA * 32, h->layout_smem>>>(d, none, nullptr, nullptr);
+    CUDA_TRY(build_cache(h, 0));
     CUDA_TRY(cudaMemsetAsync(d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(num_envs) * HEIST_WARPS_PER_CTA, 0));
     k_build_order<<<1, 1024>>>(d, env_blocks(num_envs));
     CUDA_TRY(cudaGetLastError());
@@ -155,10 +195,23 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     return 0;
 }
 
+// Per-layout visibility tables (heist_cache.cuh); without the cache every env is "uncached".
+static cudaError_t build_cache(HeistHandle *h, cudaStream_t s) {
+    if (!h->d.vc_p) {
+        const int n = h->N;
+        return cudaMemcpyAsync(h->d.n_uncached, &n, sizeof(int), cudaMemcpyHostToDevice, s);
+    }
+    cudaError_t e = cudaMemsetAsync(h->d.n_uncached, 0, sizeof(int), s);
+    if (e != cudaSuccess) return e;
+    k_build_cache<<<h->N, VC_BUILD_THREADS, 0, s>>>(h->d);
+    return cudaGetLastError();
+}
+
 static int launch_set_layout(HeistHandle *h, const LayoutDev &lz, const int32_t *budget, uint8_t *valid_out,
                              cudaStream_t s) {
     k_set_layout<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, h->layout_smem, s>>>(h->d, lz, budget, valid_out);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(build_cache(h, s));
     CUDA_TRY(cudaMemsetAsync(h->d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(h->N) * HEIST_WARPS_PER_CTA, s));
     k_build_order<<<1, 1024, 0, s>>>(h->d, env_blocks(h->N));
     CUDA_TRY(cudaGetLastError());
@@ -197,33 +250,92 @@ extern "C" int heist_set_layout_explicit(HeistHandle *h, const HeistLayoutArrays
     return launch_set_layout(h, lz, budget, valid_out, (cudaStream_t)stream);
 }
 
+// Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_dyn
+// per chunk of ticks (heist_fast.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
+template <typename T>
+static cudaError_t grow(T **buf, size_t *cap, size_t need) {
+    if (need <= *cap) return cudaSuccess;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    (void)st;
+    if (*buf) { cudaError_t e = cudaFree(*buf); *buf = nullptr; *cap = 0; if (e != cudaSuccess) return e; }
+    cudaError_t e = cudaMalloc(buf, need * sizeof(T));
+    if (e == cudaSuccess) *cap = need;
+    return e;
+}
+
+static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
+                       uint8_t *done, uint8_t *status, uint32_t *vis_traj, int do_reset, const uint8_t *mask,
+                       cudaStream_t s) {
+    const Dev &d = h->d;
+    const size_t N = h->N, NRW = N * d.RW;
+    const bool r2 = d.R > 32, w2 = d.C > 32;
+    const int total = do_reset ? 1 : T;
+    // ticks per chunk: bounded by 256 MiB of cam_vis scratch when there is no trajectory buffer to build it in
+    int cap = 256;
+    if (!vis_traj) cap = (int)std::max<size_t>(1, std::min<size_t>(256, ((size_t)256 << 20) / (NRW * 4)));
+    for (int t0 = 0; t0 < total; t0 += cap) {
+        const int Tc = std::min(cap, total - t0), nblk = (Tc + FAST_TB - 1) / FAST_TB;
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
+        if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)Tc * NRW));
+        uint32_t *cam = vis_traj ? vis_traj + (size_t)t0 * NRW : h->scratch;
+        const size_t off = (size_t)t0 * N;
+        k_heads<<<(unsigned)((N * d.Kc + 127) / 128), 128, 0, s>>>(d, Tc, do_reset, h->heads);
+        const long long warps = (long long)N * nblk;
+        const unsigned g1 = (unsigned)((warps + FAST_WARPS - 1) / FAST_WARPS), g2 = (unsigned)((N + FAST_WARPS - 1) / FAST_WARPS);
+#define GO(RPL, W)                                                                                                       \
+    do {                                                                                                                 \
+        k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, Tc, nblk, h->heads, cam, do_reset ? mask : nullptr); \
+        k_dyn<RPL, W><<<g2, FAST_WARPS * 32, h->dyn_smem, s>>>(                                                         \
+            d, actions ? actions + off : nullptr, do_reset ? 0 : Tc, autoreset, reward ? reward + off : nullptr,         \
+            reward64 ? reward64 + off : nullptr, done ? done + off : nullptr, status ? status + off : nullptr, cam,      \
+            vis_traj ? cam : nullptr, do_reset, mask);                                                                   \
+    } while (0)
+        if (r2) { if (w2) GO(2, 2); else GO(2, 1); }
+        else { if (w2) GO(1, 2); else GO(1, 1); }
+#undef GO
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+static inline bool use_cache(const HeistHandle *h) { return h->mode == HEIST_MODE_DEFAULT && h->d.vc_p != nullptr; }
+
 extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     if (!h) return fail(-1, "heist_reset: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
     cudaStream_t s = (cudaStream_t)stream;
-    const bool big = h->d.R > 32;
-#define GO(E, B) k_reset<E, B><<<grid, block, h->step_smem, s>>>(h->d, mask)
-    if (h->exact_only) { if (big) GO(true, true); else GO(true, false); }
+    const bool big = h->d.R > 32, exact = h->mode == HEIST_MODE_EXACT;
+    Dev d = h->d;
+    d.skip_cached = use_cache(h);
+    if (d.skip_cached) { int rc = launch_fast(h, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1, mask, s); if (rc) return rc; }
+#define GO(E, B) k_reset<E, B><<<grid, block, h->step_smem, s>>>(d, mask)
+    if (exact) { if (big) GO(true, true); else GO(true, false); }
     else { if (big) GO(false, true); else GO(false, false); }
 #undef GO
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
 
-static void launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
-                        uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
+static int launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
+                       uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
-    const bool big = h->d.R > 32;
-#define GO(E, B) k_step_many<E, B><<<grid, block, h->step_smem, s>>>(h->d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
-    if (h->exact_only) { if (big) GO(true, true); else GO(true, false); }
+    const bool big = h->d.R > 32, exact = h->mode == HEIST_MODE_EXACT;
+    Dev d = h->d;
+    d.skip_cached = use_cache(h);
+    if (d.skip_cached) { int rc = launch_fast(h, actions, T, autoreset, reward, reward64, done, status, vis_traj, 0, nullptr, s); if (rc) return rc; }
+#define GO(E, B) k_step_many<E, B><<<grid, block, h->step_smem, s>>>(d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
+    if (exact) { if (big) GO(true, true); else GO(true, false); }
     else { if (big) GO(false, true); else GO(false, false); }
 #undef GO
+    CUDA_TRY(cudaGetLastError());
+    return 0;
 }
 
-extern "C" int heist_set_mode(HeistHandle *h, int exact_only) {
+extern "C" int heist_set_mode(HeistHandle *h, int mode) {
     if (!h) return fail(-1, "heist_set_mode: null handle");
-    h->exact_only = exact_only ? 1 : 0;
+    if (mode < HEIST_MODE_DEFAULT || mode > HEIST_MODE_MARCH) return fail(-10, "heist_set_mode: unknown mode %d", mode);
+    h->mode = mode;
     return 0;
 }
 
@@ -231,9 +343,7 @@ extern "C" int heist_step(HeistHandle *h, const int8_t *actions, float *reward, 
                           uint8_t *status, void *stream) {
     if (!h || !actions) return fail(-1, "heist_step: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    launch_step(h, actions, 1, 0, reward, reward64, done, status, nullptr, (cudaStream_t)stream);
-    CUDA_TRY(cudaGetLastError());
-    return 0;
+    return launch_step(h, actions, 1, 0, reward, reward64, done, status, nullptr, (cudaStream_t)stream);
 }
 
 extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward,
@@ -242,9 +352,8 @@ extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int
     if (T < 0) return fail(-9, "heist_step_many: negative T");
     if (T == 0) return 0;
     CUDA_TRY(cudaSetDevice(h->device));
-    launch_step(h, actions, T, autoreset, reward, nullptr, done, status, vis_traj, (cudaStream_t)stream);
-    CUDA_TRY(cudaGetLastError());
-    if (T >= 8) {  // re-deal the warp slots by the work each env actually did (its reset rate included)
+    { int rc = launch_step(h, actions, T, autoreset, reward, nullptr, done, status, vis_traj, (cudaStream_t)stream); if (rc) return rc; }
+    if (T >= 8 && !use_cache(h)) {  // re-deal the warp slots by the work each env actually did (its reset rate included)
         CUDA_TRY(cudaMemsetAsync(h->d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(h->N) * HEIST_WARPS_PER_CTA,
                                  (cudaStream_t)stream));
         k_build_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d, env_blocks(h->N));
@@ -278,8 +387,7 @@ extern "C" int heist_step_observe(HeistHandle *h, const int8_t *actions, int aut
                                   uint8_t *status, float *state, void *stream) {
     if (!h || !actions || !state) return fail(-1, "heist_step_observe: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    launch_step(h, actions, 1, autoreset, reward, nullptr, done, status, nullptr, (cudaStream_t)stream);
-    CUDA_TRY(cudaGetLastError());
+    { int rc = launch_step(h, actions, 1, autoreset, reward, nullptr, done, status, nullptr, (cudaStream_t)stream); if (rc) return rc; }
     return heist_observe(h, state, stream);
 }
 

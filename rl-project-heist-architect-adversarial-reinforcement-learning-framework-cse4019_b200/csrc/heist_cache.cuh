@@ -1,0 +1,256 @@
+// heist_cache.cuh -- angular visibility cache: the per-layout tables behind the table-driven step kernel.
+//
+// Reference: Camera.get_vision_cone_tiles (security.py:53-101), Guard.get_visible_tiles (security.py:161-192),
+// DynamicVisibilityMap.update (visibility.py:31-65).
+//
+// The walls of a layout never move (environment.py:118-122), so the tile sequence marked by ONE ray of a camera
+// is a function of the ray's angle alone, and that function is piecewise constant: it can only change where some
+// sample `col + cos(a) * dist` / `row - sin(a) * dist` crosses a rounding tie (m + 0.5).  For every camera the
+// build kernel below
+//   1. encloses every tie crossing of every sample in a BAND of angles: the pre-image of [tie - 2mu, tie + 2mu]
+//      (mu = 4e-12 tile, far above the ~5e-14 the reference's fp64 evaluation can deviate from the real value,
+//      far below anything a generic ray comes near), padded by 1e-9 degree, over the domain
+//      [-fov/2, 360 + fov/2) a ray angle `heading - fov/2 + fov * i / num_rays` can take (heading in [0, 360));
+//   2. sorts and merges the bands; the GAPS between them are angle intervals on which every sample of a ray
+//      stays at least mu away from every tie, so the reference's rounding -- whatever the last bit of the
+//      platform's cos/sin -- is constant there;
+//   3. marches one representative ray per gap through the reference's own arithmetic (ray_exact semantics, walls
+//      included) and stores the marked tiles as a (2*range+1)^2 window bitmap: 16 rows of 16 bits.
+// At run time (heist_fast.cuh) a tick of a camera is: find the segments its fov window covers, OR the masks of
+// the gaps that contain at least one ray, and run the few rays that fall inside a band (structurally: rays on
+// exact multiples of 30/45/90 degrees) through the exact ray-march.  A guard's cone depends only on its waypoint
+// and on which of the path's headings it carries (security.py:145-159), so guards get one mask per
+// (waypoint, heading) pair.
+#pragma once
+#include "heist_common.cuh"
+
+#define VC_ROWS 16            // mask rows per window (u16 each): 2 * range + 1 <= 15
+#define VC_MAX_RANGE 7
+#define VC_POINTS 1024        // boundary points kept per camera (2 per merged band)
+#define VC_RAW 1024           // raw bands sorted per camera (power of two)
+#define VC_IDX 560            // 1-degree buckets of the coarse index (domain <= 540 degrees + slack)
+#define VC_MU2 8e-12          // 2 * mu: position-space half width of a computed band (tiles)
+#define VC_PAD 1e-9           // angular padding on each side of a band (degrees)
+#define VC_BUILD_THREADS 128
+
+#define RINT_MAGIC_C 6755399441055744.0  // 2^52 + 2^51
+__device__ __forceinline__ int vc_rint_even(double x) { return __double2loint(__dadd_rn(x, RINT_MAGIC_C)); }
+
+// One ray of the reference's ray-march on the bit maps (security.py:69-99 cameras, :170-190 guards), from
+// sample j0 on.  `mark(r, c)` receives every visible tile (the camera's own tile is filtered by the caller's
+// functor when needed).  Walls come from the row bitmaps in global memory: this is the rare / build-time path.
+template <typename Mark>
+__device__ __forceinline__ void vc_ray(const Dev &D, const uint32_t *__restrict__ wall, int row, int col, double fov,
+                                       double heading, int num_rays, int nsamp, double unit, int ri, Mark mark) {
+    const double half_fov = __ddiv_rn(fov, 2.0);
+    const double angle_deg =
+        __dadd_rn(__dsub_rn(heading, half_fov), __ddiv_rn(__dmul_rn(fov, (double)ri), (double)num_rays));
+    double dx, dy;
+    ray_dir(angle_deg, D.deg2rad, dx, dy);
+    const double dcol = (double)col, drow = (double)row;
+    double dist = unit;
+    for (int j = 1; j <= nsamp; ++j, dist += unit) {
+        const int c = vc_rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
+        const int r = vc_rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
+        if (r < 0 || r >= D.R || c < 0 || c >= D.C) return;
+        if ((wall[r * D.W + (c >> 5)] >> (c & 31)) & 1u) return;
+        mark(r, c);
+    }
+}
+
+// Same march for a given direction angle (the representative of a gap).
+template <typename Mark>
+__device__ __forceinline__ void vc_ray_angle(const Dev &D, const uint32_t *__restrict__ wall, int row, int col,
+                                             double angle_deg, int nsamp, double unit, Mark mark) {
+    double dx, dy;
+    ray_dir(angle_deg, D.deg2rad, dx, dy);
+    const double dcol = (double)col, drow = (double)row;
+    double dist = unit;
+    for (int j = 1; j <= nsamp; ++j, dist += unit) {
+        const int c = vc_rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
+        const int r = vc_rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
+        if (r < 0 || r >= D.R || c < 0 || c >= D.C) return;
+        if ((wall[r * D.W + (c >> 5)] >> (c & 31)) & 1u) return;
+        mark(r, c);
+    }
+}
+
+__device__ __forceinline__ bool vc_cam_cacheable(double fov, double heading, double speed, int range, int num_rays) {
+    return range >= 1 && range <= VC_MAX_RANGE && fov > 0.0 && fov <= 180.0 && num_rays >= 1 && num_rays <= 32767 &&
+           fabs(heading) < 1e6 && fabs(speed) < 1e6;
+}
+__device__ __forceinline__ bool vc_guard_cacheable(double fov, int range, int num_rays, int len, int L) {
+    return range >= 0 && range <= VC_MAX_RANGE && fabs(fov) <= 1e6 && num_rays >= 1 && num_rays <= 4095 && len >= 1 &&
+           len <= L;
+}
+
+struct VcSmem {
+    double key[VC_RAW];   // band starts (sorted), later the merged boundary points
+    double end[VC_RAW];   // band ends
+    unsigned mask[VC_ROWS];
+    int n_raw, n_bands, ok;
+};
+
+// One CTA per env: tables of all its cameras and guards.  Launched after every k_set_layout.
+__global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
+    __shared__ VcSmem S;
+    const int env = blockIdx.x, tid = threadIdx.x;
+    const int n_cams = D.env_s[(size_t)env * 4 + 0], n_guards = D.env_s[(size_t)env * 4 + 1];
+    const uint32_t *wall = D.wall + (size_t)env * D.RW;
+    bool env_ok = true;
+
+    for (int k = 0; k < n_cams; ++k) {
+        const size_t o = (size_t)env * D.Kc + k;
+        const double fov = D.cam_f[o * 2], speed = D.cam_f[o * 2 + 1], heading = D.cam_heading[o];
+        const int16_t *ci = D.cam_i + o * 4;
+        const int row = ci[0], col = ci[1], range = ci[2], num_rays = ci[3];
+        if (!vc_cam_cacheable(fov, heading, speed, range, num_rays)) { env_ok = false; continue; }  // CTA-uniform
+        const int nsamp = 2 * range;
+        const double dom_lo = -0.5 * fov - 1e-6, dom_hi = 360.0 + 0.5 * fov + 1e-6;
+        if (tid == 0) {
+            S.n_raw = 2; S.ok = 1;
+            S.key[0] = -1e300; S.end[0] = dom_lo;   // everything outside the domain is one band on each side:
+            S.key[1] = dom_hi; S.end[1] = 1e300;    // rays there (odd initial headings) take the exact path
+        }
+        __syncthreads();
+        // ---- 1. bands: item = (sample j, axis, tie m + 0.5, mirror sign) x 4 periods ----
+        const int M = 2 * (VC_MAX_RANGE + 1);
+        const int items = nsamp * 2 * M * 2;
+        const double rad2deg = 180.0 / 3.14159265358979323846;
+        for (int it = tid; it < items; it += VC_BUILD_THREADS) {
+            const int sgn = it & 1, mi = (it >> 1) % M, ja = (it >> 1) / M, axis = ja & 1, j = (ja >> 1) + 1;
+            const double d = 0.5 * (double)j;
+            const double tie = (double)(mi - M / 2) + 0.5;
+            if (fabs(tie) > d + VC_MU2) continue;
+            const double t = tie / d, mu = VC_MU2 / d;
+            double c_lo = fmax(-1.0, t - mu), c_hi = fmin(1.0, t + mu);
+            if (axis) { const double a = -c_hi; c_hi = -c_lo; c_lo = a; }  // dy = -sin(a) = -cos(a - 90)
+            // cos(a - off) in [c_lo, c_hi]  <=>  a - off in +-[acos(c_hi), acos(c_lo)] + 360 n
+            const double a_lo = acos(c_hi) * rad2deg, a_hi = acos(c_lo) * rad2deg;
+            const double off = axis ? 90.0 : 0.0;
+            const double b0 = sgn ? off - a_hi : off + a_lo, b1 = sgn ? off - a_lo : off + a_hi;
+            for (int n = -1; n <= 2; ++n) {
+                const double s = b0 + 360.0 * n - VC_PAD, e = b1 + 360.0 * n + VC_PAD;
+                if (e < dom_lo || s > dom_hi) continue;
+                const int slot = atomicAdd(&S.n_raw, 1);
+                if (slot < VC_RAW) { S.key[slot] = s; S.end[slot] = e; }
+                else S.ok = 0;
+            }
+        }
+        __syncthreads();
+        bool ok = S.ok != 0;
+        const int n_raw = min(S.n_raw, VC_RAW);
+        // ---- 2. bitonic sort by start, then merge overlaps ----
+        for (int i = n_raw + tid; i < VC_RAW; i += VC_BUILD_THREADS) { S.key[i] = 2e300; S.end[i] = 2e300; }
+        __syncthreads();
+        for (int size = 2; size <= VC_RAW; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                for (int i = tid; i < VC_RAW / 2; i += VC_BUILD_THREADS) {
+                    const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
+                    const bool up = (lo & size) == 0;
+                    const double a = S.key[lo], b = S.key[hi];
+                    if ((a > b) == up) {
+                        S.key[lo] = b; S.key[hi] = a;
+                        const double ea = S.end[lo]; S.end[lo] = S.end[hi]; S.end[hi] = ea;
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        if (tid == 0) {
+            int nb = 0;
+            double cs = S.key[0], ce = S.end[0];
+            for (int i = 1; i < n_raw; ++i) {
+                const double s = S.key[i], e = S.end[i];
+                if (s <= ce) ce = fmax(ce, e);
+                else { S.key[nb] = cs; S.end[nb] = ce; ++nb; cs = s; ce = e; }
+            }
+            S.key[nb] = cs; S.end[nb] = ce; ++nb;
+            S.n_bands = nb;
+        }
+        __syncthreads();
+        const int nb = S.n_bands;
+        const int n_points = 2 * (nb - 1);   // p[2g] = end of band g, p[2g+1] = start of band g + 1
+        if (n_points > VC_POINTS) ok = false;
+        if (!ok) { env_ok = false; if (tid == 0) D.vc_meta[o * 2] = -1; __syncthreads(); continue; }
+        double *P = D.vc_p + o * VC_POINTS;
+        for (int g = tid; g < nb - 1; g += VC_BUILD_THREADS) { P[2 * g] = S.end[g]; P[2 * g + 1] = S.key[g + 1]; }
+        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = 0; D.vc_lo[o] = dom_lo; }
+        // ---- 3. one representative ray per gap -> window mask ----
+        uint16_t *MK = D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS;
+        for (int g = tid; g < nb - 1; g += VC_BUILD_THREADS) {
+            const double mid = 0.5 * (S.end[g] + S.key[g + 1]);
+            unsigned rows[VC_ROWS / 2];
+#pragma unroll
+            for (int q = 0; q < VC_ROWS / 2; ++q) rows[q] = 0;
+            vc_ray_angle(D, wall, row, col, mid, nsamp, 0.5, [&](int r, int c) {
+                if (r == row && c == col) return;  // (r, c) != (self.row, self.col), security.py:93
+                const int wr = r - row + range, wc = c - col + range;
+                const unsigned bit = 1u << (wc + 16 * (wr & 1));
+#pragma unroll
+                for (int q = 0; q < VC_ROWS / 2; ++q) if (q == (wr >> 1)) rows[q] |= bit;
+            });
+            uint4 *dst = reinterpret_cast<uint4 *>(MK + (size_t)g * VC_ROWS);
+            dst[0] = make_uint4(rows[0], rows[1], rows[2], rows[3]);
+            dst[1] = make_uint4(rows[4], rows[5], rows[6], rows[7]);
+        }
+        // ---- 4. coarse index: points below each 1-degree bucket start ----
+        uint16_t *IX = D.vc_idx + o * VC_IDX;
+        for (int q = tid; q < VC_IDX; q += VC_BUILD_THREADS) {
+            const double a = dom_lo + (double)q;
+            int lo = 0, hi = n_points;   // first index with p >= a  (p[i]: even i from S.end, odd from S.key)
+            while (lo < hi) {
+                const int m = (lo + hi) >> 1;
+                const double pm = (m & 1) ? S.key[(m >> 1) + 1] : S.end[m >> 1];
+                if (pm < a) lo = m + 1; else hi = m;
+            }
+            IX[q] = (uint16_t)lo;
+        }
+        __syncthreads();
+    }
+
+    for (int g = 0; g < n_guards; ++g) {
+        const size_t o = (size_t)env * D.Kg + g;
+        const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);  // len, speed, range, num_rays
+        const double fov = D.guard_fov[o];
+        const int HS = D.L + 1;
+        if (!vc_guard_cacheable(fov, gi.z, gi.w, gi.x, D.L)) { env_ok = false; if (tid == 0) D.vg_nh[o] = -1; continue; }
+        // distinct headings the guard can carry: 0.0 (Guard.heading default) + the per-waypoint headings
+        if (tid == 0) {
+            int nh = 1;
+            D.vg_hval[o * HS] = 0.0;
+            for (int k = 0; k < gi.x; ++k) {
+                const double h = D.guard_head[o * D.L + k];
+                int s = 255;
+                if (h == h) {
+                    for (s = 0; s < nh; ++s) if (__double_as_longlong(D.vg_hval[o * HS + s]) == __double_as_longlong(h)) break;
+                    if (s == nh) { D.vg_hval[o * HS + nh] = h; ++nh; }
+                }
+                D.vg_hslot[o * D.L + k] = (uint8_t)s;
+            }
+            D.vg_nh[o] = nh;
+            S.n_bands = nh;
+        }
+        __syncthreads();
+        const int nh = S.n_bands;
+        for (int combo = 0; combo < gi.x * nh; ++combo) {
+            const int idx = combo / nh, hs = combo - idx * nh;
+            const int row = D.guard_path[(o * D.L + idx) * 2], col = D.guard_path[(o * D.L + idx) * 2 + 1];
+            const double heading = D.vg_hval[o * HS + hs];
+            if (tid < VC_ROWS) S.mask[tid] = 0;
+            __syncthreads();
+            for (int ri = tid; ri <= gi.w; ri += VC_BUILD_THREADS)
+                vc_ray(D, wall, row, col, fov, heading, gi.w, gi.z, 1.0, ri, [&](int r, int c) {
+                    atomicOr(&S.mask[r - row + gi.z], 1u << (c - col + gi.z));
+                });
+            if (tid == 0) atomicOr(&S.mask[gi.z], 1u << gi.z);  // the guard's own tile is always lit (visibility.py:59)
+            __syncthreads();
+            if (tid < VC_ROWS) D.vg_mask[((o * D.L + idx) * HS + hs) * VC_ROWS + tid] = (uint16_t)S.mask[tid];
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        D.env_cached[env] = env_ok ? 1 : 0;
+        if (!env_ok) atomicAdd(D.n_uncached, 1);
+    }
+}

@@ -45,6 +45,19 @@ struct Dev {
     int32_t *cost;        // [N] ray-march samples per tick (load-balance estimate)
     int32_t *slot2env;    // [ceil(N/4)*4] warp slot -> env (-1: empty), cost-balanced
     int *err;             // sticky device error flags
+    // angular visibility cache (heist_cache.cuh); vc_p == nullptr: cache disabled
+    double *vc_p;         // [N][Kc][VC_POINTS] sorted boundary angles of the tie bands
+    uint16_t *vc_mask;    // [N][Kc][VC_POINTS/2][VC_ROWS] window bitmap of gap g
+    uint16_t *vc_idx;     // [N][Kc][VC_IDX] coarse index: boundary points below each 1-degree bucket
+    int32_t *vc_meta;     // [N][Kc][2] n_points (-1: not cacheable), reserved
+    double *vc_lo;        // [N][Kc] lower end of the cached angle domain
+    uint16_t *vg_mask;    // [N][Kg][L][L+1][VC_ROWS] guard cone per (waypoint, heading slot)
+    double *vg_hval;      // [N][Kg][L+1] distinct headings a guard can carry
+    uint8_t *vg_hslot;    // [N][Kg][L] slot of guard_head[k] (255: unchanged)
+    int32_t *vg_nh;       // [N][Kg] number of heading slots (-1: not cacheable)
+    uint8_t *env_cached;  // [N] every asset of the env is served by the cache
+    int *n_uncached;      // [1] envs left to the ray-march kernel
+    int skip_cached;      // launch flag: the ray-march kernel leaves cached envs to k_fast
 };
 
 enum { ERR_CAPACITY = 1, ERR_WAYPOINT = 2, ERR_RAYS = 4, ERR_BOUNDS = 8 };

@@ -623,7 +623,9 @@ k_step_many(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, flo
     const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
     dbg_init(D, smem, geo);
     for (int i = threadIdx.x; i < PEND_CAP; i += HEIST_WARPS_PER_CTA * 32) ctl->pend[i] = PEND_EMPTY;
-    const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
+    if (D.skip_cached && *D.n_uncached == 0) return;  // every env is served by k_fast (heist_fast.cuh)
+    int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
+    if (D.skip_cached && env >= 0 && D.env_cached[env]) env = -1;
     const bool have = env >= 0;
     const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
@@ -699,8 +701,9 @@ k_reset(Dev D, const uint8_t *__restrict__ mask) {
     dbg_init(D, smem, geo);
     for (int i = threadIdx.x; i < PEND_CAP; i += HEIST_WARPS_PER_CTA * 32) ctl->pend[i] = PEND_EMPTY;
     const int ctx_bytes = (int)warp_ctx_bytes(D.R, D.C, D.Kc, D.Kg);
+    if (D.skip_cached && *D.n_uncached == 0) return;
     const int env = D.slot2env[blockIdx.x * HEIST_WARPS_PER_CTA + warp];
-    const bool have = env >= 0 && (!mask || mask[env]);
+    const bool have = env >= 0 && (!mask || mask[env]) && !(D.skip_cached && D.env_cached[env]);
     const WarpCtx S = carve_warp_ctx(smem, geo, warp, D.R, D.C, D.Kc, D.Kg);
     EnvRegs E;
     int n_cams = 0, n_guards = 0;
