@@ -46,9 +46,12 @@ struct HeistHandle {
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
     int mode;        // heist_set_mode: HEIST_MODE_*
-    size_t camvis_smem, dyn_smem;
+    size_t camvis_smem, seq_smem;
     double *heads;      size_t heads_cap;     // k_heads output, grow-only [blocks][N][Kc]
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
+    uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
+    uint8_t *fin;       size_t fin_cap;       // k_seq -> k_finish: tick rebuilt its map [T][N]
+    int32_t *last_t;                          // [N] last rebuilt tick of the launch
     void *allocs[96];
     int n_allocs;
 };
@@ -80,6 +83,9 @@ extern "C" int heist_destroy(HeistHandle *h) {
     for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
     if (h->heads) cudaFree(h->heads);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->grec) cudaFree(h->grec);
+    if (h->fin) cudaFree(h->fin);
+    if (h->last_t) cudaFree(h->last_t);
     delete h;
     return 0;
 }
@@ -138,7 +144,9 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         const size_t HS = (size_t)d.L + 1;
         const size_t need = N * d.Kc * ((size_t)VC_POINTS * 8 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
                             N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
-        if (!(off && off[0] == '1') && need < free_b / 2) {
+        const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.Kg, d.L) <= (size_t)160 * 1024 &&
+                              FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024;
+        if (!(off && off[0] == '1') && need < free_b / 2 && seq_fits) {
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
             A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc);
             A(d.vg_mask, N * d.Kg * d.L * HS * VC_ROWS); A(d.vg_hval, N * d.Kg * HS);
@@ -161,16 +169,22 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);
-    h->dyn_smem = FAST_WARPS * dyn_warp_bytes(d.RW, d.Kg);
-#define SET_FAST(RPL, W)                                                                                                  \
-    CUDA_TRY(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem)); \
-    CUDA_TRY(cudaFuncSetAttribute(k_dyn<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->dyn_smem));
+    h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.Kg, d.L);
+#define SET_FAST(RPL, W) \
+    CUDA_TRY(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem));
     SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
 #undef SET_FAST
+    if (d.vc_p) {
+        CUDA_TRY(cudaFuncSetAttribute(k_seq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_seq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
+    }
     if (d.vc_p) {   // single-tick buffers up front, so that step / reset never allocate (CUDA-graph capture)
-        h->heads_cap = N * d.Kc; h->scratch_cap = N * d.RW;
+        h->heads_cap = N * d.Kc; h->scratch_cap = N * d.RW; h->grec_cap = N * d.Kg; h->fin_cap = N;
         CUDA_TRY(cudaMalloc(&h->heads, h->heads_cap * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->scratch, h->scratch_cap * sizeof(uint32_t)));
+        CUDA_TRY(cudaMalloc(&h->grec, h->grec_cap * sizeof(uint16_t)));
+        CUDA_TRY(cudaMalloc(&h->fin, h->fin_cap));
+        CUDA_TRY(cudaMalloc(&h->last_t, N * sizeof(int32_t)));
     }
     h->layout_smem = HEIST_WARPS_PER_CTA * layout_warp_bytes(d.RC, d.RW);
 #define SET_SMEM(E, B)                                                                                                    \
@@ -279,16 +293,22 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)Tc * NRW));
         uint32_t *cam = vis_traj ? vis_traj + (size_t)t0 * NRW : h->scratch;
         const size_t off = (size_t)t0 * N;
+        CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)Tc * N * d.Kg));
+        CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)Tc * N));
         k_heads<<<(unsigned)((N * d.Kc + 127) / 128), 128, 0, s>>>(d, Tc, do_reset, h->heads);
         const long long warps = (long long)N * nblk;
-        const unsigned g1 = (unsigned)((warps + FAST_WARPS - 1) / FAST_WARPS), g2 = (unsigned)((N + FAST_WARPS - 1) / FAST_WARPS);
+        const unsigned g1 = (unsigned)((warps + FAST_WARPS - 1) / FAST_WARPS), g2 = (unsigned)((N + SEQ_THREADS - 1) / SEQ_THREADS);
+        const int only_last = vis_traj ? 0 : 1;
+        const dim3 g3((unsigned)((N + 7) / 8), (unsigned)(only_last ? 1 : Tc)), g4((unsigned)((N + 7) / 8), (unsigned)Tc);
 #define GO(RPL, W)                                                                                                       \
     do {                                                                                                                 \
         k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, Tc, nblk, h->heads, cam, do_reset ? mask : nullptr); \
-        k_dyn<RPL, W><<<g2, FAST_WARPS * 32, h->dyn_smem, s>>>(                                                         \
+        k_seq<W><<<g2, SEQ_THREADS, h->seq_smem, s>>>(                                                                   \
             d, actions ? actions + off : nullptr, do_reset ? 0 : Tc, autoreset, reward ? reward + off : nullptr,         \
             reward64 ? reward64 + off : nullptr, done ? done + off : nullptr, status ? status + off : nullptr, cam,      \
-            vis_traj ? cam : nullptr, do_reset, mask);                                                                   \
+            h->grec, h->fin, h->last_t, do_reset, mask);                                                                 \
+        k_finish<RPL, W><<<g3, 256, 0, s>>>(d, Tc, cam, h->grec, h->fin, h->last_t, only_last, do_reset ? mask : nullptr); \
+        if (!only_last && !autoreset) k_fill<W><<<g4, 256, 0, s>>>(d, Tc, cam, h->fin);                                  \
     } while (0)
         if (r2) { if (w2) GO(2, 2); else GO(2, 1); }
         else { if (w2) GO(1, 2); else GO(1, 1); }
@@ -459,11 +479,12 @@ extern "C" int heist_check_errors(HeistHandle *h, void *stream) {
     CUDA_TRY(cudaMemcpy(&flags, h->d.err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
         CUDA_TRY(cudaMemset(h->d.err, 0, sizeof(int)));
-        return fail(-100 - flags, "device-side error:%s%s%s%s",
+        return fail(-100 - flags, "device-side error:%s%s%s%s%s",
                     (flags & ERR_CAPACITY) ? " capacity exceeded (max_walls/max_cams/max_guards/max_path)" : "",
                     (flags & ERR_WAYPOINT) ? " guard waypoint outside the grid" : "",
                     (flags & ERR_RAYS) ? " fov/vision_range too large" : "",
-                    (flags & ERR_BOUNDS) ? " cell-map access out of range (debug build)" : "");
+                    (flags & ERR_BOUNDS) ? " cell-map access out of range (debug build)" : "",
+                    (flags & ERR_STATE) ? " guard heading in the state view is not one of its path's headings" : "");
     }
     return 0;
 }

@@ -39,8 +39,14 @@ __device__ __forceinline__ int vc_rint_even(double x) { return __double2loint(__
 // One ray of the reference's ray-march on the bit maps (security.py:69-99 cameras, :170-190 guards), from
 // sample j0 on.  `mark(r, c)` receives every visible tile (the camera's own tile is filtered by the caller's
 // functor when needed).  Walls come from the row bitmaps in global memory: this is the rare / build-time path.
+struct VcGeo {   // what a ray needs to know about the grid
+    int R, C, W;
+    double deg2rad;
+};
+__device__ __forceinline__ VcGeo vc_geo(const Dev &D) { VcGeo g; g.R = D.R; g.C = D.C; g.W = D.W; g.deg2rad = D.deg2rad; return g; }
+
 template <typename Mark>
-__device__ __forceinline__ void vc_ray(const Dev &D, const uint32_t *__restrict__ wall, int row, int col, double fov,
+__device__ __forceinline__ void vc_ray(const VcGeo &D, const uint32_t *__restrict__ wall, int row, int col, double fov,
                                        double heading, int num_rays, int nsamp, double unit, int ri, Mark mark) {
     const double half_fov = __ddiv_rn(fov, 2.0);
     const double angle_deg =
@@ -60,7 +66,7 @@ __device__ __forceinline__ void vc_ray(const Dev &D, const uint32_t *__restrict_
 
 // Same march for a given direction angle (the representative of a gap).
 template <typename Mark>
-__device__ __forceinline__ void vc_ray_angle(const Dev &D, const uint32_t *__restrict__ wall, int row, int col,
+__device__ __forceinline__ void vc_ray_angle(const VcGeo &D, const uint32_t *__restrict__ wall, int row, int col,
                                              double angle_deg, int nsamp, double unit, Mark mark) {
     double dx, dy;
     ray_dir(angle_deg, D.deg2rad, dx, dy);
@@ -87,6 +93,9 @@ __device__ __forceinline__ bool vc_guard_cacheable(double fov, int range, int nu
 struct VcSmem {
     double key[VC_RAW];   // band starts (sorted), later the merged boundary points
     double end[VC_RAW];   // band ends
+    uint4 gm[VC_POINTS / 2][2];       // gap masks before compaction
+    unsigned short members[VC_RAW];   // raw bands merged into band i
+    unsigned short newidx[VC_RAW];    // band i -> index after dropping redundant bands (0xffff: dropped)
     unsigned mask[VC_ROWS];
     int n_raw, n_bands, ok;
 };
@@ -97,6 +106,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
     const int env = blockIdx.x, tid = threadIdx.x;
     const int n_cams = D.env_s[(size_t)env * 4 + 0], n_guards = D.env_s[(size_t)env * 4 + 1];
     const uint32_t *wall = D.wall + (size_t)env * D.RW;
+    const VcGeo geo = vc_geo(D);
     bool env_ok = true;
 
     for (int k = 0; k < n_cams; ++k) {
@@ -158,42 +168,78 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
             }
         }
         if (tid == 0) {
-            int nb = 0;
+            int nb = 0, mem = 1;
             double cs = S.key[0], ce = S.end[0];
             for (int i = 1; i < n_raw; ++i) {
                 const double s = S.key[i], e = S.end[i];
-                if (s <= ce) ce = fmax(ce, e);
-                else { S.key[nb] = cs; S.end[nb] = ce; ++nb; cs = s; ce = e; }
+                if (s <= ce) { ce = fmax(ce, e); ++mem; }
+                else { S.key[nb] = cs; S.end[nb] = ce; S.members[nb] = (unsigned short)mem; ++nb; cs = s; ce = e; mem = 1; }
             }
-            S.key[nb] = cs; S.end[nb] = ce; ++nb;
+            S.key[nb] = cs; S.end[nb] = ce; S.members[nb] = (unsigned short)mem; ++nb;
             S.n_bands = nb;
         }
         __syncthreads();
-        const int nb = S.n_bands;
-        const int n_points = 2 * (nb - 1);   // p[2g] = end of band g, p[2g+1] = start of band g + 1
-        if (n_points > VC_POINTS) ok = false;
+        const int nb0 = S.n_bands;   // gap g lies between band g and band g + 1
+        if (2 * (nb0 - 1) > VC_POINTS) ok = false;
         if (!ok) { env_ok = false; if (tid == 0) D.vc_meta[o * 2] = -1; __syncthreads(); continue; }
-        double *P = D.vc_p + o * VC_POINTS;
-        for (int g = tid; g < nb - 1; g += VC_BUILD_THREADS) { P[2 * g] = S.end[g]; P[2 * g + 1] = S.key[g + 1]; }
-        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = 0; D.vc_lo[o] = dom_lo; }
         // ---- 3. one representative ray per gap -> window mask ----
-        uint16_t *MK = D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS;
-        for (int g = tid; g < nb - 1; g += VC_BUILD_THREADS) {
+        for (int g = tid; g < nb0 - 1; g += VC_BUILD_THREADS) {
             const double mid = 0.5 * (S.end[g] + S.key[g + 1]);
             unsigned rows[VC_ROWS / 2];
 #pragma unroll
             for (int q = 0; q < VC_ROWS / 2; ++q) rows[q] = 0;
-            vc_ray_angle(D, wall, row, col, mid, nsamp, 0.5, [&](int r, int c) {
+            vc_ray_angle(geo, wall, row, col, mid, nsamp, 0.5, [&](int r, int c) {
                 if (r == row && c == col) return;  // (r, c) != (self.row, self.col), security.py:93
                 const int wr = r - row + range, wc = c - col + range;
                 const unsigned bit = 1u << (wc + 16 * (wr & 1));
 #pragma unroll
                 for (int q = 0; q < VC_ROWS / 2; ++q) if (q == (wr >> 1)) rows[q] |= bit;
             });
-            uint4 *dst = reinterpret_cast<uint4 *>(MK + (size_t)g * VC_ROWS);
-            dst[0] = make_uint4(rows[0], rows[1], rows[2], rows[3]);
-            dst[1] = make_uint4(rows[4], rows[5], rows[6], rows[7]);
+            S.gm[g][0] = make_uint4(rows[0], rows[1], rows[2], rows[3]);
+            S.gm[g][1] = make_uint4(rows[4], rows[5], rows[6], rows[7]);
         }
+        __syncthreads();
+        // ---- 3b. drop redundant bands.  A band that comes from ONE tie crossing separates two gaps whose tile
+        // sequences differ in that one sample only; a ray inside it takes one of the two sequences.  When both
+        // gaps mark the same tiles the ray does too, whichever way it rounds: band and gaps merge into one gap.
+        // (Bands merged from several crossings could mix the neighbours' sequences and are kept.)
+        if (tid == 0) {
+            int kept = 1;   // band 0 (left sentinel) stays
+            S.newidx[0] = 0;
+            for (int b = 1; b < nb0; ++b) {
+                bool drop = false;
+                if (b < nb0 - 1 && S.members[b] == 1) {
+                    const uint4 a0 = S.gm[b - 1][0], a1 = S.gm[b - 1][1], c0 = S.gm[b][0], c1 = S.gm[b][1];
+                    drop = a0.x == c0.x && a0.y == c0.y && a0.z == c0.z && a0.w == c0.w && a1.x == c1.x && a1.y == c1.y &&
+                           a1.z == c1.z && a1.w == c1.w;
+                }
+                S.newidx[b] = drop ? (unsigned short)0xffff : (unsigned short)kept;
+                if (!drop) ++kept;
+            }
+            S.n_bands = kept;
+        }
+        __syncthreads();
+        const int nb = S.n_bands;
+        const int n_points = 2 * (nb - 1);   // p[2g] = end of band g, p[2g+1] = start of band g + 1
+        {   // compact bands and gap masks in place (new index <= old index; whole chunk read before it is written)
+            for (int c0 = 0; c0 < nb0; c0 += VC_BUILD_THREADS) {
+                const int b = c0 + tid;
+                double ks = 0, ke = 0; uint4 m0 = make_uint4(0, 0, 0, 0), m1 = m0; int ni = 0xffff;
+                if (b < nb0) { ks = S.key[b]; ke = S.end[b]; ni = S.newidx[b]; if (b < nb0 - 1) { m0 = S.gm[b][0]; m1 = S.gm[b][1]; } }
+                __syncthreads();
+                // gap b (right of band b) keeps its mask under band b's new index; a dropped band's right gap
+                // equals its left one, which is already stored
+                if (b < nb0 && ni != 0xffff) { S.key[ni] = ks; S.end[ni] = ke; if (b < nb0 - 1) { S.gm[ni][0] = m0; S.gm[ni][1] = m1; } }
+                __syncthreads();
+            }
+        }
+        double *P = D.vc_p + o * VC_POINTS;
+        uint4 *MK4 = reinterpret_cast<uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
+        for (int g = tid; g < nb - 1; g += VC_BUILD_THREADS) {
+            P[2 * g] = S.end[g]; P[2 * g + 1] = S.key[g + 1];
+            MK4[2 * g] = S.gm[g][0]; MK4[2 * g + 1] = S.gm[g][1];
+        }
+        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = 2 * (nb0 - 1); D.vc_lo[o] = dom_lo; }
         // ---- 4. coarse index: points below each 1-degree bucket start ----
         uint16_t *IX = D.vc_idx + o * VC_IDX;
         for (int q = tid; q < VC_IDX; q += VC_BUILD_THREADS) {
@@ -240,7 +286,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
             if (tid < VC_ROWS) S.mask[tid] = 0;
             __syncthreads();
             for (int ri = tid; ri <= gi.w; ri += VC_BUILD_THREADS)
-                vc_ray(D, wall, row, col, fov, heading, gi.w, gi.z, 1.0, ri, [&](int r, int c) {
+                vc_ray(geo, wall, row, col, fov, heading, gi.w, gi.z, 1.0, ri, [&](int r, int c) {
                     atomicOr(&S.mask[r - row + gi.z], 1u << (c - col + gi.z));
                 });
             if (tid == 0) atomicOr(&S.mask[gi.z], 1u << gi.z);  // the guard's own tile is always lit (visibility.py:59)

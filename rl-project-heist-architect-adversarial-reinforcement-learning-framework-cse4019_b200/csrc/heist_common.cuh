@@ -60,7 +60,7 @@ struct Dev {
     int skip_cached;      // launch flag: the ray-march kernel leaves cached envs to k_fast
 };
 
-enum { ERR_CAPACITY = 1, ERR_WAYPOINT = 2, ERR_RAYS = 4, ERR_BOUNDS = 8 };
+enum { ERR_CAPACITY = 1, ERR_WAYPOINT = 2, ERR_RAYS = 4, ERR_BOUNDS = 8, ERR_STATE = 16 };
 enum { F_DONE = 1, F_DETECTED = 2, F_VAULT = 4 };
 
 // Python `x % 360.0` (floatobject.c float_rem): fmod, then shift negative remainders up.

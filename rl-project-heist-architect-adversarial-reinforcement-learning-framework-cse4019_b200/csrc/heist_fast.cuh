@@ -12,10 +12,10 @@
 //   k_cam_vis  warp per (env, tick block): union of the camera cones of every tick of the block from the cache
 //              (heist_cache.cuh) -> cam_vis[t][env] row bitmaps.  Embarrassingly parallel over env x time: no
 //              sequential dependence, no load imbalance between envs, latency hidden by occupancy;
-//   k_dyn      warp per env, lane = grid row, sequential in t: move, guard patrol + guard cone (one cached mask
-//              per (waypoint, heading)), cam_vis[t] OR guards -> visibility map, detection / vault / timeout,
-//              rewards, auto-reset.  HBM-streaming: reads cam_vis + actions, writes the visibility trajectory
-//              and reward / done / status.
+//   k_seq      thread per env, sequential in t: move, guard patrol + guard cone (one cached mask per (waypoint,
+//              heading)), cam_vis[t] OR guards -> visibility map, detection / vault / timeout, rewards,
+//              auto-reset.  HBM-streaming: reads cam_vis + actions, finishes the visibility trajectory in place,
+//              writes reward / done / status.
 // Rays that fall inside a tie band (or outside the cached angle domain) are marched exactly like the reference
 // does, so results are bit-identical to heist_step.cuh's.
 #pragma once
@@ -29,18 +29,11 @@ struct FastCam {
     double heading, speed, fov, inv_step, dom_lo;
     const double *P;        // boundary points
     const uint16_t *MK;     // gap masks
-    int row, col, range, num_rays, n_points, s0, carry, pad;
-};
-struct FastGuard {
-    double heading, fov;
-    int len, speed, range, num_rays, idx, hslot, nh, pad;
+    int row, col, range, num_rays, n_points, s0, pad0, pad1;
 };
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
     return (size_t)Kc * sizeof(FastCam) + (((size_t)RW * 4 + 15) & ~(size_t)15) + 32;
-}
-__host__ __device__ inline size_t dyn_warp_bytes(int RW, int Kg) {
-    return (size_t)Kg * sizeof(FastGuard) + (((size_t)RW * 4 + 15) & ~(size_t)15);
 }
 
 // bit (r, c) of a lane-per-row bitmap (all lanes get the answer; r, c warp-uniform)
@@ -93,9 +86,27 @@ __device__ __forceinline__ int fast_nrays(double p, double base, double inv_step
     return max(0, min(NR, __double2int_ru((p - base) * inv_step)));
 }
 
+// Rare path of k_cam_vis, kept out of line: camera rays [r0, r1) sit on (or within 1e-9 degree of) a rounding
+// tie, or outside the cached angle domain -> march them exactly like the reference does.
+__device__ __noinline__ void cam_exact_rays(VcGeo D, const uint32_t *wall, uint32_t *xvis, const FastCam *cam, int r0,
+                                            int r1) {
+    const int row = cam->row, col = cam->col, W = D.W;
+    for (int ri = r0; ri < r1; ++ri)
+        vc_ray(D, wall, row, col, cam->fov, cam->heading, cam->num_rays, 2 * cam->range, 0.5, ri, [&](int r, int c) {
+            if (r == row && c == col) return;   // (r, c) != (self.row, self.col), security.py:93
+            atomicOr(&xvis[r * W + (c >> 5)], 1u << (c & 31));
+        });
+}
+
+#define CV_PASSES 4   // 32-segment passes whose loads are in flight together
+
 // Union of the camera cones of one env for FAST_TB consecutive ticks -> out[t][env][RW].
+// One pass = 32 consecutive segments of a camera's boundary-point table, starting on an even segment: lane j
+// classifies segment sb + j (ray count below its upper boundary point; the lower one comes from lane j - 1), and
+// -- independently, so that neither load waits for the other -- loads one 16-byte half of the mask of gap
+// (sb >> 1) + (j >> 1).  A gap's mask is kept iff its segment turns out to contain a ray.
 template <int RPL, int W>
-__global__ void __launch_bounds__(FAST_WARPS * 32)
+__global__ void __launch_bounds__(FAST_WARPS * 32, 6)
 k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -127,15 +138,15 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
     for (int i = lane; i < D.RW; i += 32) xvis[i] = 0;
     const int t_end = min(T, (b + 1) * FAST_TB);
     for (int t = b * FAST_TB; t < t_end; ++t) {
-        // every camera's window start (coarse index) and the ray count below it: one load level for all cameras
+        // every camera's window start from its coarse index: one load level for all cameras of the env.
+        // Segments below IX[q] hold no ray of this tick; start one earlier (its upper point gives lane 1 its
+        // lower ray count) and on an even segment.
         if (lane < n_cams) {
             FastCam &Cm = cams[lane];
             if (t > b * FAST_TB) Cm.heading = py_mod360(__dadd_rn(Cm.heading, Cm.speed));
             const double base = Cm.heading - Cm.fov * 0.5;
             const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
-            const int s0 = IX[q];
-            Cm.s0 = s0;
-            Cm.carry = s0 > 0 ? fast_nrays(Cm.P[s0 - 1], base, Cm.inv_step, Cm.num_rays + 1) : 0;
+            Cm.s0 = max(0, (int)IX[q] - 1) & ~1;
         }
         __syncwarp();
         uint32_t vis[RPL][W];
@@ -149,50 +160,47 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
             const double base = Cm.heading - Cm.fov * 0.5, inv_step = Cm.inv_step;
             const int NR = Cm.num_rays + 1, n_points = Cm.n_points;
             const double *P = Cm.P;
-            int carry = Cm.carry;
-            uint32_t acc[VC_ROWS / 2];
-#pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
+            const uint4 *MK4 = reinterpret_cast<const uint4 *>(Cm.MK);   // gap g = uint4 2g, 2g + 1
+            int carry = 0;
+            bool first = Cm.s0 > 0;   // lane 0 of the first pass only supplies the lower count of lane 1
+            uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;   // even lanes: mask words 0-3, odd lanes: words 4-7
             bool more = true;
-            for (int sb = Cm.s0; more; sb += 128) {
-                double pv[4];   // four 32-segment passes in flight
+            for (int sb = Cm.s0; more; sb += 32 * CV_PASSES) {
+                double pv[CV_PASSES];
+                uint4 mv[CV_PASSES];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < CV_PASSES; ++u) {
                     const int s = sb + 32 * u + lane;
                     pv[u] = s < n_points ? P[s] : 1e300;
+                    // half (lane & 1) of gap (sb + 32u) / 2 + (lane >> 1), i.e. of segment sb + 32u + (lane | 1)
+                    mv[u] = (sb + 32 * u + (lane | 1)) < n_points ? __ldg(MK4 + (sb + 32 * u) + lane) : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < CV_PASSES; ++u) {
                     if (!more) break;
-                    const int s = sb + 32 * u + lane;
                     const int n_s = fast_nrays(pv[u], base, inv_step, NR);
                     int n_prev = __shfl_up_sync(0xffffffffu, n_s, 1);
-                    if (lane == 0) n_prev = carry;
+                    if (lane == 0) n_prev = first ? n_s : carry;
+                    first = false;
                     carry = __shfl_sync(0xffffffffu, n_s, 31);
-                    if (n_s > n_prev) {
-                        if (s & 1) {   // gap (s - 1) / 2: every ray inside marks the same tiles
-                            const uint4 *mk = reinterpret_cast<const uint4 *>(Cm.MK + (size_t)(s >> 1) * VC_ROWS);
-                            const uint4 m0 = __ldg(mk), m1 = __ldg(mk + 1);
-                            acc[0] |= m0.x; acc[1] |= m0.y; acc[2] |= m0.z; acc[3] |= m0.w;
-                            acc[4] |= m1.x; acc[5] |= m1.y; acc[6] |= m1.z; acc[7] |= m1.w;
-                        } else {       // band: rays on (or within 1e-9 degree of) a rounding tie -> exact march
-                            exact_used = true;
-                            for (int ri = n_prev; ri < n_s; ++ri)
-                                vc_ray(D, wall_g, Cm.row, Cm.col, Cm.fov, Cm.heading, Cm.num_rays, 2 * Cm.range, 0.5, ri,
-                                       [&](int r, int c) {
-                                           if (r == Cm.row && c == Cm.col) return;
-                                           atomicOr(&xvis[r * D.W + (c >> 5)], 1u << (c & 31));
-                                       });
-                        }
+                    const bool hit = n_s > n_prev;
+                    const unsigned hits = __ballot_sync(0xffffffffu, hit);
+                    if ((hits >> (lane | 1)) & 1u) { acc0 |= mv[u].x; acc1 |= mv[u].y; acc2 |= mv[u].z; acc3 |= mv[u].w; }
+                    if (hits & 0x55555555u) {   // a band holds a ray (rare)
+                        exact_used = true;
+                        if (hit && !(lane & 1)) cam_exact_rays(vc_geo(D), wall_g, xvis, &Cm, n_prev, n_s);
                     }
                     if (carry >= NR) more = false;  // warp-uniform
                 }
             }
-#pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(0xffffffffu, acc[i]);
+            // words 0-3 from the even lanes, 4-7 from the odd lanes
+            const uint32_t e0 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc0), e1 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc1);
+            const uint32_t e2 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc2), e3 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc3);
+            const uint32_t o0 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc0 : 0u), o1 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc1 : 0u);
+            const uint32_t o2 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc2 : 0u), o3 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc3 : 0u);
             if (lane == 0) {
-                reinterpret_cast<uint4 *>(stage)[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-                reinterpret_cast<uint4 *>(stage)[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+                reinterpret_cast<uint4 *>(stage)[0] = make_uint4(e0, e1, e2, e3);
+                reinterpret_cast<uint4 *>(stage)[1] = make_uint4(o0, o1, o2, o3);
             }
             __syncwarp();
             const uint16_t *rows = reinterpret_cast<const uint16_t *>(stage);
@@ -221,61 +229,57 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
     }
 }
 
-// Guards of the env at their current waypoints -> OR into vis (guard cones + own tiles, visibility.py:44-59).
-template <int RPL, int W>
-__device__ __forceinline__ void fast_guards(const Dev &D, int env, int lane, uint32_t (&vis)[RPL][W], const FastGuard *guards,
-                                            int n_guards, uint32_t *xvis) {
-    bool exact_used = false;
-    for (int g = 0; g < n_guards; ++g) {
-        const FastGuard &G = guards[g];
-        const size_t o = (size_t)env * D.Kg + g;
-        const int row = D.guard_path[(o * D.L + G.idx) * 2], col = D.guard_path[(o * D.L + G.idx) * 2 + 1];
-        if (G.hslot >= 0) {
-            const uint16_t *mk = D.vg_mask + ((o * D.L + G.idx) * (size_t)(D.L + 1) + G.hslot) * VC_ROWS;
-#pragma unroll
-            for (int a = 0; a < RPL; ++a) {
-                const int wr = lane + 32 * a - (row - G.range);
-                if (wr >= 0 && wr <= 2 * G.range) fast_or_row<W>(vis[a], mk[wr], col - G.range);
-            }
-        } else {   // a heading that is not one of the path's (state written by hand): march the whole cone
-            exact_used = true;
-            const uint32_t *wall_g = D.wall + (size_t)env * D.RW;
-            for (int ri = lane; ri <= G.num_rays; ri += 32)
-                vc_ray(D, wall_g, row, col, G.fov, G.heading, G.num_rays, G.range, 1.0, ri,
-                       [&](int r, int c) { atomicOr(&xvis[r * D.W + (c >> 5)], 1u << (c & 31)); });
-            if (lane == 0) atomicOr(&xvis[row * D.W + (col >> 5)], 1u << (col & 31));
-        }
-    }
-    if (__any_sync(0xffffffffu, exact_used)) {
-        __syncwarp();
-#pragma unroll
-        for (int a = 0; a < RPL; ++a) {
-            const int r = lane + 32 * a;
-            if (r < D.R) {
-#pragma unroll
-                for (int w = 0; w < W; ++w) { vis[a][w] |= xvis[r * D.W + w]; xvis[r * D.W + w] = 0; }
-            }
-        }
-        __syncwarp();
-    }
+// ---------------------------------------------------------------------------------------------
+// k_seq: the sequential part of a launch, one THREAD per env (everything here is scalar per env: position,
+// rewards, guard indices; a warp per env would execute it 32 times over).  Per tick: move, guards advance,
+// detection from ONE word of cam_vis[t] OR the guards' cached masks at the Solver's row, vault / timeout,
+// rewards, auto-reset.  The Solver's path does not depend on what it sees (until an episode ends), so the
+// cam_vis word of tick t + 1 is prefetched at the predicted row while tick t is being decided.
+// What k_finish needs to complete the maps -- the guards' (waypoint, heading slot) of every tick -- is recorded.
+// Walls and per-guard patrol data are staged in shared memory as planes [item][thread] (no bank conflicts).
+// ---------------------------------------------------------------------------------------------
+#define SEQ_THREADS 32
+#define SEQ_PG 4         // guards whose mask row is prefetched one tick ahead
+__host__ __device__ inline size_t seq_thread_bytes(int RW, int Kg, int L) { return (size_t)RW * 4 + (size_t)Kg * (5 + 3 * (size_t)L); }
+
+struct SeqGuards {   // byte planes in shared memory, one column per thread
+    uint8_t *base;
+    int Kg, L, tid;
+    __device__ __forceinline__ uint8_t &len(int g)   { return base[(size_t)(g * 5 + 0) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &stp(int g)   { return base[(size_t)(g * 5 + 1) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &range(int g) { return base[(size_t)(g * 5 + 2) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &idx(int g)   { return base[(size_t)(g * 5 + 3) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &hs(int g)    { return base[(size_t)(g * 5 + 4) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &pr(int g, int k)    { return base[(size_t)(Kg * 5 + (g * L + k) * 3 + 0) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &pc(int g, int k)    { return base[(size_t)(Kg * 5 + (g * L + k) * 3 + 1) * SEQ_THREADS + tid]; }
+    __device__ __forceinline__ uint8_t &hslot(int g, int k) { return base[(size_t)(Kg * 5 + (g * L + k) * 3 + 2) * SEQ_THREADS + tid]; }
+};
+
+// guard cone + own tile of guard (o = env * Kg + g) at waypoint k with heading slot hs, grid row r
+// (visibility.py:44-59) -> OR into the W words of that row
+template <int W>
+__device__ __forceinline__ void guard_row(const Dev &D, size_t o, int k, int hs, int prow, int pcol, int rng, int r,
+                                          uint32_t (&v)[W]) {
+    const int wr = r - (prow - rng);
+    if (wr < 0 || wr > 2 * rng) return;
+    const unsigned bits = D.vg_mask[((o * D.L + k) * (size_t)(D.L + 1) + hs) * VC_ROWS + wr];
+    fast_or_row<W>(v, bits, pcol - rng);
 }
 
-// T steps per launch (T = 1: HeistEnvironment.step), or -- with do_reset -- HeistEnvironment.reset for the masked
-// envs.  cam_vis[t][env][RW] holds the camera part of tick t's visibility (k_cam_vis); when vis_out == cam_vis the
-// trajectory is finished in place.
-template <int RPL, int W>
-__global__ void __launch_bounds__(FAST_WARPS * 32)
-k_dyn(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
+template <int W>
+__global__ void __launch_bounds__(SEQ_THREADS)
+k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
       double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
-      const uint32_t *cam_vis, uint32_t *vis_out, int do_reset, const uint8_t *__restrict__ mask) {
+      const uint32_t *__restrict__ cam_vis, uint16_t *__restrict__ grec, uint8_t *__restrict__ fin,
+      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int env = blockIdx.x * FAST_WARPS + warp;
+    const int tid = threadIdx.x;
+    const int env = blockIdx.x * SEQ_THREADS + tid;
     if (env >= D.N || !D.env_cached[env]) return;
-    if (do_reset && mask && !mask[env]) return;
-    unsigned char *sp = smem + (size_t)warp * dyn_warp_bytes(D.RW, D.Kg);
-    FastGuard *guards = reinterpret_cast<FastGuard *>(sp);    sp += (size_t)D.Kg * sizeof(FastGuard);
-    uint32_t *xvis = reinterpret_cast<uint32_t *>(sp);
+    if (do_reset && mask && !mask[env]) { last_t[env] = -1; return; }
+    uint32_t *wall = reinterpret_cast<uint32_t *>(smem);   // plane [word][thread]
+    SeqGuards G;
+    G.base = smem + (size_t)D.RW * 4 * SEQ_THREADS; G.Kg = D.Kg; G.L = D.L; G.tid = tid;
 
     // ---- load ----
     const int4 es = *reinterpret_cast<const int4 *>(D.env_s + (size_t)env * 4);
@@ -285,163 +289,249 @@ k_dyn(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     EnvRegs E;
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    uint32_t wall[RPL][W], vis[RPL][W], cam[RPL][W];
-#pragma unroll
-    for (int a = 0; a < RPL; ++a) {
-        const int r = lane + 32 * a;
-#pragma unroll
-        for (int w = 0; w < W; ++w) {
-            wall[a][w] = r < D.R ? D.wall[(size_t)env * D.RW + r * D.W + w] : 0xffffffffu;
-            vis[a][w] = r < D.R ? D.vis[(size_t)env * D.RW + r * D.W + w] : 0u;
-            cam[a][w] = r < D.R ? cam_vis[(size_t)env * D.RW + r * D.W + w] : 0u;   // tick 0
+    for (int i = 0; i < D.RW; ++i) wall[i * SEQ_THREADS + tid] = D.wall[(size_t)env * D.RW + i];
+    for (int g = 0; g < n_guards; ++g) {
+        const size_t o = (size_t)env * D.Kg + g;
+        const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);   // len, speed, range, num_rays
+        G.len(g) = (uint8_t)gi.x; G.stp(g) = (uint8_t)py_imod(gi.y, gi.x); G.range(g) = (uint8_t)gi.z;
+        G.idx(g) = (uint8_t)D.guard_idx[o];
+        for (int k = 0; k < gi.x; ++k) {
+            G.pr(g, k) = D.guard_path[(o * D.L + k) * 2]; G.pc(g, k) = D.guard_path[(o * D.L + k) * 2 + 1];
+            G.hslot(g, k) = D.vg_hslot[o * D.L + k];
         }
+        // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
+        // state view; it is reported (ERR_STATE) and treated as the default heading.
+        const double h = D.guard_heading[o];
+        int hs = -1;
+        const int nh = D.vg_nh[o];
+        for (int s = 0; s < nh; ++s)
+            if (__double_as_longlong(D.vg_hval[o * (D.L + 1) + s]) == __double_as_longlong(h)) { hs = s; break; }
+        if (hs < 0) { atomicOr(D.err, ERR_STATE); hs = 0; }
+        G.hs(g) = (uint8_t)hs;
     }
-    for (int i = lane; i < D.RW; i += 32) xvis[i] = 0;
-    if (lane < n_guards) {
-        const size_t o = (size_t)env * D.Kg + lane;
-        FastGuard &G = guards[lane];
-        const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);
-        G.len = gi.x; G.speed = gi.y; G.range = gi.z; G.num_rays = gi.w;
-        G.fov = D.guard_fov[o]; G.heading = D.guard_heading[o]; G.idx = D.guard_idx[o];
-        G.nh = D.vg_nh[o];
-        G.hslot = -1;
-        for (int s = 0; s < G.nh; ++s)
-            if (__double_as_longlong(D.vg_hval[o * (D.L + 1) + s]) == __double_as_longlong(G.heading)) { G.hslot = s; break; }
-    }
-    __syncwarp();
 
     int status = HEIST_RUNNING;
-    int n_adv = 0;   // camera updates executed by this launch
+    int n_adv = 0;           // camera updates executed by this launch
+    int last = -1;           // last tick of this launch whose visibility map was rebuilt
+    // HeistEnvironment.reset (environment.py:183-214): headings persist, guards back to waypoint 0.  The map after a
+    // reset is completed by k_finish from the recorded guard state; nothing is detected on a reset.
+#define SEQ_RESET_STATE()                                                                    \
+    do {                                                                                     \
+        E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0;                           \
+        E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c); E.init = E.prev;               \
+        for (int g = 0; g < n_guards; ++g) G.idx(g) = 0;                                     \
+    } while (0)
+#define SEQ_RECORD(o_)                                                                                         \
+    do {                                                                                                       \
+        for (int g = 0; g < n_guards; ++g) grec[(o_) * D.Kg + g] = (uint16_t)(G.idx(g) | (G.hs(g) << 8));    \
+    } while (0)
     if (do_reset) {
-        E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0;
-        E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c); E.init = E.prev;
-        if (lane < n_guards) guards[lane].idx = 0;
-        __syncwarp();
-#pragma unroll
-        for (int a = 0; a < RPL; ++a)
-#pragma unroll
-            for (int w = 0; w < W; ++w) vis[a][w] = cam[a][w];
-        fast_guards<RPL, W>(D, env, lane, vis, guards, n_guards, xvis);
+        SEQ_RESET_STATE();
+        fin[env] = 1; SEQ_RECORD((size_t)env); last = 0;
+        T = 0;
     }
-    bool pending_reset = false;
-    for (int t = 0; t < T;) {
+    // Speculation: until an episode ends, the Solver's path and the guards' patrol do not depend on what is seen.
+    // At the end of tick t the state tick t + 1 will be decided in is therefore known (unless t ends the episode),
+    // and the words that decide it -- the cam_vis word(s) and the guards' mask rows at the Solver's next row -- are
+    // requested one tick ahead; actions are requested two ticks ahead.  Every thread runs exactly T iterations
+    // (an auto-reset is part of the tick that ended the episode), so the threads of a warp stay in step.
+    int a_cur = 0, a_nxt = 0;
+    if (T > 0) { a_cur = actions[env]; a_nxt = T > 1 ? actions[(size_t)D.N + env] : 0; }
+    int pre_row = -1;
+    uint32_t pre[W];
+    unsigned pre_g[SEQ_PG], pre_key[SEQ_PG];   // mask row / (waypoint | slot << 8) it was fetched for
+#pragma unroll
+    for (int w = 0; w < W; ++w) pre[w] = 0;
+#pragma unroll
+    for (int g = 0; g < SEQ_PG; ++g) { pre_g[g] = 0; pre_key[g] = 0xffffffffu; }
+    for (int t = 0; t < T; ++t) {
         const size_t o = (size_t)t * D.N + env;
-        int kind = 0;  // 0: already done, 1: step, 2: auto-reset
-        if (pending_reset) {   // the trainer's `if done: reset()` (environment.py:183-214)
-            E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0;
-            E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c); E.init = E.prev;
-            if (lane < n_guards) guards[lane].idx = 0;
-            kind = 2;
-        } else if (!(E.flags & F_DONE)) {   // a done env is not mutated (:232-233)
-            const int action = actions[o];
+        bool rebuilt = false;
+        double rw = 0.0;
+        status = HEIST_ALREADY_DONE;
+        if (!(E.flags & F_DONE)) {   // a done env is not mutated (:232-233)
             // move (:239-246): blocked by the grid edge or a WALL tile
-            const int nr = E.r + (action == 2) - (action == 1), nc = E.c + (action == 4) - (action == 3);
-            if (nr >= 0 && nr < D.R && nc >= 0 && nc < D.C) {   // (warp-uniform)
-                if (!fast_bit<RPL, W>(wall, nr, nc)) { E.r = nr; E.c = nc; }
-            }
+            const int nr = E.r + (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
+            if (nr >= 0 && nr < D.R && nc >= 0 && nc < D.C &&
+                !((wall[(nr * D.W + (nc >> 5)) * SEQ_THREADS + tid] >> (nc & 31)) & 1u)) { E.r = nr; E.c = nc; }
             ++n_adv;   // cameras rotate (:251-252): their cones for this tick are cam_vis[t]
-            if (lane < n_guards) {
-                FastGuard &G = guards[lane];
-                if (G.len >= 2) {
-                    const size_t go = ((size_t)env * D.Kg + lane) * D.L;
-                    const int old = G.idx;
-                    const double h = D.guard_head[go + old];
-                    if (h == h) { G.heading = h; G.hslot = D.vg_hslot[go + old]; }  // NaN: the move is (0, 0)
-                    G.idx = py_imod(old + G.speed, G.len);
+            for (int g = 0; g < n_guards; ++g) {   // Guard.update (security.py:145-159)
+                const int len = G.len(g);
+                if (len >= 2) {
+                    const int old = G.idx(g);
+                    const int hsl = G.hslot(g, old);
+                    if (hsl != 255) G.hs(g) = (uint8_t)hsl;   // 255: the move is (0, 0), heading unchanged
+                    int ni = old + G.stp(g);
+                    if (ni >= len) ni -= len;
+                    G.idx(g) = (uint8_t)ni;
                 }
             }
-            kind = 1;
+            // visibility at the Solver's tile: camera cones OR guard cones / own tiles
+            uint32_t v[W];
+            const bool hit = E.r == pre_row;
+            if (hit) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) v[w] = pre[w];
+            } else {
+#pragma unroll
+                for (int w = 0; w < W; ++w) v[w] = cam_vis[o * D.RW + E.r * D.W + w];
+            }
+#pragma unroll
+            for (int g = 0; g < SEQ_PG; ++g) {
+                if (g < n_guards) {
+                    const int k = G.idx(g), hs = G.hs(g), rng = G.range(g);
+                    if (hit && pre_key[g] == (unsigned)(k | (hs << 8))) fast_or_row<W>(v, pre_g[g], (int)G.pc(g, k) - rng);
+                    else guard_row<W>(D, (size_t)env * D.Kg + g, k, hs, G.pr(g, k), G.pc(g, k), rng, E.r, v);
+                }
+            }
+            for (int g = SEQ_PG; g < n_guards; ++g) {
+                const int k = G.idx(g);
+                guard_row<W>(D, (size_t)env * D.Kg + g, k, G.hs(g), G.pr(g, k), G.pc(g, k), G.range(g), E.r, v);
+            }
+            const bool detected = (v[(W == 2) ? (E.c >> 5) : 0] >> (E.c & 31)) & 1u;
+            // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297)
+            rw = D.reward_step;
+            status = HEIST_RUNNING;
+            const int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
+            rw = __dadd_rn(rw, __dmul_rn((double)(E.prev - curr), 0.1));
+            E.prev = curr;
+            if (curr <= 3 && E.init > 3) rw = __dadd_rn(rw, __dmul_rn(0.05, (double)(3 - curr)));
+            if (detected) {
+                E.flags |= F_DETECTED | F_DONE;
+                rw = __dadd_rn(rw, D.reward_detection);
+                status = HEIST_DETECTED;
+            }
+            if (E.r == D.vault_r && E.c == D.vault_c) {
+                E.flags |= F_VAULT | F_DONE;
+                rw = __dadd_rn(rw, D.reward_vault);
+                status = HEIST_VAULT_REACHED;
+            }
+            E.tick += 1;
+            if (E.tick >= D.max_steps) {
+                E.flags |= F_DONE;
+                status = HEIST_TIMEOUT;
+                double cf = __dsub_rn(1.0, __ddiv_rn((double)curr, (double)max(E.init, 1)));
+                if (!(cf > 0.0)) cf = 0.0;
+                rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
+            }
+            if (status == HEIST_VAULT_REACHED) E.n_vault++;        // training.py:535-540
+            else if (status == HEIST_DETECTED) E.n_detect++;
+            else if (status == HEIST_TIMEOUT) E.n_timeout++;
+            rebuilt = true;
         }
-        __syncwarp();
-        if (kind) {
+        if (reward) reward[o] = (float)rw;
+        if (reward64) reward64[o] = rw;
+        if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
+        if (status_out) status_out[o] = (uint8_t)status;
+        if (autoreset && (E.flags & F_DONE)) { SEQ_RESET_STATE(); rebuilt = true; }   // the trainer's `if done: reset()`
+        // the visibility map of tick t is final: tell k_finish how to complete it
+        fin[o] = rebuilt ? 1 : 0;
+        if (rebuilt) { last = t; SEQ_RECORD(o); }
+        // requests for tick t + 1
+        a_cur = a_nxt;
+        if (t + 2 < T) a_nxt = actions[o + 2 * (size_t)D.N];
+        pre_row = -1;
+        if (t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state
+            const int nr = E.r + (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
+            pre_row = E.r;
+            if (nr >= 0 && nr < D.R && nc >= 0 && nc < D.C &&
+                !((wall[(nr * D.W + (nc >> 5)) * SEQ_THREADS + tid] >> (nc & 31)) & 1u)) pre_row = nr;
 #pragma unroll
-            for (int a = 0; a < RPL; ++a)
+            for (int w = 0; w < W; ++w) pre[w] = cam_vis[(o + D.N) * D.RW + pre_row * D.W + w];
 #pragma unroll
-                for (int w = 0; w < W; ++w) vis[a][w] = cam[a][w];
-            fast_guards<RPL, W>(D, env, lane, vis, guards, n_guards, xvis);
-        }
-        if (kind != 2) {
-            double rw = 0.0;
-            status = HEIST_ALREADY_DONE;
-            if (kind == 1) {
-                // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297)
-                rw = D.reward_step;
-                status = HEIST_RUNNING;
-                const int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
-                rw = __dadd_rn(rw, __dmul_rn((double)(E.prev - curr), 0.1));
-                E.prev = curr;
-                if (curr <= 3 && E.init > 3) rw = __dadd_rn(rw, __dmul_rn(0.05, (double)(3 - curr)));
-                if (fast_bit<RPL, W>(vis, E.r, E.c)) {
-                    E.flags |= F_DETECTED | F_DONE;
-                    rw = __dadd_rn(rw, D.reward_detection);
-                    status = HEIST_DETECTED;
-                }
-                if (E.r == D.vault_r && E.c == D.vault_c) {
-                    E.flags |= F_VAULT | F_DONE;
-                    rw = __dadd_rn(rw, D.reward_vault);
-                    status = HEIST_VAULT_REACHED;
-                }
-                E.tick += 1;
-                if (E.tick >= D.max_steps) {
-                    E.flags |= F_DONE;
-                    status = HEIST_TIMEOUT;
-                    double cf = __dsub_rn(1.0, __ddiv_rn((double)curr, (double)max(E.init, 1)));
-                    if (!(cf > 0.0)) cf = 0.0;
-                    rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
-                }
-                if (status == HEIST_VAULT_REACHED) E.n_vault++;        // training.py:535-540
-                else if (status == HEIST_DETECTED) E.n_detect++;
-                else if (status == HEIST_TIMEOUT) E.n_timeout++;
-            }
-            if (lane == 0) {
-                if (reward) reward[o] = (float)rw;
-                if (reward64) reward64[o] = rw;
-                if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
-                if (status_out) status_out[o] = (uint8_t)status;
-            }
-            pending_reset = autoreset && (E.flags & F_DONE);
-        } else pending_reset = false;
-        if (!pending_reset) {   // tick t is complete: its visibility map is final
-            ++t;
-#pragma unroll
-            for (int a = 0; a < RPL; ++a) {
-                const int r = lane + 32 * a;
-                if (r < D.R) {
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        const size_t at = o * D.RW + r * D.W + w;
-                        if (t < T) cam[a][w] = cam_vis[at + (size_t)D.N * D.RW];   // next tick's camera cones
-                        if (vis_out) vis_out[at] = vis[a][w];
+            for (int g = 0; g < SEQ_PG; ++g) {
+                if (g < n_guards) {
+                    int k = G.idx(g), hs = G.hs(g);
+                    const int len = G.len(g), rng = G.range(g);
+                    if (len >= 2) {
+                        const int hsl = G.hslot(g, k);
+                        if (hsl != 255) hs = hsl;
+                        k += G.stp(g);
+                        if (k >= len) k -= len;
                     }
+                    pre_key[g] = (unsigned)(k | (hs << 8));
+                    const int wr = pre_row - ((int)G.pr(g, k) - rng);
+                    pre_g[g] = 0;
+                    if (wr >= 0 && wr <= 2 * rng)
+                        pre_g[g] = D.vg_mask[((((size_t)env * D.Kg + g) * D.L + k) * (size_t)(D.L + 1) + hs) * VC_ROWS + wr];
                 }
             }
         }
     }
+#undef SEQ_RESET_STATE
+#undef SEQ_RECORD
 
     // ---- store ----
-    if (lane == 0) {
-        *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
-        *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =
-            make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
-    }
-    if (lane < n_cams) {   // headings after the camera updates this launch executed
-        const size_t co = (size_t)env * D.Kc + lane;
+    last_t[env] = last;
+    *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
+    *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =
+        make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
+    for (int k = 0; k < n_cams; ++k) {   // headings after the camera updates this launch executed
+        const size_t co = (size_t)env * D.Kc + k;
         double h = D.cam_heading[co];
         const double speed = D.cam_f[co * 2 + 1];
         for (int a = 0; a < n_adv; ++a) h = py_mod360(__dadd_rn(h, speed));
         D.cam_heading[co] = h;
     }
-    if (lane < n_guards) {
-        const size_t go = (size_t)env * D.Kg + lane;
-        D.guard_heading[go] = guards[lane].heading;
-        D.guard_idx[go] = guards[lane].idx;
+    for (int g = 0; g < n_guards; ++g) {
+        const size_t go = (size_t)env * D.Kg + g;
+        D.guard_heading[go] = D.vg_hval[go * (D.L + 1) + G.hs(g)];
+        D.guard_idx[go] = G.idx(g);
+    }
+}
+
+// k_finish: warp per (tick, env), lane = grid row: visibility row = cam_vis row OR the guards' masks at the state
+// k_seq recorded -> written in place (the buffer is the caller's trajectory, or scratch) and, for the last
+// rebuilt tick of an env, to its current map D.vis.  only_last: no trajectory wanted -- warp per env.
+// Ticks an env spent done without auto-reset (fin == 0) keep the env's current map; they are filled by k_fill
+// once D.vis is final.
+template <int RPL, int W>
+__global__ void __launch_bounds__(256)
+k_finish(Dev D, int T, uint32_t *buf, const uint16_t *__restrict__ grec, const uint8_t *__restrict__ fin,
+         const int32_t *__restrict__ last_t, int only_last, const uint8_t *__restrict__ mask) {
+    const int lane = threadIdx.x & 31;   // grid: x = env / 8, y = tick
+    const int env = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (env >= D.N || !D.env_cached[env] || (mask && !mask[env])) return;
+    const int lt = last_t[env];
+    const int t = only_last ? lt : (int)blockIdx.y;
+    if (t < 0) return;
+    const size_t o = (size_t)t * D.N + env;
+    if (!fin[o]) return;
+    uint32_t v[RPL][W];
+#pragma unroll
+    for (int a = 0; a < RPL; ++a)
+#pragma unroll
+        for (int w = 0; w < W; ++w) { const int r = lane + 32 * a; v[a][w] = r < D.R ? buf[o * D.RW + r * D.W + w] : 0u; }
+    const int n_guards = D.env_s[(size_t)env * 4 + 1];
+    for (int g = 0; g < n_guards; ++g) {
+        const size_t go = (size_t)env * D.Kg + g;
+        const unsigned rec = grec[o * D.Kg + g];
+        const int k = rec & 255, hs = rec >> 8;
+        const int prow = D.guard_path[(go * D.L + k) * 2], pcol = D.guard_path[(go * D.L + k) * 2 + 1], rng = D.guard_i[go * 4 + 2];
+#pragma unroll
+        for (int a = 0; a < RPL; ++a) guard_row<W>(D, go, k, hs, prow, pcol, rng, lane + 32 * a, v[a]);
     }
 #pragma unroll
     for (int a = 0; a < RPL; ++a) {
         const int r = lane + 32 * a;
         if (r < D.R) {
 #pragma unroll
-            for (int w = 0; w < W; ++w) D.vis[(size_t)env * D.RW + r * D.W + w] = vis[a][w];
+            for (int w = 0; w < W; ++w) {
+                if (!only_last) buf[o * D.RW + r * D.W + w] = v[a][w];
+                if (t == lt) D.vis[(size_t)env * D.RW + r * D.W + w] = v[a][w];
+            }
         }
     }
+}
+
+// k_fill (no auto-reset only): ticks an env spent done copy its current map, final once k_finish has run.
+template <int W>
+__global__ void __launch_bounds__(256)
+k_fill(Dev D, int T, uint32_t *buf, const uint8_t *__restrict__ fin) {
+    const int lane = threadIdx.x & 31;   // grid: x = env / 8, y = tick; lane strides over the RW words
+    const int env = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (env >= D.N || !D.env_cached[env]) return;
+    const size_t te = (size_t)blockIdx.y * D.N + env;
+    if (fin[te]) return;
+    for (int i = lane; i < D.RW; i += 32) buf[te * D.RW + i] = D.vis[(size_t)env * D.RW + i];
 }
