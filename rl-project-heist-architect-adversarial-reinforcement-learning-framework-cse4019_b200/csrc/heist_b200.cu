@@ -51,7 +51,9 @@ struct HeistHandle {
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
     uint8_t *fin;       size_t fin_cap;       // k_seq -> k_finish: tick rebuilt its map [T][N]
-    int32_t *last_t;                          // [N] last rebuilt tick of the launch
+    int32_t *last_t;    size_t last_cap;      // [chunks][N] last rebuilt tick of each chunk
+    cudaStream_t s_seq, s_fin;                // side streams of the pipelined launch
+    cudaEvent_t ev_fork, ev_join, ev_cam[64], ev_seq[64];
     void *allocs[96];
     int n_allocs;
 };
@@ -86,6 +88,11 @@ extern "C" int heist_destroy(HeistHandle *h) {
     if (h->grec) cudaFree(h->grec);
     if (h->fin) cudaFree(h->fin);
     if (h->last_t) cudaFree(h->last_t);
+    if (h->s_seq) {
+        cudaStreamDestroy(h->s_seq); cudaStreamDestroy(h->s_fin);
+        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+        for (int i = 0; i < 64; ++i) { cudaEventDestroy(h->ev_cam[i]); cudaEventDestroy(h->ev_seq[i]); }
+    }
     delete h;
     return 0;
 }
@@ -185,6 +192,15 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         CUDA_TRY(cudaMalloc(&h->grec, h->grec_cap * sizeof(uint16_t)));
         CUDA_TRY(cudaMalloc(&h->fin, h->fin_cap));
         CUDA_TRY(cudaMalloc(&h->last_t, N * sizeof(int32_t)));
+        h->last_cap = N;
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_seq, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_fin, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        for (int i = 0; i < 64; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_cam[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_seq[i], cudaEventDisableTiming));
+        }
     }
     h->layout_smem = HEIST_WARPS_PER_CTA * layout_warp_bytes(d.RC, d.RW);
 #define SET_SMEM(E, B)                                                                                                    \
@@ -277,42 +293,125 @@ static cudaError_t grow(T **buf, size_t *cap, size_t need) {
     return e;
 }
 
+// One chunk of ticks [t0, t0 + Tc) through the table-driven kernels.  s_cam / s_seq / s_fin may be one stream
+// (sequential) or three (pipelined: the camera cones of the next chunk are built while k_seq walks this one).
+struct FastChunk {
+    const int8_t *actions; float *reward; double *reward64; uint8_t *done, *status;
+    uint32_t *cam; const double *heads; uint16_t *grec; uint8_t *fin; int32_t *last_t;
+    int Tc, autoreset, do_reset, only_last; const uint8_t *mask;
+};
+
+static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
+    const Dev &d = h->d;
+    const int nblk = (c.Tc + FAST_TB - 1) / FAST_TB;
+    const unsigned g1 = (unsigned)(((long long)h->N * nblk + FAST_WARPS - 1) / FAST_WARPS);
+    const uint8_t *m = c.do_reset ? c.mask : nullptr;
+#define GO(RPL, W) k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, c.Tc, nblk, c.heads, c.cam, m)
+    if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
+    else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
+#undef GO
+}
+
+static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
+    const Dev &d = h->d;
+    // envs per warp: about 1024 warps in flight (see k_seq)
+    const int lanes = SEQ_THREADS;   // sparse warps (fewer envs per warp) shorten the chain but cost issue slots: measured slower
+    const unsigned g2 = (unsigned)((h->N + lanes - 1) / lanes);
+#define GO(W) k_seq<W><<<g2, SEQ_THREADS, h->seq_smem, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
+                                                              c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask, lanes)
+    if (d.C > 32) GO(2); else GO(1);
+#undef GO
+}
+
+static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
+    const Dev &d = h->d;
+    const dim3 g3((unsigned)((h->N + 7) / 8), (unsigned)(c.only_last ? 1 : c.Tc)), g4((unsigned)((h->N + 7) / 8), (unsigned)c.Tc);
+    const uint8_t *m = c.do_reset ? c.mask : nullptr;
+#define GO(RPL, W)                                                                                       \
+    do {                                                                                                 \
+        k_finish<RPL, W><<<g3, 256, 0, s>>>(d, c.Tc, c.cam, c.grec, c.fin, c.last_t, c.only_last, m);   \
+        if (!c.only_last && !c.autoreset) k_fill<W><<<g4, 256, 0, s>>>(d, c.Tc, c.cam, c.fin);          \
+    } while (0)
+    if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
+    else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
+#undef GO
+}
+
+#define FAST_PIPE_TC 32        // ticks per pipelined chunk (a multiple of FAST_TB)
+#define FAST_PIPE_MAX 64       // chunks (events) per launch
+
+// Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_seq ->
+// k_finish (heist_fast.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
 static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
                        uint8_t *done, uint8_t *status, uint32_t *vis_traj, int do_reset, const uint8_t *mask,
                        cudaStream_t s) {
     const Dev &d = h->d;
     const size_t N = h->N, NRW = N * d.RW;
-    const bool r2 = d.R > 32, w2 = d.C > 32;
     const int total = do_reset ? 1 : T;
-    // ticks per chunk: bounded by 256 MiB of cam_vis scratch when there is no trajectory buffer to build it in
+    const unsigned gh = (unsigned)((N * d.Kc + 127) / 128);
+    FastChunk c;
+    c.autoreset = autoreset; c.do_reset = do_reset; c.only_last = vis_traj ? 0 : 1; c.mask = mask;
+
+    // Pipelined: with auto-reset no env is ever left done at a chunk boundary, so the camera headings of the whole
+    // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_seq of chunk c.
+    const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
+    const bool pipelined = !do_reset && autoreset && total > FAST_PIPE_TC && n_chunks <= FAST_PIPE_MAX && h->s_seq &&
+                           (vis_traj || (size_t)total * NRW * 4 <= ((size_t)1 << 30));
+    if (pipelined) {
+        const int nblk = (total + FAST_TB - 1) / FAST_TB;
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
+        CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)total * N * d.Kg));
+        CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)total * N));
+        CUDA_TRY(grow(&h->last_t, &h->last_cap, (size_t)n_chunks * N));
+        if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)total * NRW));
+        uint32_t *cam = vis_traj ? vis_traj : h->scratch;
+        k_heads<<<gh, 128, 0, s>>>(d, total, 0, 1, h->heads);
+        CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_fork, 0));
+        for (int i = 0; i < n_chunks; ++i) {
+            const int t0 = i * FAST_PIPE_TC;
+            const size_t off = (size_t)t0 * N;
+            c.Tc = std::min(FAST_PIPE_TC, total - t0);
+            c.actions = actions + off; c.reward = reward ? reward + off : nullptr; c.reward64 = reward64 ? reward64 + off : nullptr;
+            c.done = done ? done + off : nullptr; c.status = status ? status + off : nullptr;
+            c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc;
+            c.grec = h->grec + off * d.Kg; c.fin = h->fin + off; c.last_t = h->last_t + (size_t)i * N;
+            launch_cam_vis(h, c, s);
+            CUDA_TRY(cudaEventRecord(h->ev_cam[i], s));
+            CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_cam[i], 0));
+            launch_seq(h, c, h->s_seq);
+            CUDA_TRY(cudaEventRecord(h->ev_seq[i], h->s_seq));
+            CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_seq[i], 0));
+            launch_finish(h, c, h->s_fin);
+        }
+        CUDA_TRY(cudaEventRecord(h->ev_join, h->s_fin));   // s_fin's last kernel waited for s_seq's last
+        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+        CUDA_TRY(cudaGetLastError());
+        return 0;
+    }
+
+    // Sequential chunks on the caller's stream; ticks per chunk bounded by 256 MiB of cam_vis scratch when there is
+    // no trajectory buffer to build the maps in.
     int cap = 256;
     if (!vis_traj) cap = (int)std::max<size_t>(1, std::min<size_t>(256, ((size_t)256 << 20) / (NRW * 4)));
     for (int t0 = 0; t0 < total; t0 += cap) {
-        const int Tc = std::min(cap, total - t0), nblk = (Tc + FAST_TB - 1) / FAST_TB;
-        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
-        if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)Tc * NRW));
-        uint32_t *cam = vis_traj ? vis_traj + (size_t)t0 * NRW : h->scratch;
         const size_t off = (size_t)t0 * N;
-        CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)Tc * N * d.Kg));
-        CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)Tc * N));
-        k_heads<<<(unsigned)((N * d.Kc + 127) / 128), 128, 0, s>>>(d, Tc, do_reset, h->heads);
-        const long long warps = (long long)N * nblk;
-        const unsigned g1 = (unsigned)((warps + FAST_WARPS - 1) / FAST_WARPS), g2 = (unsigned)((N + SEQ_THREADS - 1) / SEQ_THREADS);
-        const int only_last = vis_traj ? 0 : 1;
-        const dim3 g3((unsigned)((N + 7) / 8), (unsigned)(only_last ? 1 : Tc)), g4((unsigned)((N + 7) / 8), (unsigned)Tc);
-#define GO(RPL, W)                                                                                                       \
-    do {                                                                                                                 \
-        k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, Tc, nblk, h->heads, cam, do_reset ? mask : nullptr); \
-        k_seq<W><<<g2, SEQ_THREADS, h->seq_smem, s>>>(                                                                   \
-            d, actions ? actions + off : nullptr, do_reset ? 0 : Tc, autoreset, reward ? reward + off : nullptr,         \
-            reward64 ? reward64 + off : nullptr, done ? done + off : nullptr, status ? status + off : nullptr, cam,      \
-            h->grec, h->fin, h->last_t, do_reset, mask);                                                                 \
-        k_finish<RPL, W><<<g3, 256, 0, s>>>(d, Tc, cam, h->grec, h->fin, h->last_t, only_last, do_reset ? mask : nullptr); \
-        if (!only_last && !autoreset) k_fill<W><<<g4, 256, 0, s>>>(d, Tc, cam, h->fin);                                  \
-    } while (0)
-        if (r2) { if (w2) GO(2, 2); else GO(2, 1); }
-        else { if (w2) GO(1, 2); else GO(1, 1); }
-#undef GO
+        c.Tc = std::min(cap, total - t0);
+        const int nblk = (c.Tc + FAST_TB - 1) / FAST_TB;
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
+        CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)c.Tc * N * d.Kg));
+        CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)c.Tc * N));
+        if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)c.Tc * NRW));
+        c.actions = actions ? actions + off : nullptr; c.reward = reward ? reward + off : nullptr;
+        c.reward64 = reward64 ? reward64 + off : nullptr; c.done = done ? done + off : nullptr;
+        c.status = status ? status + off : nullptr;
+        c.cam = vis_traj ? vis_traj + (size_t)t0 * NRW : h->scratch; c.heads = h->heads;
+        c.grec = h->grec; c.fin = h->fin; c.last_t = h->last_t;
+        k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, (autoreset && !do_reset) ? 1 : 0, h->heads);
+        launch_cam_vis(h, c, s);
+        launch_seq(h, c, s);
+        launch_finish(h, c, s);
         CUDA_TRY(cudaGetLastError());
     }
     return 0;

@@ -65,8 +65,10 @@ __device__ __forceinline__ int fast_adv0(const Dev &D, int env, int do_reset) {
     return (D.env_d[(size_t)env * 8 + 4] & F_DONE) ? 0 : 1;
 }
 
-// heads[b][env][k] = heading of camera k at tick b * FAST_TB of this launch
-__global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, double *__restrict__ heads) {
+// heads[b][env][k] = heading of camera k at tick b * FAST_TB of this launch.  write_final: with auto-reset every
+// tick of the launch updates the cameras (environment.py:251-252), so the heading the launch ends on is the one
+// of its last tick and is stored here; otherwise k_seq stores it (an env may stop stepping early).
+__global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int write_final, double *__restrict__ heads) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D.N * D.Kc) return;
     const int env = i / D.Kc, k = i - env * D.Kc;
@@ -75,10 +77,13 @@ __global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, doubl
     const double speed = D.cam_f[(size_t)i * 2 + 1];
     const int adv0 = fast_adv0(D, env, do_reset);
     for (int a = 0; a < adv0; ++a) h = py_mod360(__dadd_rn(h, speed));
+    double last = h;
     for (int t = 0; t < T; ++t) {
         if (t % FAST_TB == 0) heads[(size_t)(t / FAST_TB) * D.N * D.Kc + i] = h;
+        last = h;
         h = py_mod360(__dadd_rn(h, speed));
     }
+    if (write_final && T > 0) D.cam_heading[i] = last;
 }
 
 // rays below boundary point p: clamp(ceil((p - base) / step), 0, NR)
@@ -271,11 +276,14 @@ __global__ void __launch_bounds__(SEQ_THREADS)
 k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
       double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
       const uint32_t *__restrict__ cam_vis, uint16_t *__restrict__ grec, uint8_t *__restrict__ fin,
-      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask) {
+      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask, int lanes) {
+    // `lanes` envs per warp (CTA = one warp).  The threads of a warp take different branches (episode ends, guard
+    // counts, prefetch misses) and a warp executes the union of them; with few envs in flight the launch is bound
+    // by that serial chain, not by throughput, so small batches run with sparse warps.
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
-    const int env = blockIdx.x * SEQ_THREADS + tid;
-    if (env >= D.N || !D.env_cached[env]) return;
+    const int env = blockIdx.x * lanes + tid;
+    if (tid >= lanes || env >= D.N || !D.env_cached[env]) return;
     if (do_reset && mask && !mask[env]) { last_t[env] = -1; return; }
     uint32_t *wall = reinterpret_cast<uint32_t *>(smem);   // plane [word][thread]
     SeqGuards G;
@@ -466,8 +474,8 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
     *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =
         make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
-    for (int k = 0; k < n_cams; ++k) {   // headings after the camera updates this launch executed
-        const size_t co = (size_t)env * D.Kc + k;
+    for (int k = 0; k < (autoreset ? 0 : n_cams); ++k) {   // headings after the camera updates this launch executed
+        const size_t co = (size_t)env * D.Kc + k;          // (with auto-reset: stored by k_heads)
         double h = D.cam_heading[co];
         const double speed = D.cam_f[co * 2 + 1];
         for (int a = 0; a < n_adv; ++a) h = py_mod360(__dadd_rn(h, speed));
@@ -496,20 +504,30 @@ k_finish(Dev D, int T, uint32_t *buf, const uint16_t *__restrict__ grec, const u
     const int t = only_last ? lt : (int)blockIdx.y;
     if (t < 0) return;
     const size_t o = (size_t)t * D.N + env;
-    if (!fin[o]) return;
+    // independent loads first: the tick's flag, the cam_vis rows, and -- lane g -- guard g's recorded state
+    const int n_guards = D.env_s[(size_t)env * 4 + 1];
+    const unsigned f = fin[o];
+    unsigned rec = 0;
+    if (lane < n_guards) rec = grec[o * D.Kg + lane];
     uint32_t v[RPL][W];
 #pragma unroll
     for (int a = 0; a < RPL; ++a)
 #pragma unroll
         for (int w = 0; w < W; ++w) { const int r = lane + 32 * a; v[a][w] = r < D.R ? buf[o * D.RW + r * D.W + w] : 0u; }
-    const int n_guards = D.env_s[(size_t)env * 4 + 1];
+    if (!f) return;
+    // lane g: where guard g stands and how far it sees; then every lane ORs its row(s) of every guard's mask
+    int gp = 0;
+    if (lane < n_guards) {
+        const size_t go = (size_t)env * D.Kg + lane;
+        const int k = rec & 255;
+        gp = D.guard_path[(go * D.L + k) * 2] | (D.guard_path[(go * D.L + k) * 2 + 1] << 8) | (D.guard_i[go * 4 + 2] << 16);
+    }
     for (int g = 0; g < n_guards; ++g) {
-        const size_t go = (size_t)env * D.Kg + g;
-        const unsigned rec = grec[o * D.Kg + g];
-        const int k = rec & 255, hs = rec >> 8;
-        const int prow = D.guard_path[(go * D.L + k) * 2], pcol = D.guard_path[(go * D.L + k) * 2 + 1], rng = D.guard_i[go * 4 + 2];
+        const unsigned rg = __shfl_sync(0xffffffffu, rec, g);
+        const int pg = __shfl_sync(0xffffffffu, gp, g);
 #pragma unroll
-        for (int a = 0; a < RPL; ++a) guard_row<W>(D, go, k, hs, prow, pcol, rng, lane + 32 * a, v[a]);
+        for (int a = 0; a < RPL; ++a)
+            guard_row<W>(D, (size_t)env * D.Kg + g, rg & 255, rg >> 8, pg & 255, (pg >> 8) & 255, pg >> 16, lane + 32 * a, v[a]);
     }
 #pragma unroll
     for (int a = 0; a < RPL; ++a) {
