@@ -151,7 +151,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         const size_t HS = (size_t)d.L + 1;
         const size_t need = N * d.Kc * ((size_t)VC_POINTS * 8 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
                             N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
-        const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.Kg, d.L) <= (size_t)160 * 1024 &&
+        const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
                               FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024;
         if (!(off && off[0] == '1') && need < free_b / 2 && seq_fits) {
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
@@ -176,7 +176,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);
-    h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.Kg, d.L);
+    h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.L);
 #define SET_FAST(RPL, W) \
     CUDA_TRY(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem));
     SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
@@ -315,10 +315,9 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
 static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
     // envs per warp: about 1024 warps in flight (see k_seq)
-    const int lanes = SEQ_THREADS;   // sparse warps (fewer envs per warp) shorten the chain but cost issue slots: measured slower
-    const unsigned g2 = (unsigned)((h->N + lanes - 1) / lanes);
+    const unsigned g2 = (unsigned)((h->N + SEQ_THREADS - 1) / SEQ_THREADS);
 #define GO(W) k_seq<W><<<g2, SEQ_THREADS, h->seq_smem, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
-                                                              c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask, lanes)
+                                                              c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask)
     if (d.C > 32) GO(2); else GO(1);
 #undef GO
 }

@@ -26,6 +26,7 @@
 
 #define VC_ROWS 16            // mask rows per window (u16 each): 2 * range + 1 <= 15
 #define VC_MAX_RANGE 7
+#define VC_MAX_GUARDS 4       // guards per env the table-driven kernels keep in registers
 #define VC_POINTS 1024        // boundary points kept per camera (2 per merged band)
 #define VC_RAW 1024           // raw bands sorted per camera (power of two)
 #define VC_IDX 560            // 1-degree buckets of the coarse index (domain <= 540 degrees + slack)
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
     const int n_cams = D.env_s[(size_t)env * 4 + 0], n_guards = D.env_s[(size_t)env * 4 + 1];
     const uint32_t *wall = D.wall + (size_t)env * D.RW;
     const VcGeo geo = vc_geo(D);
-    bool env_ok = true;
+    bool env_ok = n_guards <= VC_MAX_GUARDS;
 
     for (int k = 0; k < n_cams; ++k) {
         const size_t o = (size_t)env * D.Kc + k;

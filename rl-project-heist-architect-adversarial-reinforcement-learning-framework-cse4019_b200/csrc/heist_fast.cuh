@@ -238,27 +238,19 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
 // k_seq: the sequential part of a launch, one THREAD per env (everything here is scalar per env: position,
 // rewards, guard indices; a warp per env would execute it 32 times over).  Per tick: move, guards advance,
 // detection from ONE word of cam_vis[t] OR the guards' cached masks at the Solver's row, vault / timeout,
-// rewards, auto-reset.  The Solver's path does not depend on what it sees (until an episode ends), so the
-// cam_vis word of tick t + 1 is prefetched at the predicted row while tick t is being decided.
-// What k_finish needs to complete the maps -- the guards' (waypoint, heading slot) of every tick -- is recorded.
-// Walls and per-guard patrol data are staged in shared memory as planes [item][thread] (no bank conflicts).
+// rewards, auto-reset.  What k_finish needs to complete the maps -- the guards' (waypoint, heading slot) of every
+// tick -- is recorded.
+//
+// Few warps run this kernel (N / 32), each alone on its SM: its speed is the length of the per-tick dependency
+// chain, not throughput.  So nothing on that chain touches memory: the three wall rows around the Solver, each
+// guard's state, its current and next patrol word live in registers, and everything tick t + 1 will read from
+// global memory -- the cam_vis word(s) and the guards' mask rows at the Solver's next row -- is requested while
+// tick t is being decided (until an episode ends, the Solver's path and the patrols do not depend on what is
+// seen, so the next state is known); actions are requested two ticks ahead.  Every thread runs exactly T
+// iterations (an auto-reset is part of the tick that ended the episode), so the threads of a warp stay in step.
 // ---------------------------------------------------------------------------------------------
 #define SEQ_THREADS 32
-#define SEQ_PG 4         // guards whose mask row is prefetched one tick ahead
-__host__ __device__ inline size_t seq_thread_bytes(int RW, int Kg, int L) { return (size_t)RW * 4 + (size_t)Kg * (5 + 3 * (size_t)L); }
-
-struct SeqGuards {   // byte planes in shared memory, one column per thread
-    uint8_t *base;
-    int Kg, L, tid;
-    __device__ __forceinline__ uint8_t &len(int g)   { return base[(size_t)(g * 5 + 0) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &stp(int g)   { return base[(size_t)(g * 5 + 1) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &range(int g) { return base[(size_t)(g * 5 + 2) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &idx(int g)   { return base[(size_t)(g * 5 + 3) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &hs(int g)    { return base[(size_t)(g * 5 + 4) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &pr(int g, int k)    { return base[(size_t)(Kg * 5 + (g * L + k) * 3 + 0) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &pc(int g, int k)    { return base[(size_t)(Kg * 5 + (g * L + k) * 3 + 1) * SEQ_THREADS + tid]; }
-    __device__ __forceinline__ uint8_t &hslot(int g, int k) { return base[(size_t)(Kg * 5 + (g * L + k) * 3 + 2) * SEQ_THREADS + tid]; }
-};
+__host__ __device__ inline size_t seq_thread_bytes(int RW, int L) { return (size_t)RW * 4 + (size_t)VC_MAX_GUARDS * L * 4; }
 
 // guard cone + own tile of guard (o = env * Kg + g) at waypoint k with heading slot hs, grid row r
 // (visibility.py:44-59) -> OR into the W words of that row
@@ -276,18 +268,18 @@ __global__ void __launch_bounds__(SEQ_THREADS)
 k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
       double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
       const uint32_t *__restrict__ cam_vis, uint16_t *__restrict__ grec, uint8_t *__restrict__ fin,
-      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask, int lanes) {
-    // `lanes` envs per warp (CTA = one warp).  The threads of a warp take different branches (episode ends, guard
-    // counts, prefetch misses) and a warp executes the union of them; with few envs in flight the launch is bound
-    // by that serial chain, not by throughput, so small batches run with sparse warps.
+      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
-    const int env = blockIdx.x * lanes + tid;
-    if (tid >= lanes || env >= D.N || !D.env_cached[env]) return;
+    const int env = blockIdx.x * SEQ_THREADS + tid;
+    if (env >= D.N || !D.env_cached[env]) return;
     if (do_reset && mask && !mask[env]) { last_t[env] = -1; return; }
-    uint32_t *wall = reinterpret_cast<uint32_t *>(smem);   // plane [word][thread]
-    SeqGuards G;
-    G.base = smem + (size_t)D.RW * 4 * SEQ_THREADS; G.Kg = D.Kg; G.L = D.L; G.tid = tid;
+    constexpr int G = VC_MAX_GUARDS;
+    const int R = D.R, C = D.C, N = D.N, RW = D.RW, L = D.L, Kg = D.Kg;
+    // shared-memory planes [word][thread]: wall rows, then per guard the patrol words  row | col << 8 | slot << 16
+    // (slot: heading slot taken when LEAVING the waypoint, 255 = unchanged)
+    uint32_t *wall_s = reinterpret_cast<uint32_t *>(smem) + tid;
+    uint32_t *pw_s = wall_s + RW * SEQ_THREADS;
 
     // ---- load ----
     const int4 es = *reinterpret_cast<const int4 *>(D.env_s + (size_t)env * 4);
@@ -297,26 +289,52 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     EnvRegs E;
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    for (int i = 0; i < D.RW; ++i) wall[i * SEQ_THREADS + tid] = D.wall[(size_t)env * D.RW + i];
-    for (int g = 0; g < n_guards; ++g) {
-        const size_t o = (size_t)env * D.Kg + g;
-        const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);   // len, speed, range, num_rays
-        G.len(g) = (uint8_t)gi.x; G.stp(g) = (uint8_t)py_imod(gi.y, gi.x); G.range(g) = (uint8_t)gi.z;
-        G.idx(g) = (uint8_t)D.guard_idx[o];
-        for (int k = 0; k < gi.x; ++k) {
-            G.pr(g, k) = D.guard_path[(o * D.L + k) * 2]; G.pc(g, k) = D.guard_path[(o * D.L + k) * 2 + 1];
-            G.hslot(g, k) = D.vg_hslot[o * D.L + k];
+    for (int i = 0; i < RW; ++i) wall_s[i * SEQ_THREADS] = D.wall[(size_t)env * RW + i];
+    int gk[G], ghs[G], glen[G], gstp[G], grng[G], gkn[G];   // waypoint, heading slot, path length, stride, range, next waypoint
+    unsigned gw[G], gwn[G], gw0[G];                         // patrol word at gk, at gkn, at waypoint 0
+    const uint16_t *gmask[G];                               // the guard's mask table
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        gk[g] = ghs[g] = gkn[g] = 0; glen[g] = 1; gstp[g] = 0; grng[g] = 0; gw[g] = gwn[g] = gw0[g] = 0; gmask[g] = D.vg_mask;
+        if (g < n_guards) {
+            const size_t o = (size_t)env * Kg + g;
+            const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);   // len, speed, range, num_rays
+            glen[g] = gi.x; gstp[g] = gi.x >= 2 ? py_imod(gi.y, gi.x) : 0; grng[g] = gi.z;
+            gk[g] = D.guard_idx[o];
+            for (int k = 0; k < gi.x; ++k)
+                pw_s[(g * L + k) * SEQ_THREADS] = (unsigned)D.guard_path[(o * L + k) * 2] | ((unsigned)D.guard_path[(o * L + k) * 2 + 1] << 8) |
+                                                  ((unsigned)D.vg_hslot[o * L + k] << 16);
+            // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
+            // state view; it is reported (ERR_STATE) and treated as the default heading.
+            const double h = D.guard_heading[o];
+            int hs = -1;
+            const int nh = D.vg_nh[o];
+            for (int s = 0; s < nh; ++s)
+                if (__double_as_longlong(D.vg_hval[o * (L + 1) + s]) == __double_as_longlong(h)) { hs = s; break; }
+            if (hs < 0) { atomicOr(D.err, ERR_STATE); hs = 0; }
+            ghs[g] = hs;
+            gmask[g] = D.vg_mask + o * L * (size_t)(L + 1) * VC_ROWS;
+            gkn[g] = gk[g] + gstp[g]; if (gkn[g] >= glen[g]) gkn[g] -= glen[g];
+            gw[g] = pw_s[(g * L + gk[g]) * SEQ_THREADS]; gwn[g] = pw_s[(g * L + gkn[g]) * SEQ_THREADS]; gw0[g] = pw_s[(g * L) * SEQ_THREADS];
         }
-        // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
-        // state view; it is reported (ERR_STATE) and treated as the default heading.
-        const double h = D.guard_heading[o];
-        int hs = -1;
-        const int nh = D.vg_nh[o];
-        for (int s = 0; s < nh; ++s)
-            if (__double_as_longlong(D.vg_hval[o * (D.L + 1) + s]) == __double_as_longlong(h)) { hs = s; break; }
-        if (hs < 0) { atomicOr(D.err, ERR_STATE); hs = 0; }
-        G.hs(g) = (uint8_t)hs;
     }
+    // wall rows E.r - 1, E.r, E.r + 1 (rows outside the grid block)
+    uint32_t ww[3][W];
+#define SEQ_WALL_ROW(dst, row)                                                                                 \
+    do {                                                                                                       \
+        const int r_ = (row);                                                                                  \
+        _Pragma("unroll") for (int w = 0; w < W; ++w)                                                          \
+            (dst)[w] = (r_ >= 0 && r_ < R) ? wall_s[(r_ * W + w) * SEQ_THREADS] : 0xffffffffu;                 \
+    } while (0)
+#define SEQ_WALL_AROUND() do { SEQ_WALL_ROW(ww[0], E.r - 1); SEQ_WALL_ROW(ww[1], E.r); SEQ_WALL_ROW(ww[2], E.r + 1); } while (0)
+    // would the move (dr, dc) from (E.r, E.c) be accepted (:239-246)?  Uses the register rows only.
+    auto wall_word = [&](int dr, int nc) -> uint32_t {   // selects, not indexing: the rows stay in registers
+        uint32_t lo = dr < 0 ? ww[0][0] : (dr > 0 ? ww[2][0] : ww[1][0]);
+        if (W == 2) { const uint32_t hi = dr < 0 ? ww[0][W - 1] : (dr > 0 ? ww[2][W - 1] : ww[1][W - 1]); if (nc >> 5) lo = hi; }
+        return lo;
+    };
+#define SEQ_FREE(dr, nc) ((nc) >= 0 && (nc) < C && !((wall_word((dr), (nc)) >> ((nc) & 31)) & 1u))
+    SEQ_WALL_AROUND();
 
     int status = HEIST_RUNNING;
     int n_adv = 0;           // camera updates executed by this launch
@@ -327,51 +345,59 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     do {                                                                                     \
         E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0;                           \
         E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c); E.init = E.prev;               \
-        for (int g = 0; g < n_guards; ++g) G.idx(g) = 0;                                     \
+        SEQ_WALL_AROUND();                                                                   \
+        _Pragma("unroll") for (int g = 0; g < G; ++g) {                                      \
+            gk[g] = 0; gw[g] = gw0[g]; gkn[g] = gstp[g];                                     \
+            gwn[g] = pw_s[(g * L + gkn[g]) * SEQ_THREADS];                                   \
+        }                                                                                    \
     } while (0)
 #define SEQ_RECORD(o_)                                                                                         \
     do {                                                                                                       \
-        for (int g = 0; g < n_guards; ++g) grec[(o_) * D.Kg + g] = (uint16_t)(G.idx(g) | (G.hs(g) << 8));    \
+        _Pragma("unroll") for (int g = 0; g < G; ++g)                                                          \
+            if (g < n_guards) grec[(o_) * Kg + g] = (uint16_t)(gk[g] | (ghs[g] << 8));                         \
     } while (0)
     if (do_reset) {
         SEQ_RESET_STATE();
         fin[env] = 1; SEQ_RECORD((size_t)env); last = 0;
         T = 0;
     }
-    // Speculation: until an episode ends, the Solver's path and the guards' patrol do not depend on what is seen.
-    // At the end of tick t the state tick t + 1 will be decided in is therefore known (unless t ends the episode),
-    // and the words that decide it -- the cam_vis word(s) and the guards' mask rows at the Solver's next row -- are
-    // requested one tick ahead; actions are requested two ticks ahead.  Every thread runs exactly T iterations
-    // (an auto-reset is part of the tick that ended the episode), so the threads of a warp stay in step.
     int a_cur = 0, a_nxt = 0;
-    if (T > 0) { a_cur = actions[env]; a_nxt = T > 1 ? actions[(size_t)D.N + env] : 0; }
+    if (T > 0) { a_cur = actions[env]; a_nxt = T > 1 ? actions[(size_t)N + env] : 0; }
     int pre_row = -1;
     uint32_t pre[W];
-    unsigned pre_g[SEQ_PG], pre_key[SEQ_PG];   // mask row / (waypoint | slot << 8) it was fetched for
+    unsigned pre_g[G], pre_key[G];   // mask row / (waypoint | slot << 8) it was fetched for
 #pragma unroll
     for (int w = 0; w < W; ++w) pre[w] = 0;
 #pragma unroll
-    for (int g = 0; g < SEQ_PG; ++g) { pre_g[g] = 0; pre_key[g] = 0xffffffffu; }
+    for (int g = 0; g < G; ++g) { pre_g[g] = 0; pre_key[g] = 0xffffffffu; }
     for (int t = 0; t < T; ++t) {
-        const size_t o = (size_t)t * D.N + env;
+        const size_t o = (size_t)t * N + env;
         bool rebuilt = false;
         double rw = 0.0;
         status = HEIST_ALREADY_DONE;
         if (!(E.flags & F_DONE)) {   // a done env is not mutated (:232-233)
             // move (:239-246): blocked by the grid edge or a WALL tile
-            const int nr = E.r + (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
-            if (nr >= 0 && nr < D.R && nc >= 0 && nc < D.C &&
-                !((wall[(nr * D.W + (nc >> 5)) * SEQ_THREADS + tid] >> (nc & 31)) & 1u)) { E.r = nr; E.c = nc; }
+            const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
+            if (SEQ_FREE(dr, nc)) {
+                E.c = nc;
+                if (dr) {   // rows shift by one; the new outer row is only needed from the next tick on
+                    E.r += dr;
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        if (dr > 0) { ww[0][w] = ww[1][w]; ww[1][w] = ww[2][w]; } else { ww[2][w] = ww[1][w]; ww[1][w] = ww[0][w]; }
+                    }
+                    if (dr > 0) SEQ_WALL_ROW(ww[2], E.r + 1); else SEQ_WALL_ROW(ww[0], E.r - 1);
+                }
+            }
             ++n_adv;   // cameras rotate (:251-252): their cones for this tick are cam_vis[t]
-            for (int g = 0; g < n_guards; ++g) {   // Guard.update (security.py:145-159)
-                const int len = G.len(g);
-                if (len >= 2) {
-                    const int old = G.idx(g);
-                    const int hsl = G.hslot(g, old);
-                    if (hsl != 255) G.hs(g) = (uint8_t)hsl;   // 255: the move is (0, 0), heading unchanged
-                    int ni = old + G.stp(g);
-                    if (ni >= len) ni -= len;
-                    G.idx(g) = (uint8_t)ni;
+#pragma unroll
+            for (int g = 0; g < G; ++g) {   // Guard.update (security.py:145-159)
+                if (g < n_guards && glen[g] >= 2) {
+                    const int hsl = (gw[g] >> 16) & 255;
+                    if (hsl != 255) ghs[g] = hsl;   // 255: the move is (0, 0), heading unchanged
+                    gk[g] = gkn[g]; gw[g] = gwn[g];
+                    gkn[g] = gk[g] + gstp[g]; if (gkn[g] >= glen[g]) gkn[g] -= glen[g];
+                    gwn[g] = pw_s[(g * L + gkn[g]) * SEQ_THREADS];
                 }
             }
             // visibility at the Solver's tile: camera cones OR guard cones / own tiles
@@ -382,19 +408,18 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
                 for (int w = 0; w < W; ++w) v[w] = pre[w];
             } else {
 #pragma unroll
-                for (int w = 0; w < W; ++w) v[w] = cam_vis[o * D.RW + E.r * D.W + w];
+                for (int w = 0; w < W; ++w) v[w] = cam_vis[o * RW + E.r * W + w];
             }
 #pragma unroll
-            for (int g = 0; g < SEQ_PG; ++g) {
+            for (int g = 0; g < G; ++g) {
                 if (g < n_guards) {
-                    const int k = G.idx(g), hs = G.hs(g), rng = G.range(g);
-                    if (hit && pre_key[g] == (unsigned)(k | (hs << 8))) fast_or_row<W>(v, pre_g[g], (int)G.pc(g, k) - rng);
-                    else guard_row<W>(D, (size_t)env * D.Kg + g, k, hs, G.pr(g, k), G.pc(g, k), rng, E.r, v);
+                    const int prow = gw[g] & 255, pcol = (gw[g] >> 8) & 255, wr = E.r - (prow - grng[g]);
+                    if (wr >= 0 && wr <= 2 * grng[g]) {
+                        const unsigned bits = (hit && pre_key[g] == (unsigned)(gk[g] | (ghs[g] << 8)))
+                                                  ? pre_g[g] : gmask[g][(gk[g] * (L + 1) + ghs[g]) * VC_ROWS + wr];
+                        fast_or_row<W>(v, bits, pcol - grng[g]);
+                    }
                 }
-            }
-            for (int g = SEQ_PG; g < n_guards; ++g) {
-                const int k = G.idx(g);
-                guard_row<W>(D, (size_t)env * D.Kg + g, k, G.hs(g), G.pr(g, k), G.pc(g, k), G.range(g), E.r, v);
             }
             const bool detected = (v[(W == 2) ? (E.c >> 5) : 0] >> (E.c & 31)) & 1u;
             // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297)
@@ -437,37 +462,36 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         if (rebuilt) { last = t; SEQ_RECORD(o); }
         // requests for tick t + 1
         a_cur = a_nxt;
-        if (t + 2 < T) a_nxt = actions[o + 2 * (size_t)D.N];
+        if (t + 2 < T) a_nxt = actions[o + 2 * (size_t)N];
         pre_row = -1;
         if (t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state
-            const int nr = E.r + (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
-            pre_row = E.r;
-            if (nr >= 0 && nr < D.R && nc >= 0 && nc < D.C &&
-                !((wall[(nr * D.W + (nc >> 5)) * SEQ_THREADS + tid] >> (nc & 31)) & 1u)) pre_row = nr;
+            const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
+            pre_row = SEQ_FREE(dr, nc) ? E.r + dr : E.r;
 #pragma unroll
-            for (int w = 0; w < W; ++w) pre[w] = cam_vis[(o + D.N) * D.RW + pre_row * D.W + w];
+            for (int w = 0; w < W; ++w) pre[w] = cam_vis[(o + N) * RW + pre_row * W + w];
 #pragma unroll
-            for (int g = 0; g < SEQ_PG; ++g) {
+            for (int g = 0; g < G; ++g) {
                 if (g < n_guards) {
-                    int k = G.idx(g), hs = G.hs(g);
-                    const int len = G.len(g), rng = G.range(g);
-                    if (len >= 2) {
-                        const int hsl = G.hslot(g, k);
+                    int k = gk[g], hs = ghs[g];
+                    unsigned word = gw[g];
+                    if (glen[g] >= 2) {
+                        const int hsl = (word >> 16) & 255;
                         if (hsl != 255) hs = hsl;
-                        k += G.stp(g);
-                        if (k >= len) k -= len;
+                        k = gkn[g]; word = gwn[g];
                     }
                     pre_key[g] = (unsigned)(k | (hs << 8));
-                    const int wr = pre_row - ((int)G.pr(g, k) - rng);
+                    const int wr = pre_row - ((int)(word & 255) - grng[g]);
                     pre_g[g] = 0;
-                    if (wr >= 0 && wr <= 2 * rng)
-                        pre_g[g] = D.vg_mask[((((size_t)env * D.Kg + g) * D.L + k) * (size_t)(D.L + 1) + hs) * VC_ROWS + wr];
+                    if (wr >= 0 && wr <= 2 * grng[g]) pre_g[g] = gmask[g][(k * (L + 1) + hs) * VC_ROWS + wr];
                 }
             }
         }
     }
 #undef SEQ_RESET_STATE
 #undef SEQ_RECORD
+#undef SEQ_WALL_ROW
+#undef SEQ_WALL_AROUND
+#undef SEQ_FREE
 
     // ---- store ----
     last_t[env] = last;
@@ -481,10 +505,13 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         for (int a = 0; a < n_adv; ++a) h = py_mod360(__dadd_rn(h, speed));
         D.cam_heading[co] = h;
     }
-    for (int g = 0; g < n_guards; ++g) {
-        const size_t go = (size_t)env * D.Kg + g;
-        D.guard_heading[go] = D.vg_hval[go * (D.L + 1) + G.hs(g)];
-        D.guard_idx[go] = G.idx(g);
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (g < n_guards) {
+            const size_t go = (size_t)env * Kg + g;
+            D.guard_heading[go] = D.vg_hval[go * (L + 1) + ghs[g]];
+            D.guard_idx[go] = gk[g];
+        }
     }
 }
 
