@@ -208,6 +208,13 @@ int heist_architect_reward(HeistHandle *h, double *reward_out, double *solve_rat
 #define HEIST_MODE_MARCH 2
 int heist_set_mode(HeistHandle *h, int mode);
 
+/*
+ * Coverage of the angular visibility cache after the last set_layout: how many envs every asset of which is
+ * served from the cache (the rest are ray-marched), and the cache's device memory in bytes (0: disabled).
+ * Synchronises `stream`.  Any of the outputs may be NULL.
+ */
+int heist_cache_stats(HeistHandle *h, int32_t *envs_cached, int64_t *cache_bytes, void *stream);
+
 /* Synchronises `stream` and reports sticky device-side errors (capacity overflow, bad waypoint). */
 int heist_check_errors(HeistHandle *h, void *stream);
 

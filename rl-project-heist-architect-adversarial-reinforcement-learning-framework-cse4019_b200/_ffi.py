@@ -48,6 +48,7 @@ EXPORTS = {
     "heist_architect_reward": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "heist_check_errors": (C.c_int, [c_vp, c_vp]),
     "heist_set_mode": (C.c_int, [c_vp, C.c_int]),
+    "heist_cache_stats": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
 }
 
 

@@ -146,6 +146,13 @@ class BatchedHeistEnv:
         cover, 1 = all-fp64 ray-march, 2 = filtered ray-march everywhere.  All modes are bit-identical."""
         _ffi.check(self._lib.heist_set_mode(self._h, int(mode)), "heist_set_mode")
 
+    def cache_stats(self):
+        """(envs served by the angular visibility cache after the last set_layout, cache bytes on the device)."""
+        import ctypes
+        n, b = ctypes.c_int32(0), ctypes.c_int64(0)
+        _ffi.check(self._lib.heist_cache_stats(self._h, ctypes.byref(n), ctypes.byref(b), self._stream()), "heist_cache_stats")
+        return int(n.value), int(b.value)
+
     def set_exact_only(self, flag):
         """Force the all-fp64 ray-march (True) or go back to the default mode (False)."""
         self.set_mode(self.MODE_EXACT if flag else self.MODE_DEFAULT)

@@ -46,7 +46,7 @@ struct HeistHandle {
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
     int mode;        // heist_set_mode: HEIST_MODE_*
-    size_t camvis_smem, seq_smem;
+    size_t camvis_smem, seq_smem, cache_bytes;
     double *heads;      size_t heads_cap;     // k_heads output, grow-only [blocks][N][Kc]
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
@@ -154,6 +154,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
                               FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024;
         if (!(off && off[0] == '1') && need < free_b / 2 && seq_fits) {
+            h->cache_bytes = need;
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
             A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc);
             A(d.vg_mask, N * d.Kg * d.L * HS * VC_ROWS); A(d.vg_hval, N * d.Kg * HS);
@@ -447,6 +448,19 @@ static int launch_step(HeistHandle *h, const int8_t *actions, int T, int autores
     else { if (big) GO(false, true); else GO(false, false); }
 #undef GO
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_cache_stats(HeistHandle *h, int32_t *envs_cached, int64_t *cache_bytes, void *stream) {
+    if (!h) return fail(-1, "heist_cache_stats: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (envs_cached) {
+        int n_unc = 0;
+        CUDA_TRY(cudaMemcpy(&n_unc, h->d.n_uncached, sizeof(int), cudaMemcpyDeviceToHost));
+        *envs_cached = h->N - n_unc;
+    }
+    if (cache_bytes) *cache_bytes = (int64_t)h->cache_bytes;
     return 0;
 }
 

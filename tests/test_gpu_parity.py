@@ -416,9 +416,10 @@ def test_facade_reference_smoke_scripts():
     (32, 32, 1024, 100, (1, 7, 0), True),
     (64, 64, 1024, 60, (2, 4, 2), False),
 ])
-def test_filtered_fast_path_equals_all_fp64_path(R, C, N, T, counts, nice):
-    """Device vs device at full size: the fixed-point filter + exact fallback must give the same
-    bits as routing every sample through the fp64 reference arithmetic."""
+def test_cache_and_filtered_march_equal_all_fp64_path(R, C, N, T, counts, nice):
+    """Device vs device at full size: the angular visibility cache (default mode) and the fixed-point filter +
+    exact fallback (march mode) must give the same bits as routing every sample through the fp64 reference
+    arithmetic."""
     cfg = EnvironmentConfig(grid_rows=R, grid_cols=C)
     env = BatchedHeistEnv(cfg, N)
     rng = np.random.default_rng(4242 + R + N)
@@ -427,18 +428,119 @@ def test_filtered_fast_path_equals_all_fp64_path(R, C, N, T, counts, nice):
     cp = synthetic.sample_cam_params(rng, N, nice)
     acts = synthetic.sample_actions(rng, T, N)
     res = []
-    for exact in (False, True):
-        env.set_exact_only(exact)
+    for mode in (env.MODE_DEFAULT, env.MODE_MARCH, env.MODE_EXACT):
+        env.set_mode(mode)
         env.set_layout_from_asset_map(am, cp, 22 if counts else 15)
+        if mode == env.MODE_DEFAULT:   # Architect-decoded layouts are what the cache is built for: all of them
+            assert env.cache_stats()[0] == N
         env.reset()
         v0 = env.visibility_bits.clone()
         out = env.step_many(acts, autoreset=True, want_vis=True)
-        res.append((v0, {k: v.clone() for k, v in out.items()}, env.cam_heading.clone(), env.env_dyn.clone()))
-    assert torch.equal(res[0][0], res[1][0])
-    for k in res[0][1]:
-        assert torch.equal(res[0][1][k], res[1][1][k]), k
-    assert torch.equal(res[0][2], res[1][2]) and torch.equal(res[0][3], res[1][3])
+        res.append((v0, {k: v.clone() for k, v in out.items()}, env.cam_heading.clone(), env.env_dyn.clone(),
+                    env.guard_heading.clone(), env.guard_idx.clone(), env.visibility_bits.clone()))
+    env.check_errors()
+    for other in res[1:]:
+        assert torch.equal(res[0][0], other[0])
+        for k in res[0][1]:
+            assert torch.equal(res[0][1][k], other[1][k]), k
+        for i in range(2, 7):
+            assert torch.equal(res[0][i], other[i]), i
     assert res[0][1]["vis_bits"].ne(0).any()
+
+
+@pytest.mark.parametrize("R,N,autoreset", [(20, 1024, True), (20, 512, False), (64, 256, True)])
+def test_cached_path_launch_shapes_agree(R, N, autoreset):
+    """The table-driven path has several launch shapes -- pipelined chunks (auto-reset, T > 32), sequential chunks,
+    single ticks, with the maps built in the caller's trajectory or in scratch.  They must agree with each other
+    and carry state across launches (envs that are done when a launch begins included)."""
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=R, max_steps=40)
+    env = BatchedHeistEnv(cfg, N)
+    rng = np.random.default_rng(77 + R)
+    am = synthetic.sample_asset_maps(rng, N, R, R)
+    cp = synthetic.sample_cam_params(rng, N)
+    T = 100
+    acts = torch.as_tensor(synthetic.sample_actions(rng, T, N)).cuda()
+
+    def fresh():
+        env.set_layout_from_asset_map(am, cp, 15)
+        env.reset()
+
+    def state():
+        return [x.clone() for x in (env.env_dyn, env.cam_heading, env.guard_heading, env.guard_idx, env.visibility_bits)]
+
+    fresh()
+    ref = env.step_many(acts, autoreset=autoreset, want_vis=True)
+    ref = {k: v.clone() for k, v in ref.items()}
+    ref_state = state()
+    # (1) no trajectory buffer: maps built in scratch, same outputs and same final state
+    fresh()
+    out = env.step_many(acts, autoreset=autoreset, want_vis=False)
+    for k in ("reward", "done", "status"):
+        assert torch.equal(out[k], ref[k]), k
+    for a, b in zip(state(), ref_state):
+        assert torch.equal(a, b)
+    # (2) the same rollout in uneven pieces (33 + 1 + 7 + 59 ticks)
+    fresh()
+    t0 = 0
+    for n in (33, 1, 7, 59):
+        o = env.step_many(acts[t0:t0 + n], autoreset=autoreset, want_vis=True)
+        for k in ref:
+            assert torch.equal(o[k], ref[k][t0:t0 + n]), (k, t0)
+        t0 += n
+    for a, b in zip(state(), ref_state):
+        assert torch.equal(a, b)
+    # (3) against the ray-march on the same inputs
+    env.set_mode(env.MODE_MARCH)
+    fresh()
+    o = env.step_many(acts, autoreset=autoreset, want_vis=True)
+    for k in ref:
+        assert torch.equal(o[k], ref[k]), k
+    for a, b in zip(state(), ref_state):
+        assert torch.equal(a, b)
+    env.check_errors()
+
+
+def test_cache_coverage_and_fallback_mix():
+    """Assets outside the cache's range (vision_range > 7, fov > 180, more than 4 guards) leave their env to the
+    ray-march kernel; both kernels then serve one batch.  HEIST_NO_VIS_CACHE=1 disables the cache altogether."""
+    import os
+    cfg = EnvironmentConfig(max_steps=30)
+    N = 64
+    env = BatchedHeistEnv(cfg, N, max_cams=8, max_guards=8, max_path=8)
+    lays = []
+    for i in range(N):
+        cams = [{"row": 5, "col": 5 + (i % 7), "fov_angle": 60.0 + i, "heading": 10.0 * i, "rotation_speed": 7.5, "vision_range": 6}]
+        if i % 4 == 1:
+            cams.append({"row": 12, "col": 12, "fov_angle": 90.0, "heading": 0.0, "rotation_speed": 15.0, "vision_range": 9})
+        if i % 4 == 2:
+            cams.append({"row": 12, "col": 12, "fov_angle": 200.0, "heading": 0.0, "rotation_speed": 15.0, "vision_range": 3})
+        guards = [{"patrol_path": [(15, 3), (15, 4), (15, 5), (14, 5)], "speed": 1, "vision_range": 4, "fov_angle": 90.0}]
+        if i % 4 == 3:
+            guards = guards * 5
+        lays.append(([(8, 8), (8, 9)], cams, guards))
+    env.set_layout_explicit(lays, budget=np.full(N, 100, np.int32))
+    cached, nbytes = env.cache_stats()
+    assert cached == N // 4 and nbytes > 0
+    oenvs = []
+    for w, c, g in lays:
+        e = ho.OracleEnv(20, 20, max_steps=30, budget=100)
+        e.set_layout(w, c, g)
+        oenvs.append(e)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(np.random.default_rng(3), 70, N)
+    out = env.step_many(acts, autoreset=True, want_vis=True)
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    for k in ("done", "status", "reward"):
+        assert np.array_equal(out[k].cpu().numpy(), ref[k]), k
+    assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+    env.check_errors()
+    os.environ["HEIST_NO_VIS_CACHE"] = "1"
+    try:
+        env2 = BatchedHeistEnv(cfg, 8)
+    finally:
+        del os.environ["HEIST_NO_VIS_CACHE"]
+    assert env2.cache_stats() == (0, 0)
 
 
 def test_debug_bounds_build_reports_no_out_of_range_access():
