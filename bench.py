@@ -33,6 +33,8 @@ def workload_config(args, world):
                         f"Solver-only rollout T={args.ticks}, auto-reset, uniform actions",
             "grid": [args.rows, args.cols], "envs_per_gpu": args.envs, "ticks_per_step": args.ticks,
             "budget": args.budget, "max_steps": 200, "parallelism": f"env-shard x{world} (no data-path collective)",
+            "visibility": {0: "angular cache (k_heads, k_cam_vis, k_seq, k_finish; ray-march for uncovered envs)",
+                           1: "all-fp64 ray-march", 2: "filtered ray-march"}[args.mode],
             "l2": "flushed between timed iterations (256 MiB write)"}
 
 
@@ -42,17 +44,12 @@ def b_step_bytes(rows, cols, kc, kg):
     return 1 + (g + 32 * kc + 40 * kg + 16) + (8 * kc + 12 * kg + 16) + g + 5
 
 
-def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture (or None)."""
+def measured(key, field):
+    """Per-step figures from the committed ncu capture of this command (profiles/traffic.json), or None:
+    dram_bytes_per_launch = dram__bytes_read.sum + dram__bytes_write.sum, warp_inst_per_launch = smsp__inst_executed.sum,
+    summed over the kernels of one step."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
-
-
-def measured_inst(kernel):
-    try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[kernel]["warp_inst_per_launch"]
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key][field]
     except Exception:
         return None
 
@@ -178,9 +175,11 @@ def run_ours(args, rank, world, local_rank):
     cfg = heist_b200.EnvironmentConfig(grid_rows=args.rows, grid_cols=args.cols, max_steps=200,
                                        architect_budget=args.budget)
     env = heist_b200.BatchedHeistEnv(cfg, args.envs, device=dev)
+    env.set_mode(args.mode)
     seed = synthetic.BASE_SEED + rank
     synthetic.make_valid_workload(env, seed, args.budget, exact_counts=args.exact_counts)
     env.reset()
+    envs_cached, cache_bytes = env.cache_stats()
     kc = float(env.env_static[:, 0].float().mean().item())
     kg = float(env.env_static[:, 1].float().mean().item())
     rng = np.random.default_rng(seed + 7919)
@@ -230,7 +229,9 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
 
     # (1) kernel-resident throughput: inputs already in HBM
+    launches0 = env.launch_count()
     ms_value = timed_loop(lambda i: env.step_many(acts_dev[i], autoreset=True, out=out))
+    launches_per_step = (env.launch_count() - launches0) // (args.warmup + args.steps)
     steps_per_iter = T * N  # auto-reset: every (tick, env) is a live env step
     total_steps = steps_per_iter * args.steps * world
     value = total_steps / (ms_value * 1e-3)
@@ -277,6 +278,7 @@ def run_ours(args, rank, world, local_rank):
     if rank != 0:
         return
     ms_kernel = ms_value / args.steps
+    tkey = "step_cached" if (args.mode == 0 and cache_bytes) else "k_step_many"
     bstep = b_step_bytes(args.rows, args.cols, kc, kg)
     achieved = bstep * steps_per_iter / (ms_kernel * 1e-3) / 1e9
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -284,14 +286,18 @@ def run_ours(args, rank, world, local_rank):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T * N, "d2h_bytes_per_step": 5 * T * N,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": 2 * args.steps,  # k_step_many + k_build_order per step
-            "roofline": {"bound": "hbm", "kernel": "k_step_many", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured_traffic("k_step_many"), "peak_source": peak_src,
+            "gpu_launches": launches_per_step * args.steps,  # counted by the library (heist_launch_count)
+            "roofline": {"bound": "hbm", "kernel": tkey, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": measured(tkey, "dram_bytes_per_launch"), "peak_source": peak_src,
                          "bytes_per_env_step": bstep, "mean_cams": kc, "mean_guards": kg,
-                         "note": "the ray-march is instruction-issue bound, not HBM bound (SURVEY 8d, DESIGN.md 5): "
-                                 "frac is honest and small; see profiles/ for issue-slot utilisation"},
+                         "launches_per_step": launches_per_step, "kernel_share": measured(tkey, "share"),
+                         "note": "achieved = SURVEY 8d algorithmic bytes of the packed step x env-steps / duration of the whole "
+                                 "step (all of its kernels, pipelined over three streams, timed on the caller's stream); the "
+                                 "step is bound by L2-resident table lookups and warp-instruction issue, not by HBM "
+                                 "(DESIGN.md 4): frac is honest and small, traffic is the step's measured DRAM bytes"},
+            "cache": {"envs_cached": envs_cached, "envs": N, "bytes": cache_bytes},
             "clocks": clocks, "other_kernels": extra}
-    inst = measured_inst("k_step_many")
+    inst = measured(tkey, "warp_inst_per_launch")
     if inst and args.config == 2 and args.envs == 4096 and args.ticks == 200 and clocks and clocks.get("sm_mhz"):
         # informational: the bound that actually applies.  Warp-instructions per launch from the committed ncu
         # capture, issue peak = 148 SMs x 4 schedulers x 1 instruction/clock at the SM clock sampled during the run.
@@ -320,6 +326,8 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4],
                     help="BASELINE.json configs[] index: 2 = 20x20/4096 envs (default, the headline), 3 = 32x32/65536 "
                          "envs, 4 cameras + 2 guards, 4 = 64x64/262144 envs split over the GPUs")
+    ap.add_argument("--mode", type=int, default=0, choices=[0, 1, 2],
+                    help="heist_set_mode: 0 = angular visibility cache (default), 1 = all-fp64 ray-march, 2 = filtered ray-march")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

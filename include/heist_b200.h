@@ -215,6 +215,9 @@ int heist_set_mode(HeistHandle *h, int mode);
  */
 int heist_cache_stats(HeistHandle *h, int32_t *envs_cached, int64_t *cache_bytes, void *stream);
 
+/* Kernels this handle has launched for reset / step / step_many / step_observe since heist_create (bench accounting). */
+int heist_launch_count(HeistHandle *h, int64_t *count);
+
 /* Synchronises `stream` and reports sticky device-side errors (capacity overflow, bad waypoint). */
 int heist_check_errors(HeistHandle *h, void *stream);
 

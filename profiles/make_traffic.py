@@ -1,0 +1,47 @@
+"""profiles/traffic.json from an ncu CSV of `bench.py --steps 2 --warmup 3 --no-cpu-baseline` (read here, no GPU).
+
+usage: python profiles/make_traffic.py launches.csv [key]
+The CSV must carry gpu__time_duration.sum, dram__bytes_read.sum, dram__bytes_write.sum, smsp__inst_executed.sum for
+every launch.  One step = the kernels from the 4th k_heads launch (first timed step_many) up to the 5th; for the
+ray-march modes, the 4th k_step_many launch alone."""
+import collections, csv, json, os, sys
+
+
+def main():
+    path = sys.argv[1]
+    key = sys.argv[2] if len(sys.argv) > 2 else "step_cached"
+    rows = [r for r in csv.reader(open(path)) if len(r) > 5]
+    hdr = rows[0]
+    iid, ik, im, iv = hdr.index("ID"), hdr.index("Kernel Name"), hdr.index("Metric Name"), hdr.index("Metric Value")
+    launches = collections.OrderedDict()
+    for r in rows[1:]:
+        launches.setdefault(int(r[iid]), {"name": r[ik].split("(")[0].replace("void ", "")})[r[im]] = float(r[iv].replace(",", ""))
+    seq = list(launches.values())
+    anchor = "k_heads" if key == "step_cached" else "k_step_many"
+    idx = [i for i, l in enumerate(seq) if l["name"].startswith(anchor)]
+    step = seq[idx[3]:idx[4]] if key == "step_cached" else [seq[idx[3]]]
+    step = [l for l in step if l["name"].startswith("k_")]
+    tot_t = sum(l["gpu__time_duration.sum"] for l in step)
+    share = collections.OrderedDict()
+    for l in step:
+        n = l["name"].split("<")[0]
+        share[n] = share.get(n, 0.0) + l["gpu__time_duration.sum"] / tot_t
+    out_path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "traffic.json")
+    try:
+        data = json.load(open(out_path))
+    except Exception:
+        data = {}
+    data[key] = {
+        "dram_bytes_per_launch": int(sum(l["dram__bytes_read.sum"] + l["dram__bytes_write.sum"] for l in step)),
+        "warp_inst_per_launch": int(sum(l["smsp__inst_executed.sum"] for l in step)),
+        "kernels_per_step": len(step),
+        "serialized_us": round(tot_t / 1e3, 1),
+        "share": {k: round(v, 3) for k, v in share.items()},
+        "source": os.path.basename(path) + " (ncu, kernels serialised and cold-cache: use shares and counters, not the absolute time)",
+    }
+    json.dump(data, open(out_path, "w"), indent=1)
+    print(json.dumps(data[key], indent=1))
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,7 @@ EXPORTS = {
     "heist_check_errors": (C.c_int, [c_vp, c_vp]),
     "heist_set_mode": (C.c_int, [c_vp, C.c_int]),
     "heist_cache_stats": (C.c_int, [c_vp, c_vp, c_vp, c_vp]),
+    "heist_launch_count": (C.c_int, [c_vp, c_vp]),
 }
 
 

@@ -153,6 +153,13 @@ class BatchedHeistEnv:
         _ffi.check(self._lib.heist_cache_stats(self._h, ctypes.byref(n), ctypes.byref(b), self._stream()), "heist_cache_stats")
         return int(n.value), int(b.value)
 
+    def launch_count(self):
+        """Kernels launched by reset / step / step_many / step_observe on this handle so far."""
+        import ctypes
+        n = ctypes.c_int64(0)
+        _ffi.check(self._lib.heist_launch_count(self._h, ctypes.byref(n)), "heist_launch_count")
+        return int(n.value)
+
     def set_exact_only(self, flag):
         """Force the all-fp64 ray-march (True) or go back to the default mode (False)."""
         self.set_mode(self.MODE_EXACT if flag else self.MODE_DEFAULT)

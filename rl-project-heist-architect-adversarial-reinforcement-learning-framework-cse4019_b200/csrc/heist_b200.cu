@@ -47,6 +47,7 @@ struct HeistHandle {
     size_t step_smem, layout_smem;
     int mode;        // heist_set_mode: HEIST_MODE_*
     size_t camvis_smem, seq_smem, cache_bytes;
+    long long launches;   // kernels launched by reset / step / step_many (heist_launch_count)
     double *heads;      size_t heads_cap;     // k_heads output, grow-only [blocks][N][Kc]
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
@@ -311,6 +312,7 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
+    h->launches += 1;
 }
 
 static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
@@ -321,6 +323,7 @@ static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
                                                               c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask)
     if (d.C > 32) GO(2); else GO(1);
 #undef GO
+    h->launches += 1;
 }
 
 static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
@@ -335,6 +338,7 @@ static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
+    h->launches += (!c.only_last && !c.autoreset) ? 2 : 1;
 }
 
 #define FAST_PIPE_TC 32        // ticks per pipelined chunk (a multiple of FAST_TB)
@@ -366,6 +370,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)total * NRW));
         uint32_t *cam = vis_traj ? vis_traj : h->scratch;
         k_heads<<<gh, 128, 0, s>>>(d, total, 0, 1, h->heads);
+        h->launches += 1;
         CUDA_TRY(cudaEventRecord(h->ev_fork, s));
         CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_fork, 0));
@@ -409,6 +414,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         c.cam = vis_traj ? vis_traj + (size_t)t0 * NRW : h->scratch; c.heads = h->heads;
         c.grec = h->grec; c.fin = h->fin; c.last_t = h->last_t;
         k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, (autoreset && !do_reset) ? 1 : 0, h->heads);
+        h->launches += 1;
         launch_cam_vis(h, c, s);
         launch_seq(h, c, s);
         launch_finish(h, c, s);
@@ -432,6 +438,7 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     if (exact) { if (big) GO(true, true); else GO(true, false); }
     else { if (big) GO(false, true); else GO(false, false); }
 #undef GO
+    h->launches += 1;
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
@@ -447,7 +454,14 @@ static int launch_step(HeistHandle *h, const int8_t *actions, int T, int autores
     if (exact) { if (big) GO(true, true); else GO(true, false); }
     else { if (big) GO(false, true); else GO(false, false); }
 #undef GO
+    h->launches += 1;
     CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int heist_launch_count(HeistHandle *h, int64_t *count) {
+    if (!h || !count) return fail(-1, "heist_launch_count: null argument");
+    *count = h->launches;
     return 0;
 }
 
@@ -489,6 +503,7 @@ extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int
         CUDA_TRY(cudaMemsetAsync(h->d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(h->N) * HEIST_WARPS_PER_CTA,
                                  (cudaStream_t)stream));
         k_build_order<<<1, 1024, 0, (cudaStream_t)stream>>>(h->d, env_blocks(h->N));
+        h->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
     return 0;
