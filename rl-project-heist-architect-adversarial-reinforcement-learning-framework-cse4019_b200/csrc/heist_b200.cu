@@ -150,10 +150,10 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         size_t free_b = 0, total_b = 0;
         cudaMemGetInfo(&free_b, &total_b);
         const size_t HS = (size_t)d.L + 1;
-        const size_t need = N * d.Kc * ((size_t)VC_POINTS * 8 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
+        const size_t need = N * d.Kc * ((size_t)VC_POINTS * 4 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
                             N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
         const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
-                              FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024;
+                              FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024 && d.L <= 32;
         if (!(off && off[0] == '1') && need < free_b / 2 && seq_fits) {
             h->cache_bytes = need;
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
@@ -328,7 +328,7 @@ static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
 
 static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
-    const dim3 g3((unsigned)((h->N + 7) / 8), (unsigned)(c.only_last ? 1 : c.Tc)), g4((unsigned)((h->N + 7) / 8), (unsigned)c.Tc);
+    const dim3 g3((unsigned)((h->N + 7) / 8), (unsigned)(c.only_last ? 1 : (c.Tc + FIN_TB - 1) / FIN_TB)), g4((unsigned)((h->N + 7) / 8), (unsigned)c.Tc);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
 #define GO(RPL, W)                                                                                       \
     do {                                                                                                 \
@@ -369,6 +369,9 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         CUDA_TRY(grow(&h->last_t, &h->last_cap, (size_t)n_chunks * N));
         if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)total * NRW));
         uint32_t *cam = vis_traj ? vis_traj : h->scratch;
+        static const bool timing = getenv("HEIST_TIMING") != nullptr;   // debug: per-stage timeline of one launch
+        cudaEvent_t te[3][FAST_PIPE_MAX + 1];
+        if (timing) { for (int a = 0; a < 3; ++a) for (int i = 0; i <= n_chunks; ++i) cudaEventCreate(&te[a][i]); cudaEventRecord(te[0][0], s); }
         k_heads<<<gh, 128, 0, s>>>(d, total, 0, 1, h->heads);
         h->launches += 1;
         CUDA_TRY(cudaEventRecord(h->ev_fork, s));
@@ -383,16 +386,29 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc;
             c.grec = h->grec + off * d.Kg; c.fin = h->fin + off; c.last_t = h->last_t + (size_t)i * N;
             launch_cam_vis(h, c, s);
+            if (timing) cudaEventRecord(te[0][i + 1], s);
             CUDA_TRY(cudaEventRecord(h->ev_cam[i], s));
             CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_cam[i], 0));
             launch_seq(h, c, h->s_seq);
+            if (timing) cudaEventRecord(te[1][i + 1], h->s_seq);
             CUDA_TRY(cudaEventRecord(h->ev_seq[i], h->s_seq));
             CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_seq[i], 0));
             launch_finish(h, c, h->s_fin);
+            if (timing) cudaEventRecord(te[2][i + 1], h->s_fin);
         }
         CUDA_TRY(cudaEventRecord(h->ev_join, h->s_fin));   // s_fin's last kernel waited for s_seq's last
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
         CUDA_TRY(cudaGetLastError());
+        if (timing) {
+            cudaDeviceSynchronize();
+            const char *nm[3] = {"cam_vis", "seq", "finish"};
+            for (int a = 0; a < 3; ++a) {
+                fprintf(stderr, "[heist timing] %-8s done at (us):", nm[a]);
+                for (int i = 1; i <= n_chunks; ++i) { float ms = 0; cudaEventElapsedTime(&ms, te[0][0], te[a][i]); fprintf(stderr, " %7.1f", ms * 1e3f); }
+                fprintf(stderr, "\n");
+            }
+            for (int a = 0; a < 3; ++a) for (int i = 0; i <= n_chunks; ++i) cudaEventDestroy(te[a][i]);
+        }
         return 0;
     }
 

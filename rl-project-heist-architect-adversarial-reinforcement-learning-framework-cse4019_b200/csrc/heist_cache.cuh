@@ -118,6 +118,13 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
         if (!vc_cam_cacheable(fov, heading, speed, range, num_rays)) { env_ok = false; continue; }  // CTA-uniform
         const int nsamp = 2 * range;
         const double dom_lo = -0.5 * fov - 1e-6, dom_hi = 360.0 + 0.5 * fov + 1e-6;
+        // Boundary points are stored in units of the ray pitch above dom_lo as fixed point below 2^29, so that the
+        // per-tick ray count below a point is an integer subtract and shift (k_cam_vis).  The quantisation (under 2
+        // units for point and base together) is absorbed by widening every band by 4 units.
+        const double inv_step = 1.0 / (fov / (double)num_rays);
+        const int sh = max(0, min(24, 28 - ilogb((dom_hi - dom_lo) * inv_step)));
+        const double fx_scale = inv_step * (double)(1 << sh);
+        const double pad = VC_PAD + 4.0 / fx_scale;
         if (tid == 0) {
             S.n_raw = 2; S.ok = 1;
             S.key[0] = -1e300; S.end[0] = dom_lo;   // everything outside the domain is one band on each side:
@@ -141,7 +148,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
             const double off = axis ? 90.0 : 0.0;
             const double b0 = sgn ? off - a_hi : off + a_lo, b1 = sgn ? off - a_lo : off + a_hi;
             for (int n = -1; n <= 2; ++n) {
-                const double s = b0 + 360.0 * n - VC_PAD, e = b1 + 360.0 * n + VC_PAD;
+                const double s = b0 + 360.0 * n - pad, e = b1 + 360.0 * n + pad;
                 if (e < dom_lo || s > dom_hi) continue;
                 const int slot = atomicAdd(&S.n_raw, 1);
                 if (slot < VC_RAW) { S.key[slot] = s; S.end[slot] = e; }
@@ -234,13 +241,14 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
                 __syncthreads();
             }
         }
-        double *P = D.vc_p + o * VC_POINTS;
+        int32_t *P = D.vc_p + o * VC_POINTS;
         uint4 *MK4 = reinterpret_cast<uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
         for (int g = tid; g < nb - 1; g += VC_BUILD_THREADS) {
-            P[2 * g] = S.end[g]; P[2 * g + 1] = S.key[g + 1];
+            P[2 * g] = (int32_t)floor((S.end[g] - dom_lo) * fx_scale); P[2 * g + 1] = (int32_t)floor((S.key[g + 1] - dom_lo) * fx_scale);
             MK4[2 * g] = S.gm[g][0]; MK4[2 * g + 1] = S.gm[g][1];
         }
-        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = 2 * (nb0 - 1); D.vc_lo[o] = dom_lo; }
+        for (int i = n_points + tid; i < VC_POINTS; i += VC_BUILD_THREADS) P[i] = 0x7fffffff;   // no ray lies above
+        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = sh; D.vc_lo[o] = dom_lo; }
         // ---- 4. coarse index: points below each 1-degree bucket start ----
         uint16_t *IX = D.vc_idx + o * VC_IDX;
         for (int q = tid; q < VC_IDX; q += VC_BUILD_THREADS) {

@@ -46,10 +46,10 @@ struct Dev {
     int32_t *slot2env;    // [ceil(N/4)*4] warp slot -> env (-1: empty), cost-balanced
     int *err;             // sticky device error flags
     // angular visibility cache (heist_cache.cuh); vc_p == nullptr: cache disabled
-    double *vc_p;         // [N][Kc][VC_POINTS] sorted boundary angles of the tie bands
+    int32_t *vc_p;        // [N][Kc][VC_POINTS] sorted boundary points of the tie bands: (angle - lo) / ray pitch, fixed point
     uint16_t *vc_mask;    // [N][Kc][VC_POINTS/2][VC_ROWS] window bitmap of gap g
     uint16_t *vc_idx;     // [N][Kc][VC_IDX] coarse index: boundary points below each 1-degree bucket
-    int32_t *vc_meta;     // [N][Kc][2] n_points (-1: not cacheable), reserved
+    int32_t *vc_meta;     // [N][Kc][2] n_points (-1: not cacheable), fixed-point shift of vc_p
     double *vc_lo;        // [N][Kc] lower end of the cached angle domain
     uint16_t *vg_mask;    // [N][Kg][L][L+1][VC_ROWS] guard cone per (waypoint, heading slot)
     double *vg_hval;      // [N][Kg][L+1] distinct headings a guard can carry

@@ -26,10 +26,10 @@
 #define FAST_TB 8      // ticks per k_cam_vis warp
 
 struct FastCam {
-    double heading, speed, fov, inv_step, dom_lo;
-    const double *P;        // boundary points
+    double heading, speed, fov, fx_scale, dom_lo;
+    const int32_t *P;       // boundary points (fixed point, heist_cache.cuh)
     const uint16_t *MK;     // gap masks
-    int row, col, range, num_rays, n_points, s0, pad0, pad1;
+    int row, col, range, num_rays, n_points, s0, sh, base_fx;
 };
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
@@ -86,9 +86,9 @@ __global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int w
     if (write_final && T > 0) D.cam_heading[i] = last;
 }
 
-// rays below boundary point p: clamp(ceil((p - base) / step), 0, NR)
-__device__ __forceinline__ int fast_nrays(double p, double base, double inv_step, int NR) {
-    return max(0, min(NR, __double2int_ru((p - base) * inv_step)));
+// rays below boundary point p: clamp(ceil((p - base) / 2^sh), 0, NR), p and base in fixed-point ray pitches
+__device__ __forceinline__ int fast_nrays(int p, int base_fx, int round_up, int sh, int NR) {
+    return max(0, min(NR, (p - base_fx + round_up) >> sh));
 }
 
 // Rare path of k_cam_vis, kept out of line: camera rays [r0, r1) sit on (or within 1e-9 degree of) a rounding
@@ -133,9 +133,10 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
         Cm.heading = heads[(size_t)b * D.N * D.Kc + o];
         Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
-        Cm.inv_step = 1.0 / (Cm.fov / (double)Cm.num_rays);
         Cm.dom_lo = D.vc_lo[o];
         Cm.n_points = D.vc_meta[o * 2];
+        Cm.sh = D.vc_meta[o * 2 + 1];
+        Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
         Cm.P = D.vc_p + o * VC_POINTS;
         Cm.MK = D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS;
         IX = D.vc_idx + o * VC_IDX;
@@ -152,6 +153,8 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
             const double base = Cm.heading - Cm.fov * 0.5;
             const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
             Cm.s0 = max(0, (int)IX[q] - 1) & ~1;
+            // the first ray in fixed point; far outside the domain every ray is in a sentinel band anyway
+            Cm.base_fx = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
         }
         __syncwarp();
         uint32_t vis[RPL][W];
@@ -162,28 +165,28 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         bool exact_used = false;
         for (int k = 0; k < n_cams; ++k) {
             const FastCam &Cm = cams[k];
-            const double base = Cm.heading - Cm.fov * 0.5, inv_step = Cm.inv_step;
+            const int base_fx = Cm.base_fx, sh = Cm.sh, round_up = (1 << sh) - 1;
             const int NR = Cm.num_rays + 1, n_points = Cm.n_points;
-            const double *P = Cm.P;
+            const int32_t *P = Cm.P;
             const uint4 *MK4 = reinterpret_cast<const uint4 *>(Cm.MK);   // gap g = uint4 2g, 2g + 1
             int carry = 0;
             bool first = Cm.s0 > 0;   // lane 0 of the first pass only supplies the lower count of lane 1
             uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;   // even lanes: mask words 0-3, odd lanes: words 4-7
             bool more = true;
             for (int sb = Cm.s0; more; sb += 32 * CV_PASSES) {
-                double pv[CV_PASSES];
+                int pv[CV_PASSES];
                 uint4 mv[CV_PASSES];
 #pragma unroll
                 for (int u = 0; u < CV_PASSES; ++u) {
                     const int s = sb + 32 * u + lane;
-                    pv[u] = s < n_points ? P[s] : 1e300;
+                    pv[u] = P[min(s, VC_POINTS - 1)];   // padded with INT_MAX above n_points
                     // half (lane & 1) of gap (sb + 32u) / 2 + (lane >> 1), i.e. of segment sb + 32u + (lane | 1)
                     mv[u] = (sb + 32 * u + (lane | 1)) < n_points ? __ldg(MK4 + (sb + 32 * u) + lane) : make_uint4(0, 0, 0, 0);
                 }
 #pragma unroll
                 for (int u = 0; u < CV_PASSES; ++u) {
                     if (!more) break;
-                    const int n_s = fast_nrays(pv[u], base, inv_step, NR);
+                    const int n_s = fast_nrays(pv[u], base_fx, round_up, sh, NR);
                     int n_prev = __shfl_up_sync(0xffffffffu, n_s, 1);
                     if (lane == 0) n_prev = first ? n_s : carry;
                     first = false;
@@ -515,55 +518,73 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     }
 }
 
-// k_finish: warp per (tick, env), lane = grid row: visibility row = cam_vis row OR the guards' masks at the state
-// k_seq recorded -> written in place (the buffer is the caller's trajectory, or scratch) and, for the last
-// rebuilt tick of an env, to its current map D.vis.  only_last: no trajectory wanted -- warp per env.
+// k_finish: warp per (env, block of FIN_TB ticks), lane = grid row: visibility row = cam_vis row OR the guards'
+// masks at the state k_seq recorded -> written in place (the buffer is the caller's trajectory, or scratch) and,
+// for the last rebuilt tick of an env, to its current map D.vis.  The env's patrol words sit in registers (lane k
+// holds waypoint k of every guard; max_path <= 32), so a tick costs one shuffle pair and one 2-byte mask load
+// per guard.  only_last: no trajectory wanted -- one tick per env.
 // Ticks an env spent done without auto-reset (fin == 0) keep the env's current map; they are filled by k_fill
 // once D.vis is final.
+#define FIN_TB 8
 template <int RPL, int W>
 __global__ void __launch_bounds__(256)
 k_finish(Dev D, int T, uint32_t *buf, const uint16_t *__restrict__ grec, const uint8_t *__restrict__ fin,
          const int32_t *__restrict__ last_t, int only_last, const uint8_t *__restrict__ mask) {
-    const int lane = threadIdx.x & 31;   // grid: x = env / 8, y = tick
+    const int lane = threadIdx.x & 31;   // grid: x = env / 8, y = tick block
     const int env = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (env >= D.N || !D.env_cached[env] || (mask && !mask[env])) return;
     const int lt = last_t[env];
-    const int t = only_last ? lt : (int)blockIdx.y;
-    if (t < 0) return;
-    const size_t o = (size_t)t * D.N + env;
-    // independent loads first: the tick's flag, the cam_vis rows, and -- lane g -- guard g's recorded state
-    const int n_guards = D.env_s[(size_t)env * 4 + 1];
-    const unsigned f = fin[o];
-    unsigned rec = 0;
-    if (lane < n_guards) rec = grec[o * D.Kg + lane];
-    uint32_t v[RPL][W];
+    int t0 = blockIdx.y * FIN_TB, t1 = min(T, t0 + FIN_TB);
+    if (only_last) { t0 = lt; t1 = lt + 1; }
+    if (t0 < 0) return;
+    constexpr int G = VC_MAX_GUARDS;
+    const int n_guards = D.env_s[(size_t)env * 4 + 1], L = D.L, Kg = D.Kg, RW = D.RW;
+    unsigned pw[G];            // lane k: waypoint k of guard g  (row | col << 8 | range << 16)
+    const uint16_t *gmask[G];
 #pragma unroll
-    for (int a = 0; a < RPL; ++a)
-#pragma unroll
-        for (int w = 0; w < W; ++w) { const int r = lane + 32 * a; v[a][w] = r < D.R ? buf[o * D.RW + r * D.W + w] : 0u; }
-    if (!f) return;
-    // lane g: where guard g stands and how far it sees; then every lane ORs its row(s) of every guard's mask
-    int gp = 0;
-    if (lane < n_guards) {
-        const size_t go = (size_t)env * D.Kg + lane;
-        const int k = rec & 255;
-        gp = D.guard_path[(go * D.L + k) * 2] | (D.guard_path[(go * D.L + k) * 2 + 1] << 8) | (D.guard_i[go * 4 + 2] << 16);
+    for (int g = 0; g < G; ++g) {
+        pw[g] = 0; gmask[g] = D.vg_mask;
+        if (g < n_guards) {
+            const size_t go = (size_t)env * Kg + g;
+            if (lane < L) pw[g] = (unsigned)D.guard_path[(go * L + lane) * 2] | ((unsigned)D.guard_path[(go * L + lane) * 2 + 1] << 8) |
+                                  ((unsigned)D.guard_i[go * 4 + 2] << 16);
+            gmask[g] = D.vg_mask + go * L * (size_t)(L + 1) * VC_ROWS;
+        }
     }
-    for (int g = 0; g < n_guards; ++g) {
-        const unsigned rg = __shfl_sync(0xffffffffu, rec, g);
-        const int pg = __shfl_sync(0xffffffffu, gp, g);
+    for (int t = t0; t < t1; ++t) {
+        const size_t o = (size_t)t * D.N + env;
+        const unsigned f = fin[o];
+        unsigned rec = 0;
+        if (lane < n_guards) rec = grec[o * Kg + lane];
+        uint32_t v[RPL][W];
 #pragma unroll
         for (int a = 0; a < RPL; ++a)
-            guard_row<W>(D, (size_t)env * D.Kg + g, rg & 255, rg >> 8, pg & 255, (pg >> 8) & 255, pg >> 16, lane + 32 * a, v[a]);
-    }
 #pragma unroll
-    for (int a = 0; a < RPL; ++a) {
-        const int r = lane + 32 * a;
-        if (r < D.R) {
+            for (int w = 0; w < W; ++w) { const int r = lane + 32 * a; v[a][w] = r < D.R ? buf[o * RW + r * W + w] : 0u; }
+        if (!f) continue;   // warp-uniform
 #pragma unroll
-            for (int w = 0; w < W; ++w) {
-                if (!only_last) buf[o * D.RW + r * D.W + w] = v[a][w];
-                if (t == lt) D.vis[(size_t)env * D.RW + r * D.W + w] = v[a][w];
+        for (int g = 0; g < G; ++g) {
+            if (g < n_guards) {
+                const unsigned rg = __shfl_sync(0xffffffffu, rec, g);
+                const int k = rg & 255, hs = rg >> 8;
+                const unsigned word = __shfl_sync(0xffffffffu, pw[g], k);
+                const int prow = word & 255, pcol = (word >> 8) & 255, rng = word >> 16;
+#pragma unroll
+                for (int a = 0; a < RPL; ++a) {
+                    const int wr = lane + 32 * a - (prow - rng);
+                    if (wr >= 0 && wr <= 2 * rng) fast_or_row<W>(v[a], gmask[g][(k * (L + 1) + hs) * VC_ROWS + wr], pcol - rng);
+                }
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < RPL; ++a) {
+            const int r = lane + 32 * a;
+            if (r < D.R) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    if (!only_last) buf[o * RW + r * W + w] = v[a][w];
+                    if (t == lt) D.vis[(size_t)env * RW + r * W + w] = v[a][w];
+                }
             }
         }
     }
