@@ -33,7 +33,7 @@ struct FastCam {
 };
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
-    return (size_t)Kc * sizeof(FastCam) + (((size_t)RW * 4 + 15) & ~(size_t)15) + 32;
+    return (size_t)Kc * sizeof(FastCam) + 2 * (((size_t)RW * 4 + 15) & ~(size_t)15) + 32;
 }
 
 // bit (r, c) of a lane-per-row bitmap (all lanes get the answer; r, c warp-uniform)
@@ -91,16 +91,29 @@ __device__ __forceinline__ int fast_nrays(int p, int base_fx, int round_up, int 
     return max(0, min(NR, (p - base_fx + round_up) >> sh));
 }
 
-// Rare path of k_cam_vis, kept out of line: camera rays [r0, r1) sit on (or within 1e-9 degree of) a rounding
-// tie, or outside the cached angle domain -> march them exactly like the reference does.
-__device__ __noinline__ void cam_exact_rays(VcGeo D, const uint32_t *wall, uint32_t *xvis, const FastCam *cam, int r0,
-                                            int r1) {
-    const int row = cam->row, col = cam->col, W = D.W;
-    for (int ri = r0; ri < r1; ++ri)
-        vc_ray(D, wall, row, col, cam->fov, cam->heading, cam->num_rays, 2 * cam->range, 0.5, ri, [&](int r, int c) {
-            if (r == row && c == col) return;   // (r, c) != (self.row, self.col), security.py:93
-            atomicOr(&xvis[r * W + (c >> 5)], 1u << (c & 31));
-        });
+// Rare path of k_cam_vis, kept out of line: camera ray `ri` sits on (or within 1e-9 degree of) a rounding tie, or
+// outside the cached angle domain -> march it exactly like the reference does (security.py:69-99), the whole warp
+// on one ray: lane j evaluates sample j + 1 (at most 14 samples), a ballot finds the first blocked one.
+// `wall` is the env's wall bitmap in shared memory.
+__device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32_t *xvis, const FastCam *cam, int ri, int lane) {
+    const int row = cam->row, col = cam->col, nsamp = 2 * cam->range;
+    const double fov = cam->fov;
+    const double angle_deg = __dadd_rn(__dsub_rn(cam->heading, __ddiv_rn(fov, 2.0)),
+                                       __ddiv_rn(__dmul_rn(fov, (double)ri), (double)cam->num_rays));
+    double dx, dy;
+    ray_dir(angle_deg, D.deg2rad, dx, dy);
+    const double dist = 0.5 * (double)(lane + 1);   // step - 1 + sub: exact multiples of 0.5
+    int r = 0, c = 0;
+    bool blocked = true;
+    if (lane < nsamp) {
+        c = vc_rint_even(__dadd_rn((double)col, __dmul_rn(dx, dist)));
+        r = vc_rint_even(__dadd_rn((double)row, __dmul_rn(dy, dist)));
+        blocked = r < 0 || r >= D.R || c < 0 || c >= D.C;
+        if (!blocked) blocked = (wall[r * D.W + (c >> 5)] >> (c & 31)) & 1u;
+    }
+    const int first_blocked = __ffs(__ballot_sync(0xffffffffu, blocked)) - 1;   // lanes >= nsamp always are
+    if (lane < first_blocked && !(r == row && c == col))   // (r, c) != (self.row, self.col), security.py:93
+        atomicOr(&xvis[r * D.W + (c >> 5)], 1u << (c & 31));
 }
 
 #define CV_PASSES 4   // 32-segment passes whose loads are in flight together
@@ -122,8 +135,8 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
     unsigned char *sp = smem + (size_t)warp * camvis_warp_bytes(D.RW, D.Kc);
     FastCam *cams = reinterpret_cast<FastCam *>(sp);        sp += (size_t)D.Kc * sizeof(FastCam);
     uint32_t *xvis = reinterpret_cast<uint32_t *>(sp);      sp += ((size_t)D.RW * 4 + 15) & ~(size_t)15;
+    uint32_t *wall_s = reinterpret_cast<uint32_t *>(sp);    sp += ((size_t)D.RW * 4 + 15) & ~(size_t)15;
     uint32_t *stage = reinterpret_cast<uint32_t *>(sp);
-    const uint32_t *wall_g = D.wall + (size_t)env * D.RW;
     const int n_cams = D.env_s[(size_t)env * 4];
     const uint16_t *IX = nullptr;
     if (lane < n_cams) {
@@ -141,7 +154,7 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         Cm.MK = D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS;
         IX = D.vc_idx + o * VC_IDX;
     }
-    for (int i = lane; i < D.RW; i += 32) xvis[i] = 0;
+    for (int i = lane; i < D.RW; i += 32) { xvis[i] = 0; wall_s[i] = D.wall[(size_t)env * D.RW + i]; }
     const int t_end = min(T, (b + 1) * FAST_TB);
     for (int t = b * FAST_TB; t < t_end; ++t) {
         // every camera's window start from its coarse index: one load level for all cameras of the env.
@@ -194,9 +207,13 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
                     const bool hit = n_s > n_prev;
                     const unsigned hits = __ballot_sync(0xffffffffu, hit);
                     if ((hits >> (lane | 1)) & 1u) { acc0 |= mv[u].x; acc1 |= mv[u].y; acc2 |= mv[u].z; acc3 |= mv[u].w; }
-                    if (hits & 0x55555555u) {   // a band holds a ray (rare)
+                    unsigned bh = hits & 0x55555555u;   // bands that hold a ray (rare)
+                    while (bh) {
+                        const int src = __ffs(bh) - 1;
+                        bh &= bh - 1;
+                        const int r0 = __shfl_sync(0xffffffffu, n_prev, src), r1 = __shfl_sync(0xffffffffu, n_s, src);
+                        for (int ri = r0; ri < r1; ++ri) cam_exact_ray(vc_geo(D), wall_s, xvis, &Cm, ri, lane);
                         exact_used = true;
-                        if (hit && !(lane & 1)) cam_exact_rays(vc_geo(D), wall_g, xvis, &Cm, n_prev, n_s);
                     }
                     if (carry >= NR) more = false;  // warp-uniform
                 }
