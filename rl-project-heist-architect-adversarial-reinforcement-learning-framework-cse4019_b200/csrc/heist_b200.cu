@@ -53,8 +53,8 @@ struct HeistHandle {
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
     uint8_t *fin;       size_t fin_cap;       // k_seq -> k_finish: tick rebuilt its map [T][N]
     int32_t *last_t;    size_t last_cap;      // [chunks][N] last rebuilt tick of each chunk
-    cudaStream_t s_seq, s_fin;                // side streams of the pipelined launch
-    cudaEvent_t ev_fork, ev_join, ev_cam[64], ev_seq[64];
+    cudaStream_t s_seq, s_fin, s_cam2;        // side streams of the pipelined launch
+    cudaEvent_t ev_fork, ev_join, ev_join2, ev_cam[64], ev_seq[64];
     void *allocs[96];
     int n_allocs;
 };
@@ -90,8 +90,8 @@ extern "C" int heist_destroy(HeistHandle *h) {
     if (h->fin) cudaFree(h->fin);
     if (h->last_t) cudaFree(h->last_t);
     if (h->s_seq) {
-        cudaStreamDestroy(h->s_seq); cudaStreamDestroy(h->s_fin);
-        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join);
+        cudaStreamDestroy(h->s_seq); cudaStreamDestroy(h->s_fin); cudaStreamDestroy(h->s_cam2);
+        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_join2);
         for (int i = 0; i < 64; ++i) { cudaEventDestroy(h->ev_cam[i]); cudaEventDestroy(h->ev_seq[i]); }
     }
     delete h;
@@ -195,8 +195,14 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         CUDA_TRY(cudaMalloc(&h->fin, h->fin_cap));
         CUDA_TRY(cudaMalloc(&h->last_t, N * sizeof(int32_t)));
         h->last_cap = N;
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_seq, cudaStreamNonBlocking));
+        {   // k_seq is the serial chain of a launch: its blocks go first
+            int lo = 0, hi = 0;
+            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY(cudaStreamCreateWithPriority(&h->s_seq, cudaStreamNonBlocking, hi));
+        }
         CUDA_TRY(cudaStreamCreateWithFlags(&h->s_fin, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_cam2, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         for (int i = 0; i < 64; ++i) {
@@ -377,7 +383,11 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         CUDA_TRY(cudaEventRecord(h->ev_fork, s));
         CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_fork, 0));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_cam2, h->ev_fork, 0));
         for (int i = 0; i < n_chunks; ++i) {
+            // camera chunks are independent of each other: alternate two streams so that the tail of one chunk
+            // overlaps the head of the next
+            cudaStream_t sc = (i & 1) ? h->s_cam2 : s;
             const int t0 = i * FAST_PIPE_TC;
             const size_t off = (size_t)t0 * N;
             c.Tc = std::min(FAST_PIPE_TC, total - t0);
@@ -385,9 +395,9 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             c.done = done ? done + off : nullptr; c.status = status ? status + off : nullptr;
             c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc;
             c.grec = h->grec + off * d.Kg; c.fin = h->fin + off; c.last_t = h->last_t + (size_t)i * N;
-            launch_cam_vis(h, c, s);
-            if (timing) cudaEventRecord(te[0][i + 1], s);
-            CUDA_TRY(cudaEventRecord(h->ev_cam[i], s));
+            launch_cam_vis(h, c, sc);
+            if (timing) cudaEventRecord(te[0][i + 1], sc);
+            CUDA_TRY(cudaEventRecord(h->ev_cam[i], sc));
             CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_cam[i], 0));
             launch_seq(h, c, h->s_seq);
             if (timing) cudaEventRecord(te[1][i + 1], h->s_seq);
@@ -398,6 +408,8 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         }
         CUDA_TRY(cudaEventRecord(h->ev_join, h->s_fin));   // s_fin's last kernel waited for s_seq's last
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
+        CUDA_TRY(cudaEventRecord(h->ev_join2, h->s_cam2));
+        CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join2, 0));
         CUDA_TRY(cudaGetLastError());
         if (timing) {
             cudaDeviceSynchronize();

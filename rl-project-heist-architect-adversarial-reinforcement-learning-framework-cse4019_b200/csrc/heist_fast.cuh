@@ -381,8 +381,16 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         fin[env] = 1; SEQ_RECORD((size_t)env); last = 0;
         T = 0;
     }
-    int a_cur = 0, a_nxt = 0;
-    if (T > 0) { a_cur = actions[env]; a_nxt = T > 1 ? actions[(size_t)N + env] : 0; }
+    // actions: a small register queue, requested SEQ_AQ ticks ahead (they stream from HBM: one new sector per tick)
+    constexpr int SEQ_AQ = 4;
+    int a_cur = 0, a_q[SEQ_AQ];
+#pragma unroll
+    for (int i = 0; i < SEQ_AQ; ++i) a_q[i] = 0;
+    if (T > 0) {
+        a_cur = actions[env];
+#pragma unroll
+        for (int i = 0; i < SEQ_AQ; ++i) if (i + 1 < T) a_q[i] = actions[(size_t)(i + 1) * N + env];
+    }
     int pre_row = -1;
     uint32_t pre[W];
     unsigned pre_g[G], pre_key[G];   // mask row / (waypoint | slot << 8) it was fetched for
@@ -481,8 +489,10 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         fin[o] = rebuilt ? 1 : 0;
         if (rebuilt) { last = t; SEQ_RECORD(o); }
         // requests for tick t + 1
-        a_cur = a_nxt;
-        if (t + 2 < T) a_nxt = actions[o + 2 * (size_t)N];
+        a_cur = a_q[0];
+#pragma unroll
+        for (int i = 0; i + 1 < SEQ_AQ; ++i) a_q[i] = a_q[i + 1];
+        a_q[SEQ_AQ - 1] = (t + 1 + SEQ_AQ < T) ? actions[o + (size_t)(1 + SEQ_AQ) * N] : 0;
         pre_row = -1;
         if (t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state
             const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
