@@ -124,7 +124,7 @@ __device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32
 // -- independently, so that neither load waits for the other -- loads one 16-byte half of the mask of gap
 // (sb >> 1) + (j >> 1).  A gap's mask is kept iff its segment turns out to contain a ray.
 template <int RPL, int W>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 6)
+__global__ void __launch_bounds__(FAST_WARPS * 32, 5)
 k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, const uint8_t *__restrict__ mask) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
