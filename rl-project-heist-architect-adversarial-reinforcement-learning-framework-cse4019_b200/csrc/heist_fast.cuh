@@ -12,10 +12,11 @@
 //   k_cam_vis  warp per (env, tick block): union of the camera cones of every tick of the block from the cache
 //              (heist_cache.cuh) -> cam_vis[t][env] row bitmaps.  Embarrassingly parallel over env x time: no
 //              sequential dependence, no load imbalance between envs, latency hidden by occupancy;
-//   k_seq      thread per env, sequential in t: move, guard patrol + guard cone (one cached mask per (waypoint,
-//              heading)), cam_vis[t] OR guards -> visibility map, detection / vault / timeout, rewards,
-//              auto-reset.  HBM-streaming: reads cam_vis + actions, finishes the visibility trajectory in place,
-//              writes reward / done / status.
+//   k_seq      thread per env, sequential in t: move, guard patrol, detection from one word of cam_vis[t] OR the
+//              guards' cached masks (one per (waypoint, heading)) at the Solver's row, vault / timeout, rewards,
+//              auto-reset; records each tick's guard state.  A serial chain, overlapped with k_cam_vis of the next
+//              chunk of ticks (heist_b200.cu launch_fast);
+//   k_finish   warp per (env, tick block): cam_vis[t] OR the guards' masks -> the visibility trajectory, in place.
 // Rays that fall inside a tie band (or outside the cached angle domain) are marched exactly like the reference
 // does, so results are bit-identical to heist_step.cuh's.
 #pragma once
@@ -34,19 +35,6 @@ struct FastCam {
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
     return (size_t)Kc * sizeof(FastCam) + 2 * (((size_t)RW * 4 + 15) & ~(size_t)15) + 32;
-}
-
-// bit (r, c) of a lane-per-row bitmap (all lanes get the answer; r, c warp-uniform)
-template <int RPL, int W>
-__device__ __forceinline__ unsigned fast_bit(const uint32_t (&m)[RPL][W], int r, int c) {
-    uint32_t w = m[0][0];
-    if (W == 2 && (c >> 5)) w = m[0][W - 1];
-    if (RPL == 2) {
-        uint32_t w1 = m[RPL - 1][0];
-        if (W == 2 && (c >> 5)) w1 = m[RPL - 1][W - 1];
-        if (r >> 5) w = w1;
-    }
-    return (__shfl_sync(0xffffffffu, w, r & 31) >> (c & 31)) & 1u;
 }
 
 // OR a 16-bit window row (bit i = column col0 + i) into lane-row words
@@ -266,7 +254,7 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
 // guard's state, its current and next patrol word live in registers, and everything tick t + 1 will read from
 // global memory -- the cam_vis word(s) and the guards' mask rows at the Solver's next row -- is requested while
 // tick t is being decided (until an episode ends, the Solver's path and the patrols do not depend on what is
-// seen, so the next state is known); actions are requested two ticks ahead.  Every thread runs exactly T
+// seen, so the next state is known); actions are requested four ticks ahead.  Every thread runs exactly T
 // iterations (an auto-reset is part of the tick that ended the episode), so the threads of a warp stay in step.
 // ---------------------------------------------------------------------------------------------
 #define SEQ_THREADS 32
