@@ -48,6 +48,9 @@ struct HeistHandle {
     int mode;        // heist_set_mode: HEIST_MODE_*
     size_t camvis_smem, seq_smem, cache_bytes;
     long long launches;   // kernels launched by reset / step / step_many (heist_launch_count)
+    int *n_unc_host;      // pinned copy of d.n_uncached, refreshed (async) after every cache build
+    cudaEvent_t ev_unc;   // ... complete when this event is
+    int all_cached;       // -1 unknown, 0 some envs need the ray-march kernels, 1 none does (their launch is skipped)
     double *heads;      size_t heads_cap;     // k_heads output, grow-only [blocks][N][Kc]
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
@@ -89,6 +92,8 @@ extern "C" int heist_destroy(HeistHandle *h) {
     if (h->grec) cudaFree(h->grec);
     if (h->fin) cudaFree(h->fin);
     if (h->last_t) cudaFree(h->last_t);
+    if (h->n_unc_host) cudaFreeHost(h->n_unc_host);
+    if (h->ev_unc) cudaEventDestroy(h->ev_unc);
     if (h->s_seq) {
         cudaStreamDestroy(h->s_seq); cudaStreamDestroy(h->s_fin); cudaStreamDestroy(h->s_cam2);
         cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_join2);
@@ -142,6 +147,9 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     A(z.guard_path, N * d.Kg * d.L * 2); A(z.guard_head, N * d.Kg * d.L); A(z.guard_speed, N * d.Kg);
     A(z.guard_range, N * d.Kg); A(z.guard_fov, N * d.Kg);
     A(d.env_cached, N); A(d.n_uncached, (size_t)1);
+    if (e == cudaSuccess) e = cudaHostAlloc(&h->n_unc_host, sizeof(int), cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_unc, cudaEventDisableTiming);
+    h->all_cached = -1;
     if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc: %s", cudaGetErrorString(e)); }
     // Visibility cache (heist_cache.cuh): ~25 KB per camera slot.  Optional: when it does not fit, every env
     // stays on the ray-march kernel.
@@ -242,7 +250,10 @@ static cudaError_t build_cache(HeistHandle *h, cudaStream_t s) {
     cudaError_t e = cudaMemsetAsync(h->d.n_uncached, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
     k_build_cache<<<h->N, VC_BUILD_THREADS, 0, s>>>(h->d);
-    return cudaGetLastError();
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    h->all_cached = -1;
+    if ((e = cudaMemcpyAsync(h->n_unc_host, h->d.n_uncached, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
+    return cudaEventRecord(h->ev_unc, s);
 }
 
 static int launch_set_layout(HeistHandle *h, const LayoutDev &lz, const int32_t *budget, uint8_t *valid_out,
@@ -306,7 +317,7 @@ static cudaError_t grow(T **buf, size_t *cap, size_t need) {
 struct FastChunk {
     const int8_t *actions; float *reward; double *reward64; uint8_t *done, *status;
     uint32_t *cam; const double *heads; uint16_t *grec; uint8_t *fin; int32_t *last_t;
-    int Tc, autoreset, do_reset, only_last; const uint8_t *mask;
+    int Tc, autoreset, do_reset, only_last, store_heading; const uint8_t *mask;
 };
 
 static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
@@ -314,7 +325,7 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const int nblk = (c.Tc + FAST_TB - 1) / FAST_TB;
     const unsigned g1 = (unsigned)(((long long)h->N * nblk + FAST_WARPS - 1) / FAST_WARPS);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
-#define GO(RPL, W) k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, c.Tc, nblk, c.heads, c.cam, m)
+#define GO(RPL, W) k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, c.Tc, nblk, c.heads, c.cam, m, c.do_reset)
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
@@ -326,7 +337,7 @@ static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     // envs per warp: about 1024 warps in flight (see k_seq)
     const unsigned g2 = (unsigned)((h->N + SEQ_THREADS - 1) / SEQ_THREADS);
 #define GO(W) k_seq<W><<<g2, SEQ_THREADS, h->seq_smem, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
-                                                              c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask)
+                                                              c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask, c.store_heading)
     if (d.C > 32) GO(2); else GO(1);
 #undef GO
     h->launches += 1;
@@ -380,6 +391,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         if (timing) { for (int a = 0; a < 3; ++a) for (int i = 0; i <= n_chunks; ++i) cudaEventCreate(&te[a][i]); cudaEventRecord(te[0][0], s); }
         k_heads<<<gh, 128, 0, s>>>(d, total, 0, 1, h->heads);
         h->launches += 1;
+        c.store_heading = 0;
         CUDA_TRY(cudaEventRecord(h->ev_fork, s));
         CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_fork, 0));
@@ -441,8 +453,15 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         c.status = status ? status + off : nullptr;
         c.cam = vis_traj ? vis_traj + (size_t)t0 * NRW : h->scratch; c.heads = h->heads;
         c.grec = h->grec; c.fin = h->fin; c.last_t = h->last_t;
-        k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, (autoreset && !do_reset) ? 1 : 0, h->heads);
-        h->launches += 1;
+        const int heads_final = (autoreset && !do_reset) ? 1 : 0;   // k_heads can store the heading the chunk ends on
+        if (nblk > 1) {
+            k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, heads_final, h->heads);
+            h->launches += 1;
+            c.store_heading = !heads_final;
+        } else {   // single ticks: k_cam_vis derives the heading itself, k_seq stores it
+            c.heads = nullptr;
+            c.store_heading = 1;
+        }
         launch_cam_vis(h, c, s);
         launch_seq(h, c, s);
         launch_finish(h, c, s);
@@ -453,6 +472,19 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
 
 static inline bool use_cache(const HeistHandle *h) { return h->mode == HEIST_MODE_DEFAULT && h->d.vc_p != nullptr; }
 
+// Does any env need the ray-march kernels next to the table-driven ones?  Learnt without a sync from the count the
+// cache build copies to pinned memory; until that copy has landed (or while `s` is being captured) the answer is yes.
+static bool march_needed(HeistHandle *h, cudaStream_t s) {
+    if (!use_cache(h)) return true;
+    if (h->all_cached < 0) {
+        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return true; }
+        if (cudaEventQuery(h->ev_unc) != cudaSuccess) { cudaGetLastError(); return true; }
+        h->all_cached = *h->n_unc_host == 0 ? 1 : 0;
+    }
+    return h->all_cached != 1;
+}
+
 extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     if (!h) return fail(-1, "heist_reset: null handle");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -462,6 +494,7 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
     Dev d = h->d;
     d.skip_cached = use_cache(h);
     if (d.skip_cached) { int rc = launch_fast(h, nullptr, 0, 0, nullptr, nullptr, nullptr, nullptr, nullptr, 1, mask, s); if (rc) return rc; }
+    if (!march_needed(h, s)) return 0;
 #define GO(E, B) k_reset<E, B><<<grid, block, h->step_smem, s>>>(d, mask)
     if (exact) { if (big) GO(true, true); else GO(true, false); }
     else { if (big) GO(false, true); else GO(false, false); }
@@ -478,6 +511,7 @@ static int launch_step(HeistHandle *h, const int8_t *actions, int T, int autores
     Dev d = h->d;
     d.skip_cached = use_cache(h);
     if (d.skip_cached) { int rc = launch_fast(h, actions, T, autoreset, reward, reward64, done, status, vis_traj, 0, nullptr, s); if (rc) return rc; }
+    if (!march_needed(h, s)) return 0;
 #define GO(E, B) k_step_many<E, B><<<grid, block, h->step_smem, s>>>(d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
     if (exact) { if (big) GO(true, true); else GO(true, false); }
     else { if (big) GO(false, true); else GO(false, false); }

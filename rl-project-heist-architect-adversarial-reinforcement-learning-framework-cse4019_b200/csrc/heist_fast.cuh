@@ -113,7 +113,8 @@ __device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32
 // (sb >> 1) + (j >> 1).  A gap's mask is kept iff its segment turns out to contain a ray.
 template <int RPL, int W>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 5)
-k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, const uint8_t *__restrict__ mask) {
+k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, const uint8_t *__restrict__ mask,
+          int do_reset) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * FAST_WARPS + warp;
@@ -132,7 +133,11 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         FastCam &Cm = cams[lane];
         const int16_t *ci = D.cam_i + o * 4;
         Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
-        Cm.heading = heads[(size_t)b * D.N * D.Kc + o];
+        if (heads) Cm.heading = heads[(size_t)b * D.N * D.Kc + o];
+        else {   // single tick block: no k_heads launch, the heading of tick 0 is one update (or none) away
+            Cm.heading = D.cam_heading[o];
+            if (fast_adv0(D, env, do_reset)) Cm.heading = py_mod360(__dadd_rn(Cm.heading, Cm.speed));
+        }
         Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
         Cm.dom_lo = D.vc_lo[o];
         Cm.n_points = D.vc_meta[o * 2];
@@ -276,7 +281,7 @@ __global__ void __launch_bounds__(SEQ_THREADS)
 k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
       double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
       const uint32_t *__restrict__ cam_vis, uint16_t *__restrict__ grec, uint8_t *__restrict__ fin,
-      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask) {
+      int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask, int store_heading) {
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int env = blockIdx.x * SEQ_THREADS + tid;
@@ -516,8 +521,8 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
     *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =
         make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
-    for (int k = 0; k < (autoreset ? 0 : n_cams); ++k) {   // headings after the camera updates this launch executed
-        const size_t co = (size_t)env * D.Kc + k;          // (with auto-reset: stored by k_heads)
+    for (int k = 0; k < (store_heading ? n_cams : 0); ++k) {   // headings after the camera updates this launch executed
+        const size_t co = (size_t)env * D.Kc + k;              // (otherwise stored by k_heads)
         double h = D.cam_heading[co];
         const double speed = D.cam_f[co * 2 + 1];
         for (int a = 0; a < n_adv; ++a) h = py_mod360(__dadd_rn(h, speed));
