@@ -159,11 +159,13 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
         bool ok = S.ok != 0;
         const int n_raw = min(S.n_raw, VC_RAW);
         // ---- 2. bitonic sort by start, then merge overlaps ----
-        for (int i = n_raw + tid; i < VC_RAW; i += VC_BUILD_THREADS) { S.key[i] = 2e300; S.end[i] = 2e300; }
+        int n_sort = 64;   // sort only as many slots as there are bands (next power of two)
+        while (n_sort < n_raw) n_sort <<= 1;
+        for (int i = n_raw + tid; i < n_sort; i += VC_BUILD_THREADS) { S.key[i] = 2e300; S.end[i] = 2e300; }
         __syncthreads();
-        for (int size = 2; size <= VC_RAW; size <<= 1) {
+        for (int size = 2; size <= n_sort; size <<= 1) {
             for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = tid; i < VC_RAW / 2; i += VC_BUILD_THREADS) {
+                for (int i = tid; i < n_sort / 2; i += VC_BUILD_THREADS) {
                     const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
                     const bool up = (lo & size) == 0;
                     const double a = S.key[lo], b = S.key[hi];

@@ -535,6 +535,28 @@ def test_cache_coverage_and_fallback_mix():
         assert np.array_equal(out[k].cpu().numpy(), ref[k]), k
     assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
     env.check_errors()
+    # the same handle with layouts the cache covers completely (the ray-march launches are then skipped), and back
+    for lays2, want in ((lays[::4] * 4, N), (lays, N // 4)):
+        env.set_layout_explicit(lays2, budget=np.full(N, 100, np.int32))
+        assert env.cache_stats()[0] == want
+        oenvs = []
+        for w, c, g in lays2:
+            e = ho.OracleEnv(20, 20, max_steps=30, budget=100)
+            e.set_layout(w, c, g)
+            oenvs.append(e)
+        env.reset()
+        ho.reset_all(oenvs)
+        for t in range(3):   # single ticks first: they decide from the asynchronous coverage count
+            rew, done, status = env.step(acts[t])
+            env.reset(mask=done)
+        ref = ho.rollout(oenvs, acts[:3], autoreset=True, want_vis=True)
+        assert np.array_equal(u32(env.visibility_bits), ref["vis_bits"][2])
+        out = env.step_many(acts[3:], autoreset=True, want_vis=True)
+        ref = ho.rollout(oenvs, acts[3:], autoreset=True, want_vis=True)
+        for k in ("done", "status", "reward"):
+            assert np.array_equal(out[k].cpu().numpy(), ref[k]), k
+        assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+    env.check_errors()
     os.environ["HEIST_NO_VIS_CACHE"] = "1"
     try:
         env2 = BatchedHeistEnv(cfg, 8)
