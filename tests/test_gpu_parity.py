@@ -500,6 +500,41 @@ def test_cached_path_launch_shapes_agree(R, N, autoreset):
     env.check_errors()
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_cached_path_vs_ray_march_ragged_shapes(seed):
+    """Soak: ragged grids, odd batch sizes, dense asset maps, nice / generic angles, both auto-reset modes, one call or
+    uneven pieces -- the table-driven path and the ray-march must agree on every output and on the final state."""
+    rng = np.random.default_rng(1000 + seed)
+    R, C = [(20, 20), (32, 32), (64, 64), (9, 40), (50, 11), (33, 33)][seed]
+    N, T = int(rng.choice([1, 31, 257])), int(rng.choice([40, 97]))
+    budget, max_steps = int(rng.choice([8, 15, 22])), int(rng.choice([25, 200]))
+    autoreset, nice = seed % 4 < 2, bool(seed % 2)
+    pieces = [T] if seed % 3 else [T // 3, 1, T - T // 3 - 1]
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C, architect_budget=budget, max_steps=max_steps)
+    env = BatchedHeistEnv(cfg, N)
+    am = synthetic.sample_asset_maps(rng, N, R, C, p_wall=0.04, p_cam=0.02, p_guard=0.01)
+    cp = synthetic.sample_cam_params(rng, N, nice)
+    acts = torch.as_tensor(synthetic.sample_actions(rng, T, N)).cuda()
+    res = []
+    for mode in (env.MODE_DEFAULT, env.MODE_MARCH):
+        env.set_mode(mode)
+        env.set_layout_from_asset_map(am, cp, budget)
+        env.reset()
+        outs, t0 = [], 0
+        for n in pieces:
+            o = env.step_many(acts[t0:t0 + n], autoreset=autoreset, want_vis=True)
+            outs.append({k: v.clone() for k, v in o.items()})
+            t0 += n
+        res.append((outs, [x.clone() for x in (env.env_dyn, env.cam_heading, env.guard_heading, env.guard_idx,
+                                               env.visibility_bits)]))
+    for a, b in zip(res[0][0], res[1][0]):
+        for k in a:
+            assert torch.equal(a[k], b[k]), k
+    for a, b in zip(res[0][1], res[1][1]):
+        assert torch.equal(a, b)
+    env.check_errors()
+
+
 def test_cache_coverage_and_fallback_mix():
     """Assets outside the cache's range (vision_range > 7, fov > 180, more than 4 guards) leave their env to the
     ray-march kernel; both kernels then serve one batch.  HEIST_NO_VIS_CACHE=1 disables the cache altogether."""
