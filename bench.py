@@ -321,7 +321,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default: 100 for config 2, 5 / 3 for configs 3 / 4)")
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
@@ -337,6 +337,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = {2: 100, 3: 5, 4: 3}[args.config] if args.impl == "ours" else 5
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     args.exact_counts = None
     if args.config == 3:
