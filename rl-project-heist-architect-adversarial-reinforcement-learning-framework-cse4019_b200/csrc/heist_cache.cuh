@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
             P[2 * g] = (int32_t)floor((S.end[g] - dom_lo) * fx_scale); P[2 * g + 1] = (int32_t)floor((S.key[g + 1] - dom_lo) * fx_scale);
             MK4[2 * g] = S.gm[g][0]; MK4[2 * g + 1] = S.gm[g][1];
         }
-        for (int i = n_points + tid; i < VC_POINTS; i += VC_BUILD_THREADS) P[i] = 0x7fffffff;   // no ray lies above
+        // padding: above every ray (real points are < 2^29, the first ray is clamped to +-2^29: no overflow in
+        // point - first_ray + round_up, and (2^30 - 2^29) >> sh exceeds the ray count by construction of sh)
+        for (int i = n_points + tid; i < VC_POINTS; i += VC_BUILD_THREADS) P[i] = 0x3fffffff;
         if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = sh; D.vc_lo[o] = dom_lo; }
         // ---- 4. coarse index: points below each 1-degree bucket start ----
         uint16_t *IX = D.vc_idx + o * VC_IDX;

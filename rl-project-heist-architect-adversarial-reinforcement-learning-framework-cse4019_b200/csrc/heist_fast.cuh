@@ -104,13 +104,13 @@ __device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32
         atomicOr(&xvis[r * D.W + (c >> 5)], 1u << (c & 31));
 }
 
-#define CV_PASSES 4   // 32-segment passes whose loads are in flight together
+#define CV_PASSES 2   // 32-gap passes whose loads are in flight together (2 x 32 gaps = 128 segments)
 
 // Union of the camera cones of one env for FAST_TB consecutive ticks -> out[t][env][RW].
-// One pass = 32 consecutive segments of a camera's boundary-point table, starting on an even segment: lane j
-// classifies segment sb + j (ray count below its upper boundary point; the lower one comes from lane j - 1), and
-// -- independently, so that neither load waits for the other -- loads one 16-byte half of the mask of gap
-// (sb >> 1) + (j >> 1).  A gap's mask is kept iff its segment turns out to contain a ray.
+// One pass = 32 consecutive gaps of a camera's table, lane j = gap g0 + j: it loads the gap's two boundary points
+// (one 8-byte load) and, independently, its 32-byte mask; the ray counts below the two points say whether the gap
+// holds a ray (then the mask is OR-ed in) and, with the upper count of lane j - 1, whether the band in front of
+// it does (rare: those rays are marched exactly).
 template <int RPL, int W>
 __global__ void __launch_bounds__(FAST_WARPS * 32, 5)
 k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, const uint8_t *__restrict__ mask,
@@ -173,52 +173,53 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
             const FastCam &Cm = cams[k];
             const int base_fx = Cm.base_fx, sh = Cm.sh, round_up = (1 << sh) - 1;
             const int NR = Cm.num_rays + 1, n_points = Cm.n_points;
-            const int32_t *P = Cm.P;
-            const uint4 *MK4 = reinterpret_cast<const uint4 *>(Cm.MK);   // gap g = uint4 2g, 2g + 1
-            int carry = 0;
-            bool first = Cm.s0 > 0;   // lane 0 of the first pass only supplies the lower count of lane 1
-            uint32_t acc0 = 0, acc1 = 0, acc2 = 0, acc3 = 0;   // even lanes: mask words 0-3, odd lanes: words 4-7
+            const int2 *P2 = reinterpret_cast<const int2 *>(Cm.P);      // gap g = points 2g (its start), 2g + 1 (its end)
+            const uint4 *MK4 = reinterpret_cast<const uint4 *>(Cm.MK);   // ... and uint4 2g, 2g + 1
+            const int n_gaps = n_points >> 1;
+            int carry = 0;             // rays below the end of the previous gap
+            bool first = Cm.s0 > 0;    // the band in front of the first gap looked at lies before the window: no rays
+            uint32_t acc[VC_ROWS / 2];
+#pragma unroll
+            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
             bool more = true;
-            for (int sb = Cm.s0; more; sb += 32 * CV_PASSES) {
-                int pv[CV_PASSES];
-                uint4 mv[CV_PASSES];
+            for (int gb = Cm.s0 >> 1; more; gb += 32 * CV_PASSES) {
+                int2 pv[CV_PASSES];
+                uint4 m0[CV_PASSES], m1[CV_PASSES];
 #pragma unroll
                 for (int u = 0; u < CV_PASSES; ++u) {
-                    const int s = sb + 32 * u + lane;
-                    pv[u] = P[min(s, VC_POINTS - 1)];   // padded with INT_MAX above n_points
-                    // half (lane & 1) of gap (sb + 32u) / 2 + (lane >> 1), i.e. of segment sb + 32u + (lane | 1)
-                    mv[u] = (sb + 32 * u + (lane | 1)) < n_points ? __ldg(MK4 + (sb + 32 * u) + lane) : make_uint4(0, 0, 0, 0);
+                    const int g = gb + 32 * u + lane;
+                    pv[u] = P2[min(g, VC_POINTS / 2 - 1)];   // padded above n_points with a point no ray reaches
+                    m0[u] = m1[u] = make_uint4(0, 0, 0, 0);
+                    if (g < n_gaps) { m0[u] = __ldg(MK4 + 2 * g); m1[u] = __ldg(MK4 + 2 * g + 1); }
                 }
 #pragma unroll
                 for (int u = 0; u < CV_PASSES; ++u) {
                     if (!more) break;
-                    const int n_s = fast_nrays(pv[u], base_fx, round_up, sh, NR);
-                    int n_prev = __shfl_up_sync(0xffffffffu, n_s, 1);
-                    if (lane == 0) n_prev = first ? n_s : carry;
+                    const int n_lo = fast_nrays(pv[u].x, base_fx, round_up, sh, NR), n_hi = fast_nrays(pv[u].y, base_fx, round_up, sh, NR);
+                    int prev_hi = __shfl_up_sync(0xffffffffu, n_hi, 1);
+                    if (lane == 0) prev_hi = first ? n_lo : carry;
                     first = false;
-                    carry = __shfl_sync(0xffffffffu, n_s, 31);
-                    const bool hit = n_s > n_prev;
-                    const unsigned hits = __ballot_sync(0xffffffffu, hit);
-                    if ((hits >> (lane | 1)) & 1u) { acc0 |= mv[u].x; acc1 |= mv[u].y; acc2 |= mv[u].z; acc3 |= mv[u].w; }
-                    unsigned bh = hits & 0x55555555u;   // bands that hold a ray (rare)
+                    carry = __shfl_sync(0xffffffffu, n_hi, 31);
+                    if (n_hi > n_lo) {   // the gap holds a ray: every ray inside marks the same tiles
+                        acc[0] |= m0[u].x; acc[1] |= m0[u].y; acc[2] |= m0[u].z; acc[3] |= m0[u].w;
+                        acc[4] |= m1[u].x; acc[5] |= m1[u].y; acc[6] |= m1[u].z; acc[7] |= m1[u].w;
+                    }
+                    unsigned bh = __ballot_sync(0xffffffffu, n_lo > prev_hi);   // bands that hold a ray (rare)
                     while (bh) {
                         const int src = __ffs(bh) - 1;
                         bh &= bh - 1;
-                        const int r0 = __shfl_sync(0xffffffffu, n_prev, src), r1 = __shfl_sync(0xffffffffu, n_s, src);
+                        const int r0 = __shfl_sync(0xffffffffu, prev_hi, src), r1 = __shfl_sync(0xffffffffu, n_lo, src);
                         for (int ri = r0; ri < r1; ++ri) cam_exact_ray(vc_geo(D), wall_s, xvis, &Cm, ri, lane);
                         exact_used = true;
                     }
                     if (carry >= NR) more = false;  // warp-uniform
                 }
             }
-            // words 0-3 from the even lanes, 4-7 from the odd lanes
-            const uint32_t e0 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc0), e1 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc1);
-            const uint32_t e2 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc2), e3 = __reduce_or_sync(0xffffffffu, (lane & 1) ? 0u : acc3);
-            const uint32_t o0 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc0 : 0u), o1 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc1 : 0u);
-            const uint32_t o2 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc2 : 0u), o3 = __reduce_or_sync(0xffffffffu, (lane & 1) ? acc3 : 0u);
+#pragma unroll
+            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(0xffffffffu, acc[i]);
             if (lane == 0) {
-                reinterpret_cast<uint4 *>(stage)[0] = make_uint4(e0, e1, e2, e3);
-                reinterpret_cast<uint4 *>(stage)[1] = make_uint4(o0, o1, o2, o3);
+                reinterpret_cast<uint4 *>(stage)[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<uint4 *>(stage)[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
             }
             __syncwarp();
             const uint16_t *rows = reinterpret_cast<const uint16_t *>(stage);
