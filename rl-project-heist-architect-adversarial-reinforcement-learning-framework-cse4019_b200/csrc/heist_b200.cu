@@ -377,10 +377,10 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
     // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_seq of chunk c.
     const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
     const bool pipelined = !do_reset && autoreset && total > FAST_PIPE_TC && n_chunks <= FAST_PIPE_MAX && h->s_seq &&
-                           (vis_traj || (size_t)total * NRW * 4 <= ((size_t)1 << 30));
+                           (vis_traj || (size_t)total * NRW * 4 <= ((size_t)1 << 30)) &&
+                           (size_t)total * N * d.Kc * 8 <= ((size_t)4 << 30);
     if (pipelined) {
-        const int nblk = (total + FAST_TB - 1) / FAST_TB;
-        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)total * N * d.Kc));
         CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)total * N * d.Kg));
         CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)total * N));
         CUDA_TRY(grow(&h->last_t, &h->last_cap, (size_t)n_chunks * N));
@@ -405,7 +405,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             c.Tc = std::min(FAST_PIPE_TC, total - t0);
             c.actions = actions + off; c.reward = reward ? reward + off : nullptr; c.reward64 = reward64 ? reward64 + off : nullptr;
             c.done = done ? done + off : nullptr; c.status = status ? status + off : nullptr;
-            c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc;
+            c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)t0 * N * d.Kc;
             c.grec = h->grec + off * d.Kg; c.fin = h->fin + off; c.last_t = h->last_t + (size_t)i * N;
             launch_cam_vis(h, c, sc);
             if (timing) cudaEventRecord(te[0][i + 1], sc);
@@ -444,7 +444,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         const size_t off = (size_t)t0 * N;
         c.Tc = std::min(cap, total - t0);
         const int nblk = (c.Tc + FAST_TB - 1) / FAST_TB;
-        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)c.Tc * N * d.Kc));
         CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)c.Tc * N * d.Kg));
         CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)c.Tc * N));
         if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)c.Tc * NRW));

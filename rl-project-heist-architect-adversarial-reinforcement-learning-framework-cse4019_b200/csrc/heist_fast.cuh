@@ -30,11 +30,11 @@ struct FastCam {
     double heading, speed, fov, fx_scale, dom_lo;
     const int32_t *P;       // boundary points (fixed point, heist_cache.cuh)
     const uint16_t *MK;     // gap masks
-    int row, col, range, num_rays, n_points, s0, sh, base_fx;
+    int row, col, range, num_rays, n_points, sh;
 };
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
-    return (size_t)Kc * sizeof(FastCam) + 2 * (((size_t)RW * 4 + 15) & ~(size_t)15) + 32;
+    return (size_t)Kc * sizeof(FastCam) + 2 * (((size_t)RW * 4 + 15) & ~(size_t)15) + 32 + (size_t)FAST_TB * Kc * 16;
 }
 
 // OR a 16-bit window row (bit i = column col0 + i) into lane-row words
@@ -53,7 +53,7 @@ __device__ __forceinline__ int fast_adv0(const Dev &D, int env, int do_reset) {
     return (D.env_d[(size_t)env * 8 + 4] & F_DONE) ? 0 : 1;
 }
 
-// heads[b][env][k] = heading of camera k at tick b * FAST_TB of this launch.  write_final: with auto-reset every
+// heads[t][env][k] = heading of camera k at tick t of this launch.  write_final: with auto-reset every
 // tick of the launch updates the cameras (environment.py:251-252), so the heading the launch ends on is the one
 // of its last tick and is stored here; otherwise k_seq stores it (an env may stop stepping early).
 __global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int write_final, double *__restrict__ heads) {
@@ -67,7 +67,7 @@ __global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int w
     for (int a = 0; a < adv0; ++a) h = py_mod360(__dadd_rn(h, speed));
     double last = h;
     for (int t = 0; t < T; ++t) {
-        if (t % FAST_TB == 0) heads[(size_t)(t / FAST_TB) * D.N * D.Kc + i] = h;
+        heads[(size_t)t * D.N * D.Kc + i] = h;
         last = h;
         h = py_mod360(__dadd_rn(h, speed));
     }
@@ -83,10 +83,11 @@ __device__ __forceinline__ int fast_nrays(int p, int base_fx, int round_up, int 
 // outside the cached angle domain -> march it exactly like the reference does (security.py:69-99), the whole warp
 // on one ray: lane j evaluates sample j + 1 (at most 14 samples), a ballot finds the first blocked one.
 // `wall` is the env's wall bitmap in shared memory.
-__device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32_t *xvis, const FastCam *cam, int ri, int lane) {
+__device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32_t *xvis, const FastCam *cam, double heading,
+                                           int ri, int lane) {
     const int row = cam->row, col = cam->col, nsamp = 2 * cam->range;
     const double fov = cam->fov;
-    const double angle_deg = __dadd_rn(__dsub_rn(cam->heading, __ddiv_rn(fov, 2.0)),
+    const double angle_deg = __dadd_rn(__dsub_rn(heading, __ddiv_rn(fov, 2.0)),
                                        __ddiv_rn(__dmul_rn(fov, (double)ri), (double)cam->num_rays));
     double dx, dy;
     ray_dir(angle_deg, D.deg2rad, dx, dy);
@@ -125,16 +126,18 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
     FastCam *cams = reinterpret_cast<FastCam *>(sp);        sp += (size_t)D.Kc * sizeof(FastCam);
     uint32_t *xvis = reinterpret_cast<uint32_t *>(sp);      sp += ((size_t)D.RW * 4 + 15) & ~(size_t)15;
     uint32_t *wall_s = reinterpret_cast<uint32_t *>(sp);    sp += ((size_t)D.RW * 4 + 15) & ~(size_t)15;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(sp);
+    uint32_t *stage = reinterpret_cast<uint32_t *>(sp);      sp += 32;
+    double *pre_head = reinterpret_cast<double *>(sp);       sp += (size_t)FAST_TB * D.Kc * 8;   // [tick][camera]
+    int *pre_s0 = reinterpret_cast<int *>(sp);               sp += (size_t)FAST_TB * D.Kc * 4;
+    int *pre_fx = reinterpret_cast<int *>(sp);
     const int n_cams = D.env_s[(size_t)env * 4];
-    const uint16_t *IX = nullptr;
     if (lane < n_cams) {
         const size_t o = (size_t)env * D.Kc + lane;
         FastCam &Cm = cams[lane];
         const int16_t *ci = D.cam_i + o * 4;
         Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
-        if (heads) Cm.heading = heads[(size_t)b * D.N * D.Kc + o];
-        else {   // single tick block: no k_heads launch, the heading of tick 0 is one update (or none) away
+        Cm.heading = 0.0;
+        if (!heads) {   // single tick block: no k_heads launch, the heading of tick 0 is one update (or none) away
             Cm.heading = D.cam_heading[o];
             if (fast_adv0(D, env, do_reset)) Cm.heading = py_mod360(__dadd_rn(Cm.heading, Cm.speed));
         }
@@ -145,24 +148,30 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
         Cm.P = D.vc_p + o * VC_POINTS;
         Cm.MK = D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS;
-        IX = D.vc_idx + o * VC_IDX;
     }
     for (int i = lane; i < D.RW; i += 32) { xvis[i] = 0; wall_s[i] = D.wall[(size_t)env * D.RW + i]; }
-    const int t_end = min(T, (b + 1) * FAST_TB);
-    for (int t = b * FAST_TB; t < t_end; ++t) {
-        // every camera's window start from its coarse index: one load level for all cameras of the env.
-        // Segments below IX[q] hold no ray of this tick; start one earlier (its upper point gives lane 1 its
-        // lower ray count) and on an even segment.
-        if (lane < n_cams) {
-            FastCam &Cm = cams[lane];
-            if (t > b * FAST_TB) Cm.heading = py_mod360(__dadd_rn(Cm.heading, Cm.speed));
-            const double base = Cm.heading - Cm.fov * 0.5;
+    const int t_begin = b * FAST_TB, t_end = min(T, (b + 1) * FAST_TB);
+    __syncwarp();
+    // Per (tick, camera) of the block, in parallel lanes: the heading, the window start from the coarse index
+    // (segments below IX[q] hold no ray of that tick; start one earlier and on an even segment) and the first ray
+    // in fixed point (far outside the domain every ray is in a sentinel band anyway).
+    for (int idx = lane; idx < (heads ? (t_end - t_begin) * n_cams : n_cams); idx += 32) {
+        const int tt0 = heads ? idx / n_cams : 0, k = idx - tt0 * n_cams;
+        const FastCam &Cm = cams[k];
+        const uint16_t *IX = D.vc_idx + ((size_t)env * D.Kc + k) * VC_IDX;
+        double h = heads ? heads[((size_t)(t_begin + tt0) * D.N + env) * D.Kc + k] : Cm.heading;
+        for (int tt = tt0; tt < (heads ? tt0 + 1 : t_end - t_begin); ++tt) {
+            if (!heads && tt > 0) h = py_mod360(__dadd_rn(h, Cm.speed));
+            const double base = h - Cm.fov * 0.5;
             const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
-            Cm.s0 = max(0, (int)IX[q] - 1) & ~1;
-            // the first ray in fixed point; far outside the domain every ray is in a sentinel band anyway
-            Cm.base_fx = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
+            pre_head[tt * D.Kc + k] = h;
+            pre_s0[tt * D.Kc + k] = max(0, (int)IX[q] - 1) & ~1;
+            pre_fx[tt * D.Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
         }
-        __syncwarp();
+    }
+    __syncwarp();
+    for (int t = t_begin; t < t_end; ++t) {
+        const int pi = (t - t_begin) * D.Kc;
         uint32_t vis[RPL][W];
 #pragma unroll
         for (int a = 0; a < RPL; ++a)
@@ -171,18 +180,19 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         bool exact_used = false;
         for (int k = 0; k < n_cams; ++k) {
             const FastCam &Cm = cams[k];
-            const int base_fx = Cm.base_fx, sh = Cm.sh, round_up = (1 << sh) - 1;
+            const int base_fx = pre_fx[pi + k], s0 = pre_s0[pi + k], sh = Cm.sh, round_up = (1 << sh) - 1;
+            const double heading = pre_head[pi + k];
             const int NR = Cm.num_rays + 1, n_points = Cm.n_points;
             const int2 *P2 = reinterpret_cast<const int2 *>(Cm.P);      // gap g = points 2g (its start), 2g + 1 (its end)
             const uint4 *MK4 = reinterpret_cast<const uint4 *>(Cm.MK);   // ... and uint4 2g, 2g + 1
             const int n_gaps = n_points >> 1;
             int carry = 0;             // rays below the end of the previous gap
-            bool first = Cm.s0 > 0;    // the band in front of the first gap looked at lies before the window: no rays
+            bool first = s0 > 0;       // the band in front of the first gap looked at lies before the window: no rays
             uint32_t acc[VC_ROWS / 2];
 #pragma unroll
             for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
             bool more = true;
-            for (int gb = Cm.s0 >> 1; more; gb += 32 * CV_PASSES) {
+            for (int gb = s0 >> 1; more; gb += 32 * CV_PASSES) {
                 int2 pv[CV_PASSES];
                 uint4 m0[CV_PASSES], m1[CV_PASSES];
 #pragma unroll
@@ -209,7 +219,7 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
                         const int src = __ffs(bh) - 1;
                         bh &= bh - 1;
                         const int r0 = __shfl_sync(0xffffffffu, prev_hi, src), r1 = __shfl_sync(0xffffffffu, n_lo, src);
-                        for (int ri = r0; ri < r1; ++ri) cam_exact_ray(vc_geo(D), wall_s, xvis, &Cm, ri, lane);
+                        for (int ri = r0; ri < r1; ++ri) cam_exact_ray(vc_geo(D), wall_s, xvis, &Cm, heading, ri, lane);
                         exact_used = true;
                     }
                     if (carry >= NR) more = false;  // warp-uniform
