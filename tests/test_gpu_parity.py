@@ -535,6 +535,36 @@ def test_cached_path_vs_ray_march_ragged_shapes(seed):
     env.check_errors()
 
 
+def test_pipelined_step_many_is_graph_capturable():
+    """The pipelined launch forks onto internal streams and joins back: once its scratch buffers exist it can be
+    captured into a CUDA graph on the caller's stream and replayed."""
+    R, N, T = 20, 1024, 64
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=R)
+    env = BatchedHeistEnv(cfg, N)
+    am, cp = synthetic.make_valid_workload(env, 1, 15)
+    acts = torch.as_tensor(synthetic.sample_actions(np.random.default_rng(2), T, N)).cuda()
+    out = {"reward": torch.empty((T, N), device="cuda"), "done": torch.empty((T, N), dtype=torch.uint8, device="cuda"),
+           "status": torch.empty((T, N), dtype=torch.uint8, device="cuda"),
+           "vis_bits": torch.empty((T, N, R, 1), dtype=torch.int32, device="cuda")}
+    env.reset()
+    ref = {k: v.clone() for k, v in env.step_many(acts, autoreset=True, out=out).items()}   # also sizes the buffers
+    env.set_layout_from_asset_map(am, cp, 15)
+    env.reset()
+    g, s = torch.cuda.CUDAGraph(), torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            env.step_many(acts, autoreset=True, out=out)
+    torch.cuda.synchronize()
+    env.set_layout_from_asset_map(am, cp, 15)
+    env.reset()
+    for v in out.values():
+        v.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    for k in ref:
+        assert torch.equal(out[k], ref[k]), k
+
+
 def test_cache_coverage_and_fallback_mix():
     """Assets outside the cache's range (vision_range > 7, fov > 180, more than 4 guards) leave their env to the
     ray-march kernel; both kernels then serve one batch.  HEIST_NO_VIS_CACHE=1 disables the cache altogether."""
