@@ -385,15 +385,16 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         fin[env] = 1; SEQ_RECORD((size_t)env); last = 0;
         T = 0;
     }
-    // actions: a small register queue, requested SEQ_AQ ticks ahead (they stream from HBM: one new sector per tick)
-    constexpr int SEQ_AQ = 4;
-    int a_cur = 0, a_q[SEQ_AQ];
-#pragma unroll
-    for (int i = 0; i < SEQ_AQ; ++i) a_q[i] = 0;
+    // actions: four registers used round-robin (slot t & 3 holds tick t and is refilled for tick t + 4 as soon as
+    // it has been read: no register is read in the iteration that follows its load -- they stream from HBM, one new
+    // sector per tick, and a load takes longer than a tick)
+    int a_cur = 0, a_q0 = 0, a_q1 = 0, a_q2 = 0, a_q3 = 0;
     if (T > 0) {
         a_cur = actions[env];
-#pragma unroll
-        for (int i = 0; i < SEQ_AQ; ++i) if (i + 1 < T) a_q[i] = actions[(size_t)(i + 1) * N + env];
+        if (1 < T) a_q1 = actions[(size_t)1 * N + env];
+        if (2 < T) a_q2 = actions[(size_t)2 * N + env];
+        if (3 < T) a_q3 = actions[(size_t)3 * N + env];
+        if (4 < T) a_q0 = actions[(size_t)4 * N + env];
     }
     int pre_row = -1;
     uint32_t pre[W];
@@ -493,10 +494,16 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         fin[o] = rebuilt ? 1 : 0;
         if (rebuilt) { last = t; SEQ_RECORD(o); }
         // requests for tick t + 1
-        a_cur = a_q[0];
-#pragma unroll
-        for (int i = 0; i + 1 < SEQ_AQ; ++i) a_q[i] = a_q[i + 1];
-        a_q[SEQ_AQ - 1] = (t + 1 + SEQ_AQ < T) ? actions[o + (size_t)(1 + SEQ_AQ) * N] : 0;
+        {   // a_cur <- tick t + 1 (slot (t + 1) & 3), then that slot <- tick t + 5
+            const bool refill = t + 5 < T;
+            const int8_t *nxt = actions + o + (size_t)5 * N;
+            switch ((t + 1) & 3) {   // warp-uniform
+                case 0: a_cur = a_q0; if (refill) a_q0 = *nxt; break;
+                case 1: a_cur = a_q1; if (refill) a_q1 = *nxt; break;
+                case 2: a_cur = a_q2; if (refill) a_q2 = *nxt; break;
+                default: a_cur = a_q3; if (refill) a_q3 = *nxt; break;
+            }
+        }
         pre_row = -1;
         if (t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state
             const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
