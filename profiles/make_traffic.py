@@ -37,7 +37,7 @@ def main():
         "kernels_per_step": len(step),
         "serialized_us": round(tot_t / 1e3, 1),
         "share": {k: round(v, 3) for k, v in share.items()},
-        "source": os.path.basename(path) + " (ncu, kernels serialised and cold-cache: use shares and counters, not the absolute time)",
+        "source": os.path.basename(path) + " (ncu launch list, kernels serialised: use shares and counters, not the absolute time)",
     }
     json.dump(data, open(out_path, "w"), indent=1)
     print(json.dumps(data[key], indent=1))
