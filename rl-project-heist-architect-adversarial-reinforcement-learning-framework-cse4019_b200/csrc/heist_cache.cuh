@@ -15,7 +15,11 @@
 //      stays at least mu away from every tie, so the reference's rounding -- whatever the last bit of the
 //      platform's cos/sin -- is constant there;
 //   3. marches one representative ray per gap through the reference's own arithmetic (ray_exact semantics, walls
-//      included) and stores the marked tiles as a (2*range+1)^2 window bitmap: 16 rows of 16 bits.
+//      included) and stores the marked tiles as a (2*range+1)^2 window bitmap: 16 rows of 16 bits;
+//   4. drops every band that comes from a single tie crossing and separates two gaps with equal bitmaps (a ray
+//      inside it takes one of the two neighbouring tile sequences, so it marks those same tiles);
+//   5. stores the boundary points as fixed-point ray pitches (the per-tick "rays below this point" becomes an
+//      integer subtract and shift) and a 1-degree coarse index over them.
 // At run time (heist_fast.cuh) a tick of a camera is: find the segments its fov window covers, OR the masks of
 // the gaps that contain at least one ray, and run the few rays that fall inside a band (structurally: rays on
 // exact multiples of 30/45/90 degrees) through the exact ray-march.  A guard's cone depends only on its waypoint
