@@ -301,11 +301,11 @@ extern "C" int heist_set_layout_explicit(HeistHandle *h, const HeistLayoutArrays
 
 // Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_dyn
 // per chunk of ticks (heist_fast.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
+// Grow-only launch scratch.  (cudaFree synchronises the device, so nothing in flight still uses the old buffer; a
+// call that has to grow cannot be captured into a CUDA graph -- run it once un-captured first.)
 template <typename T>
 static cudaError_t grow(T **buf, size_t *cap, size_t need) {
     if (need <= *cap) return cudaSuccess;
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    (void)st;
     if (*buf) { cudaError_t e = cudaFree(*buf); *buf = nullptr; *cap = 0; if (e != cudaSuccess) return e; }
     cudaError_t e = cudaMalloc(buf, need * sizeof(T));
     if (e == cudaSuccess) *cap = need;
