@@ -237,11 +237,10 @@ def run_ours(args, rank, world, local_rank):
     value = total_steps / (ms_value * 1e-3)
 
     # (2) end to end through the public API with HOST buffers: H2D actions, rollout, D2H reward + done
-    def e2e_body(i):
-        a = acts_host[i].to(dev, non_blocking=True)
-        o = env.step_many(a, autoreset=True, out=out)
-        rew_host.copy_(o["reward"], non_blocking=True)
-        done_host.copy_(o["done"], non_blocking=True)
+    host_out = {"reward": rew_host, "done": done_host}
+
+    def e2e_body(i):   # pinned host actions in, pinned host reward + done out (the copies ride along the launch)
+        env.step_many_host(acts_host[i], host_out, autoreset=True, vis_out=out["vis_bits"])
 
     ms_e2e = timed_loop(e2e_body)
     e2e_value = total_steps / (ms_e2e * 1e-3)

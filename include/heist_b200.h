@@ -150,6 +150,16 @@ int heist_step(HeistHandle *h, const int8_t *actions, float *reward, double *rew
 int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, uint8_t *done,
                     uint8_t *status, uint32_t *vis_traj, void *stream);
 
+/*
+ * heist_step_many for a driver whose rollout buffers live on the host (pinned memory): actions_host [T][N] int8
+ * in, reward_host [T][N] float32 / done_host / status_host [T][N] uint8 out (any output may be NULL); vis_traj stays
+ * a device pointer (may be NULL).  With auto-reset and T > 32 the copies are issued chunk by chunk on internal
+ * streams next to the kernels of the pipelined launch and joined onto `stream`; otherwise they bracket the launch
+ * on `stream`.  The host buffers are valid once `stream` has passed the call.
+ */
+int heist_step_many_host(HeistHandle *h, const int8_t *actions_host, int T, int autoreset, float *reward_host,
+                         uint8_t *done_host, uint8_t *status_host, uint32_t *vis_traj, void *stream);
+
 /* HeistEnvironment.get_state_tensor (environment.py:347-374): state [N][3][R][C] float32. */
 int heist_observe(HeistHandle *h, float *state, void *stream);
 

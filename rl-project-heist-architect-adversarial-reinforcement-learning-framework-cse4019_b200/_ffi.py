@@ -39,6 +39,7 @@ EXPORTS = {
     "heist_reset": (C.c_int, [c_vp, c_vp, c_vp]),
     "heist_step": (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "heist_step_many": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "heist_step_many_host": (C.c_int, [c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "heist_observe": (C.c_int, [c_vp, c_vp, c_vp]),
     "heist_observation_vectors": (C.c_int, [c_vp, c_vp, c_vp]),
     "heist_step_observe": (C.c_int, [c_vp, c_vp, C.c_int, c_vp, c_vp, c_vp, c_vp, c_vp]),

@@ -291,6 +291,29 @@ class BatchedHeistEnv:
         self._keep_a = a
         return out
 
+    def step_many_host(self, actions_host, out_host=None, autoreset=True, vis_out=None):
+        """step_many for rollout buffers that live on the HOST: actions_host [T,N] int8 (pinned), outputs into pinned
+        host tensors dict(reward f32, done u8, status u8) (allocated if not given); vis_out, if given, is a DEVICE
+        tensor [T,N,R,W] int32.  The copies ride along the pipelined launch (include/heist_b200.h); the host tensors
+        are valid after the current stream has been synchronised."""
+        a = actions_host if isinstance(actions_host, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(actions_host))
+        assert a.dtype == torch.int8 and a.device.type == "cpu" and a.is_contiguous()
+        if not a.is_pinned():
+            a = a.pin_memory()
+        T, N = a.shape
+        assert N == self.num_envs
+        if out_host is None:
+            out_host = {"reward": torch.empty((T, N), dtype=torch.float32).pin_memory(),
+                        "done": torch.empty((T, N), dtype=torch.uint8).pin_memory(),
+                        "status": torch.empty((T, N), dtype=torch.uint8).pin_memory()}
+        for v in out_host.values():
+            assert v.device.type == "cpu" and v.is_pinned() and v.is_contiguous()
+        _ffi.check(self._lib.heist_step_many_host(self._h, _ptr(a), T, int(autoreset), _ptr(out_host.get("reward")),
+                                                  _ptr(out_host.get("done")), _ptr(out_host.get("status")), _ptr(vis_out),
+                                                  self._stream()), "heist_step_many_host")
+        self._keep_h = (a, out_host, vis_out)
+        return out_host
+
     def step_observe(self, actions, autoreset=True, state_out=None):
         """One tick + the dense state for the next policy forward (training.py:523-529 for the batch).
         -> reward [N] f32, done [N] bool, status [N] u8, state [N,3,R,C] f32 (after the auto-reset, if any)."""

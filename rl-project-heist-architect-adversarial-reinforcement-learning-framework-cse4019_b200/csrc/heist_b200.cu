@@ -58,6 +58,10 @@ struct HeistHandle {
     int32_t *last_t;    size_t last_cap;      // [chunks][N] last rebuilt tick of each chunk
     cudaStream_t s_seq, s_fin, s_cam2;        // side streams of the pipelined launch
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_cam[64], ev_seq[64];
+    // heist_step_many_host: device staging of the host buffers, copy streams of the pipelined launch
+    int8_t *st_act;  float *st_rew;  uint8_t *st_done, *st_status;  size_t st_cap;
+    cudaStream_t s_h2d, s_d2h;
+    cudaEvent_t ev_h2d[64], ev_join3;
     void *allocs[96];
     int n_allocs;
 };
@@ -93,9 +97,12 @@ extern "C" int heist_destroy(HeistHandle *h) {
     if (h->fin) cudaFree(h->fin);
     if (h->last_t) cudaFree(h->last_t);
     if (h->n_unc_host) cudaFreeHost(h->n_unc_host);
+    if (h->st_act) { cudaFree(h->st_act); cudaFree(h->st_rew); cudaFree(h->st_done); cudaFree(h->st_status); }
     if (h->ev_unc) cudaEventDestroy(h->ev_unc);
     if (h->s_seq) {
         cudaStreamDestroy(h->s_seq); cudaStreamDestroy(h->s_fin); cudaStreamDestroy(h->s_cam2);
+        cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); cudaEventDestroy(h->ev_join3);
+        for (int i = 0; i < 64; ++i) cudaEventDestroy(h->ev_h2d[i]);
         cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_join2);
         for (int i = 0; i < 64; ++i) { cudaEventDestroy(h->ev_cam[i]); cudaEventDestroy(h->ev_seq[i]); }
     }
@@ -210,6 +217,10 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         }
         CUDA_TRY(cudaStreamCreateWithFlags(&h->s_fin, cudaStreamNonBlocking));
         CUDA_TRY(cudaStreamCreateWithFlags(&h->s_cam2, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
+        for (int i = 0; i < 64; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
@@ -358,14 +369,26 @@ static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     h->launches += (!c.only_last && !c.autoreset) ? 2 : 1;
 }
 
+// Host buffers of heist_step_many_host (pinned): copied chunk by chunk next to the kernels of the pipelined launch.
+struct HostIO {
+    const int8_t *actions; float *reward; uint8_t *done, *status;
+};
+
 #define FAST_PIPE_TC 32        // ticks per pipelined chunk (a multiple of FAST_TB)
 #define FAST_PIPE_MAX 64       // chunks (events) per launch
 
 // Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_seq ->
 // k_finish (heist_fast.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
+static bool fast_pipelined(const HeistHandle *h, int total, int autoreset, int do_reset, const uint32_t *vis_traj) {
+    const size_t N = h->N, NRW = N * h->d.RW;
+    const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
+    return !do_reset && autoreset && total > FAST_PIPE_TC && n_chunks <= FAST_PIPE_MAX && h->s_seq &&
+           (vis_traj || (size_t)total * NRW * 4 <= ((size_t)1 << 30)) && (size_t)total * N * h->d.Kc * 8 <= ((size_t)4 << 30);
+}
+
 static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
                        uint8_t *done, uint8_t *status, uint32_t *vis_traj, int do_reset, const uint8_t *mask,
-                       cudaStream_t s) {
+                       cudaStream_t s, const HostIO *io = nullptr) {
     const Dev &d = h->d;
     const size_t N = h->N, NRW = N * d.RW;
     const int total = do_reset ? 1 : T;
@@ -376,9 +399,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
     // Pipelined: with auto-reset no env is ever left done at a chunk boundary, so the camera headings of the whole
     // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_seq of chunk c.
     const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
-    const bool pipelined = !do_reset && autoreset && total > FAST_PIPE_TC && n_chunks <= FAST_PIPE_MAX && h->s_seq &&
-                           (vis_traj || (size_t)total * NRW * 4 <= ((size_t)1 << 30)) &&
-                           (size_t)total * N * d.Kc * 8 <= ((size_t)4 << 30);
+    const bool pipelined = fast_pipelined(h, total, autoreset, do_reset, vis_traj);
     if (pipelined) {
         CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)total * N * d.Kc));
         CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)total * N * d.Kg));
@@ -396,6 +417,10 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_cam2, h->ev_fork, 0));
+        if (io) {
+            CUDA_TRY(cudaStreamWaitEvent(h->s_h2d, h->ev_fork, 0));
+            CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_fork, 0));
+        }
         for (int i = 0; i < n_chunks; ++i) {
             // camera chunks are independent of each other: alternate two streams so that the tail of one chunk
             // overlaps the head of the next
@@ -411,9 +436,20 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             if (timing) cudaEventRecord(te[0][i + 1], sc);
             CUDA_TRY(cudaEventRecord(h->ev_cam[i], sc));
             CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_cam[i], 0));
+            if (io) {   // this chunk's actions: host -> device next to the camera kernel
+                CUDA_TRY(cudaMemcpyAsync((void *)c.actions, io->actions + off, (size_t)c.Tc * N, cudaMemcpyHostToDevice, h->s_h2d));
+                CUDA_TRY(cudaEventRecord(h->ev_h2d[i], h->s_h2d));
+                CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_h2d[i], 0));
+            }
             launch_seq(h, c, h->s_seq);
             if (timing) cudaEventRecord(te[1][i + 1], h->s_seq);
             CUDA_TRY(cudaEventRecord(h->ev_seq[i], h->s_seq));
+            if (io) {   // ... and its results: device -> host while the next chunk is walked
+                CUDA_TRY(cudaStreamWaitEvent(h->s_d2h, h->ev_seq[i], 0));
+                if (io->reward) CUDA_TRY(cudaMemcpyAsync(io->reward + off, c.reward, (size_t)c.Tc * N * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+                if (io->done) CUDA_TRY(cudaMemcpyAsync(io->done + off, c.done, (size_t)c.Tc * N, cudaMemcpyDeviceToHost, h->s_d2h));
+                if (io->status) CUDA_TRY(cudaMemcpyAsync(io->status + off, c.status, (size_t)c.Tc * N, cudaMemcpyDeviceToHost, h->s_d2h));
+            }
             CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_seq[i], 0));
             launch_finish(h, c, h->s_fin);
             if (timing) cudaEventRecord(te[2][i + 1], h->s_fin);
@@ -422,6 +458,10 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
         CUDA_TRY(cudaEventRecord(h->ev_join2, h->s_cam2));
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join2, 0));
+        if (io) {   // (s_h2d's copies were consumed by s_seq, which s_fin -- joined above -- waited for)
+            CUDA_TRY(cudaEventRecord(h->ev_join3, h->s_d2h));
+            CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join3, 0));
+        }
         CUDA_TRY(cudaGetLastError());
         if (timing) {
             cudaDeviceSynchronize();
@@ -568,6 +608,33 @@ extern "C" int heist_step_many(HeistHandle *h, const int8_t *actions, int T, int
         h->launches += 1;
         CUDA_TRY(cudaGetLastError());
     }
+    return 0;
+}
+
+extern "C" int heist_step_many_host(HeistHandle *h, const int8_t *actions_host, int T, int autoreset, float *reward_host,
+                                    uint8_t *done_host, uint8_t *status_host, uint32_t *vis_traj, void *stream) {
+    if (!h || !actions_host) return fail(-1, "heist_step_many_host: null argument");
+    if (T < 0) return fail(-9, "heist_step_many_host: negative T");
+    if (T == 0) return 0;
+    CUDA_TRY(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t n = (size_t)T * h->N;
+    if (n > h->st_cap) {
+        if (h->st_act) { cudaFree(h->st_act); cudaFree(h->st_rew); cudaFree(h->st_done); cudaFree(h->st_status); h->st_act = nullptr; h->st_cap = 0; }
+        CUDA_TRY(cudaMalloc(&h->st_act, n)); CUDA_TRY(cudaMalloc(&h->st_rew, n * 4));
+        CUDA_TRY(cudaMalloc(&h->st_done, n)); CUDA_TRY(cudaMalloc(&h->st_status, n));
+        h->st_cap = n;
+    }
+    // Copies ride along the pipelined launch when it serves every env; otherwise they bracket the call.
+    if (use_cache(h) && !march_needed(h, s) && fast_pipelined(h, T, autoreset, 0, vis_traj)) {
+        HostIO io = {actions_host, reward_host, done_host, status_host};
+        return launch_fast(h, h->st_act, T, autoreset, h->st_rew, nullptr, h->st_done, h->st_status, vis_traj, 0, nullptr, s, &io);
+    }
+    CUDA_TRY(cudaMemcpyAsync(h->st_act, actions_host, n, cudaMemcpyHostToDevice, s));
+    { int rc = heist_step_many(h, h->st_act, T, autoreset, h->st_rew, h->st_done, h->st_status, vis_traj, stream); if (rc) return rc; }
+    if (reward_host) CUDA_TRY(cudaMemcpyAsync(reward_host, h->st_rew, n * 4, cudaMemcpyDeviceToHost, s));
+    if (done_host) CUDA_TRY(cudaMemcpyAsync(done_host, h->st_done, n, cudaMemcpyDeviceToHost, s));
+    if (status_host) CUDA_TRY(cudaMemcpyAsync(status_host, h->st_status, n, cudaMemcpyDeviceToHost, s));
     return 0;
 }
 

@@ -565,6 +565,31 @@ def test_pipelined_step_many_is_graph_capturable():
         assert torch.equal(out[k], ref[k]), k
 
 
+@pytest.mark.parametrize("T,autoreset,mode", [(100, True, 0), (20, True, 0), (70, False, 0), (70, True, 2)])
+def test_step_many_host_matches_step_many(T, autoreset, mode):
+    """Host-buffer rollouts (copies riding the pipelined launch, or bracketing the sequential / ray-march ones)."""
+    N = 512
+    cfg = EnvironmentConfig(max_steps=40)
+    env = BatchedHeistEnv(cfg, N)
+    env.set_mode(mode)
+    rng = np.random.default_rng(11)
+    am, cp = synthetic.sample_asset_maps(rng, N, 20, 20), synthetic.sample_cam_params(rng, N)
+    acts = torch.as_tensor(synthetic.sample_actions(rng, T, N))
+    env.set_layout_from_asset_map(am, cp, 15)
+    env.reset()
+    ref = {k: v.cpu() for k, v in env.step_many(acts, autoreset=autoreset, want_vis=True).items()}
+    ref_dyn = env.env_dyn.clone()
+    env.set_layout_from_asset_map(am, cp, 15)
+    env.reset()
+    vis = torch.empty((T, N, env.R, env.W), dtype=torch.int32, device="cuda")
+    out = env.step_many_host(acts.pin_memory(), autoreset=autoreset, vis_out=vis)
+    torch.cuda.synchronize()
+    for k in ("reward", "done", "status"):
+        assert torch.equal(out[k], ref[k]), k
+    assert torch.equal(vis.cpu(), ref["vis_bits"]) and torch.equal(env.env_dyn, ref_dyn)
+    env.check_errors()
+
+
 def test_cache_coverage_and_fallback_mix():
     """Assets outside the cache's range (vision_range > 7, fov > 180, more than 4 guards) leave their env to the
     ray-march kernel; both kernels then serve one batch.  HEIST_NO_VIS_CACHE=1 disables the cache altogether."""
