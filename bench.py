@@ -363,7 +363,19 @@ def main():
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         torch.cuda.set_device(local_rank)
-        dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local_rank}"))
+        # NCCL writes its version banner (NCCL_DEBUG=VERSION/INFO on some boxes) to stdout: keep stdout for the one JSON
+        # line by pointing fd 1 at stderr while the communicator comes up
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=torch.device(f"cuda:{local_rank}"))
+            dist.all_reduce(torch.zeros(1, device=f"cuda:{local_rank}"))
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     try:
         run_ours(args, rank, world, local_rank)
     finally:
