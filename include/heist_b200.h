@@ -31,7 +31,7 @@ extern "C" {
 #endif
 
 #define HEIST_MAX_DIM 64
-#define HEIST_ABI_VERSION 1
+#define HEIST_ABI_VERSION 2
 
 /* info["status"] of HeistEnvironment.step, environment.py:233,236,281,288,294 */
 enum HeistStatus {
@@ -102,12 +102,19 @@ typedef struct HeistStateView {
     const uint8_t *guard_path;    /* [N][max_guards][max_path][2]                                */
     const double *guard_heading;  /* [N][max_guards]                                             */
     const int32_t *guard_idx;     /* [N][max_guards]    Guard.current_idx                        */
+    const uint8_t *wall_accepted; /* [N][max_walls]     1: the i-th wall of the last explicit set_layout request was
+                                                        placed and paid for, i.e. is in HeistEnvironment.walls
+                                                        (environment.py:118-121)                                  */
 } HeistStateView;
 
 typedef struct HeistHandle HeistHandle;
 
 int heist_abi_version(void);
 const char *heist_last_error(void);
+/* Message of the last condition that is not an error but costs performance (thread-local; "" if none): set by
+ * heist_create when the angular visibility cache could not be allocated and every env falls back to the ray-march
+ * kernels.  HEIST_REQUIRE_VIS_CACHE=1 in the environment turns that condition into an error (-11). */
+const char *heist_last_warning(void);
 
 /* HeistEnvironment.__init__ (environment.py:62-96) for num_envs independent envs on `device`. */
 int heist_create(const HeistParams *params, int num_envs, int device, HeistHandle **out);
@@ -227,6 +234,13 @@ int heist_cache_stats(HeistHandle *h, int32_t *envs_cached, int64_t *cache_bytes
 
 /* Kernels this handle has launched for reset / step / step_many / step_observe since heist_create (bench accounting). */
 int heist_launch_count(HeistHandle *h, int64_t *count);
+
+/*
+ * Verification hook: the ray directions the kernels use, dx = cos(radians(a)), dy = -sin(radians(a))
+ * (security.py:71-75), for n angles in degrees (device pointers; a handle must exist on `device`).  Angles within
+ * 1e-11 degree of a multiple of 30 (|a| <= 1440) come from a table evaluated by the host libm at heist_create.
+ */
+int heist_debug_ray_dirs(int device, const double *angles_deg, int n, double *dx, double *dy, void *stream);
 
 /* Synchronises `stream` and reports sticky device-side errors (capacity overflow, bad waypoint). */
 int heist_check_errors(HeistHandle *h, void *stream);

@@ -26,12 +26,14 @@ class HeistLayoutArrays(C.Structure):
 class HeistStateView(C.Structure):
     _fields_ = [(n, c_vp) for n in (
         "tile", "wall_bits", "vis_bits", "env_static", "env_dyn", "cam_f", "cam_i", "cam_heading",
-        "guard_fov", "guard_i", "guard_path", "guard_heading", "guard_idx")]
+        "guard_fov", "guard_i", "guard_path", "guard_heading", "guard_idx", "wall_accepted")]
 
 
 EXPORTS = {
     "heist_abi_version": (C.c_int, []),
     "heist_last_error": (C.c_char_p, []),
+    "heist_last_warning": (C.c_char_p, []),
+    "heist_debug_ray_dirs": (C.c_int, [C.c_int, c_vp, C.c_int, c_vp, c_vp, c_vp]),
     "heist_create": (C.c_int, [C.POINTER(HeistParams), C.c_int, C.c_int, C.POINTER(c_vp)]),
     "heist_destroy": (C.c_int, [c_vp]),
     "heist_decode_validate": (C.c_int, [c_vp, c_vp, c_vp, c_vp, C.c_int, C.c_int, c_vp, c_vp]),
@@ -74,7 +76,7 @@ def load():
         fn = getattr(L, name)  # AttributeError if the symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if L.heist_abi_version() != 1:
+    if L.heist_abi_version() != 2:
         raise RuntimeError("libheist_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -6,6 +6,7 @@ only the owner of device memory and streams here.  There is no CPU path.
 """
 import ctypes as C
 import math
+import warnings
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -66,7 +67,8 @@ def guard_heading_table(path, speed):
 
 class BatchedHeistEnv:
     def __init__(self, config: Optional[EnvironmentConfig] = None, num_envs: int = 1, device=None,
-                 max_walls: int = 64, max_cams: int = 8, max_guards: int = 4, max_path: int = 8):
+                 max_walls: int = 64, max_cams: int = 8, max_guards: int = 4, max_path: int = 8,
+                 warn_uncached: bool = True):
         if not torch.cuda.is_available():
             raise RuntimeError("BatchedHeistEnv needs a CUDA device (B200); there is no CPU fallback")
         self.config = config or EnvironmentConfig()
@@ -91,6 +93,11 @@ class BatchedHeistEnv:
         torch.cuda.init()
         _ffi.check(self._lib.heist_create(C.byref(p), self.num_envs, dev_index, C.byref(h)), "heist_create")
         self._h = h
+        # not an error, but a several-fold slowdown: say so (HEIST_REQUIRE_VIS_CACHE=1 makes heist_create fail instead)
+        msg = self._lib.heist_last_warning()
+        self.cache_warning = msg.decode() if msg else ""
+        if self.cache_warning and warn_uncached:
+            warnings.warn(self.cache_warning, RuntimeWarning, stacklevel=2)
         self._budget = None  # per-env int32 tensor or None (config default)
         self._make_views()
 
@@ -131,6 +138,7 @@ class BatchedHeistEnv:
         self.guard_path = view(v.guard_path, (N, Kg, L, 2), "|u1")
         self.guard_heading = view(v.guard_heading, (N, Kg), "<f8")
         self.guard_idx = view(v.guard_idx, (N, Kg), "<i4")
+        self.wall_accepted = view(v.wall_accepted, (N, max(self.max_walls, 1)), "|u1")
 
     def _dev(self, x, dtype):
         if isinstance(x, torch.Tensor):
@@ -171,12 +179,22 @@ class BatchedHeistEnv:
     def scale_budget(self, budget):
         """env.budget.scale_budget (budget.py:64-67) for the batch: int or per-env array."""
         if budget is None:
-            self._budget = None
+            self._budget, self._budget_max = None, int(self.config.architect_budget)
         elif np.isscalar(budget):
             self._budget = torch.full((self.num_envs,), int(budget), dtype=torch.int32, device=self.device)
+            self._budget_max = int(budget)
         else:
             self._budget = self._dev(budget, torch.int32)
             assert self._budget.shape == (self.num_envs,)
+            self._budget_max = int(self._budget.max().item())
+
+    def _check_decode_capacity(self):
+        """The Architect decode buys at most budget // cost assets of a kind (networks.py:283-318); the per-env lists
+        must hold them, or the layout would silently differ from the reference's."""
+        b = getattr(self, "_budget_max", int(self.config.architect_budget))
+        if b // 3 > self.max_cams or b // 5 > self.max_guards or b > self.max_walls:
+            raise ValueError(f"budget {b} can buy more assets than the capacities hold (max_walls {self.max_walls}, "
+                             f"max_cams {self.max_cams}, max_guards {self.max_guards}): create the env with larger capacities")
 
     def set_layout_from_asset_map(self, asset_map, cam_params, budget=None, allow_cameras=True, allow_guards=True):
         """Architect decode + curriculum filter + set_layout + BFS (networks.py:273-335, training.py:464-470).
@@ -184,6 +202,7 @@ class BatchedHeistEnv:
         asset_map [N,R,C] int8 {0,1,2,3}; cam_params [N,3] float32 (fov, speed, heading) -> valid [N] bool."""
         if budget is not None:
             self.scale_budget(budget)
+        self._check_decode_capacity()
         am = self._dev(asset_map, torch.int8)
         cp = self._dev(cam_params, torch.float32)
         assert am.shape == (self.num_envs, self.R, self.C) and cp.shape == (self.num_envs, 3)

@@ -22,10 +22,11 @@ class _Budget:
     def __init__(self, env, total):
         self._env = env
         self.total_budget = int(total)
+        self._scaled = False   # scale_budget zeroes `spent` until the next set_layout (budget.py:64-67)
 
     @property
     def spent(self):
-        return int(self._env._b.budget_spent[0].item())
+        return 0 if self._scaled else int(self._env._b.budget_spent[0].item())
 
     @property
     def remaining(self):
@@ -33,6 +34,7 @@ class _Budget:
 
     def scale_budget(self, new_budget):
         self.total_budget = int(new_budget)
+        self._scaled = True
         self._env._b.scale_budget(int(new_budget))
 
     def reset(self):
@@ -66,7 +68,7 @@ class HeistEnvironment:
         self.config = src if isinstance(src, EnvironmentConfig) else EnvironmentConfig(
             **{k: getattr(src, k) for k in EnvironmentConfig.__dataclass_fields__ if hasattr(src, k)})
         self._b = BatchedHeistEnv(self.config, 1, device, max_walls=max_walls, max_cams=max_cams,
-                                  max_guards=max_guards, max_path=max_path)
+                                  max_guards=max_guards, max_path=max_path, warn_uncached=False)
         self.budget = _Budget(self, self.config.architect_budget)
         self.visibility_map = _Visibility(self)
         self.walls: List[Any] = []
@@ -80,14 +82,14 @@ class HeistEnvironment:
         for g in guards:
             if len(g["patrol_path"]) > self._b.max_path:
                 raise ValueError("patrol path longer than the facade's max_path")
+        walls = [(int(r), int(c)) for r, c in walls]
         valid = self._b.set_layout_explicit([(walls, cameras, guards)])
         self._b.check_errors()
-        grid = self.grid
-        # host mirror for len()/repr only: walls of the request that are WALL tiles now (a wall later
-        # overwritten by a guard's start tile is not listed, unlike environment.py:121)
-        self.walls = [SimpleNamespace(row=int(r), col=int(c)) for r, c in walls
-                      if 0 <= r < grid.shape[0] and 0 <= c < grid.shape[1] and grid[r, c] == 1
-                      and 0 < r < grid.shape[0] - 1 and 0 < c < grid.shape[1] - 1]
+        self.budget._scaled = False
+        # HeistEnvironment.walls (environment.py:119-121): the walls of the request that were placed and paid for, in
+        # request order -- the kernel reports which (a wall a guard later overwrites stays listed, as in the reference)
+        ok = self._b.wall_accepted[0, :len(walls)].cpu().numpy()
+        self.walls = [SimpleNamespace(row=r, col=c) for (r, c), a in zip(walls, ok) if a]
         return bool(valid[0].item())
 
     def is_level_valid(self) -> bool:

@@ -22,6 +22,7 @@
 #include "heist_stream.cuh"
 
 static thread_local std::string g_err;
+static thread_local std::string g_warn;   // heist_last_warning: conditions that are not errors but cost performance
 
 static int fail(int code, const char *fmt, ...) {
     char buf[512];
@@ -37,6 +38,14 @@ static int fail(int code, const char *fmt, ...) {
     do {                                                                                      \
         cudaError_t _e = (expr);                                                              \
         if (_e != cudaSuccess) return fail((int)_e, "%s: %s", #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+extern "C" int heist_destroy(HeistHandle *h);
+// inside heist_create, once the handle exists: free it before reporting the failure
+#define CUDA_TRY_H(expr)                                                                          \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess) { heist_destroy(h); return fail((int)_e, "heist_create: %s: %s", #expr, cudaGetErrorString(_e)); } \
     } while (0)
 
 struct HeistHandle {
@@ -85,6 +94,7 @@ static inline int env_blocks(int N) { return (N + HEIST_WARPS_PER_CTA - 1) / HEI
 
 extern "C" int heist_abi_version(void) { return HEIST_ABI_VERSION; }
 extern "C" const char *heist_last_error(void) { return g_err.c_str(); }
+extern "C" const char *heist_last_warning(void) { return g_warn.c_str(); }
 
 extern "C" int heist_destroy(HeistHandle *h) {
     if (!h) return 0;
@@ -99,15 +109,67 @@ extern "C" int heist_destroy(HeistHandle *h) {
     if (h->n_unc_host) cudaFreeHost(h->n_unc_host);
     if (h->st_act) { cudaFree(h->st_act); cudaFree(h->st_rew); cudaFree(h->st_done); cudaFree(h->st_status); }
     if (h->ev_unc) cudaEventDestroy(h->ev_unc);
-    if (h->s_seq) {
-        cudaStreamDestroy(h->s_seq); cudaStreamDestroy(h->s_fin); cudaStreamDestroy(h->s_cam2);
-        cudaStreamDestroy(h->s_h2d); cudaStreamDestroy(h->s_d2h); cudaEventDestroy(h->ev_join3);
-        for (int i = 0; i < 64; ++i) cudaEventDestroy(h->ev_h2d[i]);
-        cudaEventDestroy(h->ev_fork); cudaEventDestroy(h->ev_join); cudaEventDestroy(h->ev_join2);
-        for (int i = 0; i < 64; ++i) { cudaEventDestroy(h->ev_cam[i]); cudaEventDestroy(h->ev_seq[i]); }
+    // (a heist_create that failed half-way leaves some of these null)
+    cudaStream_t streams[] = {h->s_seq, h->s_fin, h->s_cam2, h->s_h2d, h->s_d2h};
+    for (cudaStream_t st : streams) if (st) cudaStreamDestroy(st);
+    cudaEvent_t events[] = {h->ev_join3, h->ev_fork, h->ev_join, h->ev_join2};
+    for (cudaEvent_t ev : events) if (ev) cudaEventDestroy(ev);
+    for (int i = 0; i < 64; ++i) {
+        if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_cam[i]) cudaEventDestroy(h->ev_cam[i]);
+        if (h->ev_seq[i]) cudaEventDestroy(h->ev_seq[i]);
     }
+    cudaGetLastError();
     delete h;
     return 0;
+}
+
+// cos / -sin of every double within NICE_W degrees of a multiple of 30 degrees, from the HOST libm (heist_common.cuh).
+// One table per device for the life of the process (handles share it; ~0.7 MB).
+static cudaError_t upload_nice_table(int device, double deg2rad) {
+    static double2 *tab_dev[64] = {nullptr};
+    static long long lo[NICE_N];
+    static int cnt[NICE_N], off[NICE_N];
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (!tab_dev[device]) {
+        int total = 0;
+        for (int i = 0; i < NICE_N; ++i) {
+            const int k = i - NICE_K;
+            lo[i] = 0; cnt[i] = 0; off[i] = total;
+            if (k == 0) continue;
+            const double c = fabs((double)k * 30.0);
+            long long b0, b1;
+            const double a0 = c - NICE_W, a1 = c + NICE_W;
+            memcpy(&b0, &a0, 8); memcpy(&b1, &a1, 8);
+            lo[i] = b0; cnt[i] = (int)(b1 - b0 + 1);
+            total += cnt[i];
+        }
+        double2 *host = (double2 *)malloc(sizeof(double2) * (size_t)total);
+        if (!host) return cudaErrorMemoryAllocation;
+        for (int i = 0; i < NICE_N; ++i) {
+            const int k = i - NICE_K;
+            for (int j = 0; j < cnt[i]; ++j) {
+                const long long b = lo[i] + j;
+                double mag;
+                memcpy(&mag, &b, 8);
+                volatile double a = k < 0 ? -mag : mag;
+                volatile double rad = a * deg2rad;   // math.radians
+                host[off[i] + j].x = cos(rad);
+                host[off[i] + j].y = -sin(rad);
+            }
+        }
+        double2 *dev = nullptr;
+        cudaError_t e = cudaMalloc(&dev, sizeof(double2) * (size_t)total);
+        if (e == cudaSuccess) e = cudaMemcpy(dev, host, sizeof(double2) * (size_t)total, cudaMemcpyHostToDevice);
+        free(host);
+        if (e != cudaSuccess) { if (dev) cudaFree(dev); return e; }
+        tab_dev[device] = dev;
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_nice_lo, lo, sizeof(lo));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_nice_cnt, cnt, sizeof(cnt));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_nice_off, off, sizeof(off));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_nice_tab, &tab_dev[device], sizeof(double2 *));
+    return e;
 }
 
 extern "C" int heist_create(const HeistParams *params, int num_envs, int device, HeistHandle **out) {
@@ -141,7 +203,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     const size_t N = num_envs;
     cudaError_t e = cudaSuccess;
 #define A(ptr, count) if (e == cudaSuccess) e = dalloc(h, &(ptr), (count))
-    A(d.tile, N * d.RC); A(d.wall, N * d.RW); A(d.env_s, N * 4);
+    A(d.tile, N * d.RC); A(d.wall, N * d.RW); A(d.env_s, N * 4); A(d.wall_ok, N * d.Kw);
     A(d.cam_f, N * d.Kc * 2); A(d.cam_i, N * d.Kc * 4);
     A(d.guard_fov, N * d.Kg); A(d.guard_i, N * d.Kg * 4); A(d.guard_path, N * d.Kg * d.L * 2);
     A(d.guard_head, N * d.Kg * d.L);
@@ -169,73 +231,78 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
                             N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
         const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
                               FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024 && d.L <= 32;
-        if (!(off && off[0] == '1') && need < free_b / 2 && seq_fits) {
+        const bool disabled = off && off[0] == '1';
+        g_warn.clear();
+        if (!disabled && need < free_b / 2 && seq_fits) {
             h->cache_bytes = need;
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
             A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc);
             A(d.vg_mask, N * d.Kg * d.L * HS * VC_ROWS); A(d.vg_hval, N * d.Kg * HS);
             A(d.vg_hslot, N * d.Kg * d.L); A(d.vg_nh, N * d.Kg);
             if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc (visibility cache): %s", cudaGetErrorString(e)); }
+        } else if (!disabled) {
+            // not an error -- every env is ray-marched (same results, several times slower) -- but never silent
+            char buf[384];
+            if (!seq_fits)
+                snprintf(buf, sizeof(buf), "heist_create: angular visibility cache disabled: max_path %d / max_cams %d / grid %dx%d do not fit "
+                         "the table-driven kernels (max_path <= 32); every env takes the ray-march path", d.L, d.Kc, d.R, d.C);
+            else
+                snprintf(buf, sizeof(buf), "heist_create: angular visibility cache disabled: it needs %.2f GB for %d envs but only %.2f GB "
+                         "are free (limit: half of the free memory); every env takes the ray-march path", need / 1e9, num_envs, free_b / 1e9);
+            g_warn = buf;
+            const char *req = getenv("HEIST_REQUIRE_VIS_CACHE");
+            if (req && req[0] == '1') { heist_destroy(h); return fail(-11, "%s (HEIST_REQUIRE_VIS_CACHE=1)", buf); }
         }
     }
 #undef A
 
-    // cos / -sin of exact multiples of 30 degrees from the host libm (see heist_common.cuh)
-    double ndx[NICE_N], ndy[NICE_N];
-    for (int k = -NICE_K; k <= NICE_K; ++k) {
-        volatile double a = (double)k * 30.0;
-        volatile double rad = a * d.deg2rad;
-        ndx[k + NICE_K] = cos(rad);
-        ndy[k + NICE_K] = -sin(rad);
-    }
-    CUDA_TRY(cudaMemcpyToSymbol(c_nice_dx, ndx, sizeof(ndx)));
-    CUDA_TRY(cudaMemcpyToSymbol(c_nice_dy, ndy, sizeof(ndy)));
+    CUDA_TRY_H(upload_nice_table(device, d.deg2rad));
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);
     h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.L);
 #define SET_FAST(RPL, W) \
-    CUDA_TRY(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem));
     SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
 #undef SET_FAST
     if (d.vc_p) {
-        CUDA_TRY(cudaFuncSetAttribute(k_seq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
-        CUDA_TRY(cudaFuncSetAttribute(k_seq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
+        CUDA_TRY_H(cudaFuncSetAttribute(k_seq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
+        CUDA_TRY_H(cudaFuncSetAttribute(k_seq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
     }
     if (d.vc_p) {   // single-tick buffers up front, so that step / reset never allocate (CUDA-graph capture)
         h->heads_cap = N * d.Kc; h->scratch_cap = N * d.RW; h->grec_cap = N * d.Kg; h->fin_cap = N;
-        CUDA_TRY(cudaMalloc(&h->heads, h->heads_cap * sizeof(double)));
-        CUDA_TRY(cudaMalloc(&h->scratch, h->scratch_cap * sizeof(uint32_t)));
-        CUDA_TRY(cudaMalloc(&h->grec, h->grec_cap * sizeof(uint16_t)));
-        CUDA_TRY(cudaMalloc(&h->fin, h->fin_cap));
-        CUDA_TRY(cudaMalloc(&h->last_t, N * sizeof(int32_t)));
+        CUDA_TRY_H(cudaMalloc(&h->heads, h->heads_cap * sizeof(double)));
+        CUDA_TRY_H(cudaMalloc(&h->scratch, h->scratch_cap * sizeof(uint32_t)));
+        CUDA_TRY_H(cudaMalloc(&h->grec, h->grec_cap * sizeof(uint16_t)));
+        CUDA_TRY_H(cudaMalloc(&h->fin, h->fin_cap));
+        CUDA_TRY_H(cudaMalloc(&h->last_t, N * sizeof(int32_t)));
         h->last_cap = N;
         {   // k_seq is the serial chain of a launch: its blocks go first
             int lo = 0, hi = 0;
-            CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            CUDA_TRY(cudaStreamCreateWithPriority(&h->s_seq, cudaStreamNonBlocking, hi));
+            CUDA_TRY_H(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CUDA_TRY_H(cudaStreamCreateWithPriority(&h->s_seq, cudaStreamNonBlocking, hi));
         }
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_fin, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_cam2, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
-        for (int i = 0; i < 64; ++i) CUDA_TRY(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_fin, cudaStreamNonBlocking));
+        CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_cam2, cudaStreamNonBlocking));
+        CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+        CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+        CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_join3, cudaEventDisableTiming));
+        for (int i = 0; i < 64; ++i) CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_h2d[i], cudaEventDisableTiming));
+        CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_join2, cudaEventDisableTiming));
+        CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+        CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
         for (int i = 0; i < 64; ++i) {
-            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_cam[i], cudaEventDisableTiming));
-            CUDA_TRY(cudaEventCreateWithFlags(&h->ev_seq[i], cudaEventDisableTiming));
+            CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_cam[i], cudaEventDisableTiming));
+            CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_seq[i], cudaEventDisableTiming));
         }
     }
     h->layout_smem = HEIST_WARPS_PER_CTA * layout_warp_bytes(d.RC, d.RW);
 #define SET_SMEM(E, B)                                                                                                    \
-    CUDA_TRY(cudaFuncSetAttribute(k_step_many<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
-    CUDA_TRY(cudaFuncSetAttribute(k_reset<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_step_many<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem)); \
+    CUDA_TRY_H(cudaFuncSetAttribute(k_reset<E, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->step_smem));
     SET_SMEM(false, false) SET_SMEM(false, true) SET_SMEM(true, false) SET_SMEM(true, true)
 #undef SET_SMEM
-    CUDA_TRY(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
+    CUDA_TRY_H(cudaFuncSetAttribute(k_set_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->layout_smem));
 
     // HeistEnvironment.__init__: bordered grid with START/VAULT, solver at start (environment.py:62-96)
     k_pos_table<<<(d.RC + 127) / 128, 128>>>(d);
@@ -243,11 +310,11 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
     LayoutDev none;
     memset(&none, 0, sizeof(none));
     k_set_layout<<<env_blocks(num_envs), HEIST_WARPS_PER_CTA * 32, h->layout_smem>>>(d, none, nullptr, nullptr);
-    CUDA_TRY(build_cache(h, 0));
-    CUDA_TRY(cudaMemsetAsync(d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(num_envs) * HEIST_WARPS_PER_CTA, 0));
+    CUDA_TRY_H(build_cache(h, 0));
+    CUDA_TRY_H(cudaMemsetAsync(d.slot2env, 0xFF, sizeof(int32_t) * env_blocks(num_envs) * HEIST_WARPS_PER_CTA, 0));
     k_build_order<<<1, 1024>>>(d, env_blocks(num_envs));
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY_H(cudaGetLastError());
+    CUDA_TRY_H(cudaDeviceSynchronize());
     *out = h;
     return 0;
 }
@@ -283,6 +350,12 @@ extern "C" int heist_decode_validate(HeistHandle *h, const int8_t *asset_map, co
                                      void *stream) {
     if (!h || !asset_map || !cam_params) return fail(-1, "heist_decode_validate: null argument");
     if (h->d.L < 8) return fail(-7, "heist_decode_validate: max_path must be >= 8 (patrol has 8 waypoints)");
+    if (!budget) {   // the decode buys at most budget/cost assets of a kind (networks.py:283-318): they must fit the lists
+        const int b = h->p.architect_budget;
+        if (b / COST_CAMERA > h->p.max_cams || b / COST_GUARD > h->p.max_guards || b > h->p.max_walls)
+            return fail(-12, "heist_decode_validate: budget %d can buy more assets than the capacities hold (max_walls %d, "
+                        "max_cams %d, max_guards %d)", b, h->p.max_walls, h->p.max_cams, h->p.max_guards);
+    }
     CUDA_TRY(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     k_decode<<<env_blocks(h->N), HEIST_WARPS_PER_CTA * 32, 0, s>>>(h->d, h->lz, asset_map, cam_params, budget,
@@ -695,7 +768,7 @@ extern "C" int heist_get_state(HeistHandle *h, HeistStateView *v) {
     v->tile = d.tile; v->wall_bits = d.wall; v->vis_bits = d.vis; v->env_static = d.env_s; v->env_dyn = d.env_d;
     v->cam_f = d.cam_f; v->cam_i = d.cam_i; v->cam_heading = d.cam_heading;
     v->guard_fov = d.guard_fov; v->guard_i = d.guard_i; v->guard_path = d.guard_path;
-    v->guard_heading = d.guard_heading; v->guard_idx = d.guard_idx;
+    v->guard_heading = d.guard_heading; v->guard_idx = d.guard_idx; v->wall_accepted = d.wall_ok;
     return 0;
 }
 
@@ -723,6 +796,23 @@ extern "C" int heist_architect_reward(HeistHandle *h, double *reward_out, double
     if (!h || !reward_out) return fail(-1, "heist_architect_reward: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
     k_architect_reward<<<(h->N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(h->d, reward_out, solve_rate_out);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+__global__ void k_debug_ray_dirs(const double *__restrict__ a, int n, double deg2rad, double *__restrict__ dx, double *__restrict__ dy) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double x, y;
+    ray_dir(a[i], deg2rad, x, y);
+    dx[i] = x; dy[i] = y;
+}
+
+extern "C" int heist_debug_ray_dirs(int device, const double *angles_deg, int n, double *dx, double *dy, void *stream) {
+    if (!angles_deg || !dx || !dy) return fail(-1, "heist_debug_ray_dirs: null argument");
+    if (n <= 0) return 0;
+    CUDA_TRY(cudaSetDevice(device));
+    k_debug_ray_dirs<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(angles_deg, n, 3.14159265358979323846 / 180.0, dx, dy);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }

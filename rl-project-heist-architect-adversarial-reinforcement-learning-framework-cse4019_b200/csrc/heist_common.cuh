@@ -9,15 +9,24 @@
 #include <stdint.h>
 
 #define HEIST_WARPS_PER_CTA 4
-#define NICE_K 48                 // exact multiples of 30 degrees covered: |angle| <= 1440
+#define NICE_K 48                 // multiples of 30 degrees covered: |angle| <= 1440
 #define NICE_N (2 * NICE_K + 1)
+#define NICE_W 1e-11              // half width (degrees) of the window around each multiple taken from the host libm
 
-// cos / -sin of exact multiples of 30 degrees, evaluated by the HOST libm at heist_create
-// (CPython's math.cos/sin call the same libm; security.py:71-75).  These are the only angles where
-// the last ulp of cos/sin can decide a tile (cos = +-1/2, +-1: exact .5 ties in col + dx*dist),
-// so they are taken from the platform the reference runs on instead of the device's sincos.
-__constant__ double c_nice_dx[NICE_N];
-__constant__ double c_nice_dy[NICE_N];
+// cos / -sin of every double within NICE_W degrees of a multiple of 30 degrees, evaluated by the HOST libm at
+// heist_create (CPython's math.cos/sin call the same libm; security.py:71-75).  The last ulp of cos/sin can decide a
+// tile only where col + cos(a) * dist lands within a rounding error (~1e-14 tile on a 64-wide grid) of an exact
+// .5 tie, which happens structurally only at cos/sin = +-1/2, +-1 (Niven), i.e. for angles within ~7e-13 degree of
+// a multiple of 30 -- the exact multiples people type (fov 60, speed 15, heading 0) and the values a hand-typed
+// non-dyadic speed accumulates to (0.1 * 300 = 30.000000000000156).  Those angles are taken from the platform the
+// reference runs on instead of the device's sincos: window k (angle ~ (k - NICE_K) * 30) is the c_nice_cnt[k]
+// consecutive doubles of one sign starting at bit pattern c_nice_lo[k] (smallest magnitude first), stored at
+// c_nice_tab[c_nice_off[k] ...] as (cos, -sin).  Around 0 the window is not enumerable (denormals); there
+// cos(x) = 1.0 and sin(x) = x exactly for |x| < 2^-27 in glibc (s_sin.c) -- pinned by a CPU test.
+__constant__ long long c_nice_lo[NICE_N];
+__constant__ int c_nice_cnt[NICE_N];
+__constant__ int c_nice_off[NICE_N];
+__constant__ const double2 *c_nice_tab;
 
 struct Dev {
     int N, R, C, W, RW, RC;
@@ -29,6 +38,7 @@ struct Dev {
     uint8_t *tile;        // [N][RC]
     uint32_t *wall;       // [N][RW]
     int32_t *env_s;       // [N][4]  n_cams, n_guards, valid, spent
+    uint8_t *wall_ok;     // [N][Kw] wall i of the request was accepted (HeistEnvironment.walls)
     double *cam_f;        // [N][Kc][2] fov, speed
     int16_t *cam_i;       // [N][Kc][4] row, col, range, num_rays
     double *guard_fov;    // [N][Kg]
@@ -79,12 +89,20 @@ __device__ __forceinline__ int py_imod(int a, int n) { int m = a % n; return m <
 
 // Ray direction for angle_deg: dx = cos(radians(a)), dy = -sin(radians(a))  (security.py:71-75).
 __device__ __forceinline__ void ray_dir(double angle_deg, double deg2rad, double &dx, double &dy) {
-    double k = rint(angle_deg * (1.0 / 30.0));
-    if (fabs(k) <= (double)NICE_K && __dmul_rn(k, 30.0) == angle_deg) {
-        int i = (int)k + NICE_K;
-        dx = c_nice_dx[i];
-        dy = c_nice_dy[i];
-        return;
+    const double k = rint(angle_deg * (1.0 / 30.0));
+    if (fabs(k) <= (double)NICE_K) {
+        const int i = (int)k + NICE_K;
+        if (i == NICE_K) {   // around 0: cos = 1, sin(x) = x (see above)
+            if (fabs(angle_deg) <= NICE_W) { dx = 1.0; dy = -__dmul_rn(angle_deg, deg2rad); return; }
+        } else {
+            const unsigned long long d = (unsigned long long)(__double_as_longlong(fabs(angle_deg)) - c_nice_lo[i]);
+            if (d < (unsigned long long)c_nice_cnt[i]) {
+                const double2 v = c_nice_tab[c_nice_off[i] + (int)d];
+                dx = v.x;
+                dy = v.y;
+                return;
+            }
+        }
     }
     double s, c;
     sincos(__dmul_rn(angle_deg, deg2rad), &s, &c);

@@ -209,10 +209,12 @@ k_set_layout(Dev D, LayoutDev Lz, const int32_t *__restrict__ budget, uint8_t *_
         for (int i = 0; i < nw; ++i) {
             const int16_t *w = Lz.wall_rc + ((size_t)env * D.Kw + i) * 2;
             int r = w[0], c = w[1];
-            if (r > 0 && r < R - 1 && c > 0 && c < C - 1 && tile[r * C + c] == HEIST_EMPTY && total - spent >= COST_WALL) {
+            const bool ok = r > 0 && r < R - 1 && c > 0 && c < C - 1 && tile[r * C + c] == HEIST_EMPTY && total - spent >= COST_WALL;
+            if (ok) {
                 spent += COST_WALL;
                 tile[r * C + c] = HEIST_WALL;
             }
+            D.wall_ok[(size_t)env * D.Kw + i] = ok ? 1 : 0;
         }
         // cameras (:124-135)
         int nc = Lz.n_cams ? Lz.n_cams[env] : 0;

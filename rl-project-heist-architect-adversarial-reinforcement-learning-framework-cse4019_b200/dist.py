@@ -28,10 +28,65 @@ def shard_range(total, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def _world(group=None):
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+class GradBucket:
+    """Persistent flat gradient bucket: every parameter's .grad is a VIEW into one contiguous buffer, so the
+    all-reduce between backward() and clip_grad_norm_ (agents/solver.py:195-199, agents/architect.py:138-141) is one
+    collective on memory the backward pass already wrote -- no per-step torch.cat, no copy-back.
+
+        bucket = GradBucket(net.parameters())
+        loss.backward()             # accumulates into the views (zero them with bucket.zero(), not set_to_none)
+        work = bucket.allreduce_async()   # NCCL: ReduceOp.AVG on its own stream
+        ...                               # independent work (next minibatch's state expansion) overlaps
+        bucket.wait(work)
+        clip_grad_norm_(...); optimizer.step(); bucket.zero()
+    """
+
+    def __init__(self, params, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        if not self.params:
+            raise ValueError("GradBucket: no trainable parameters")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        self.flat = torch.zeros(sum(p.numel() for p in self.params), dtype=dt, device=dev)
+        off = 0
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            off += n
+        self.nbytes = self.flat.numel() * self.flat.element_size()
+
+    def zero(self):
+        self.flat.zero_()
+
+    def allreduce_async(self):
+        """Start the all-reduce (mean over ranks); returns a handle for wait(), or None for a single process."""
+        world = _world(self.group)
+        if world == 1:
+            return None
+        avg = dist.get_backend(self.group) == "nccl"
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        return (work, None if avg else world)
+
+    def wait(self, handle):
+        if handle is None:
+            return
+        work, div = handle
+        work.wait()
+        if div:
+            self.flat /= div
+
+    def allreduce(self):
+        self.wait(self.allreduce_async())
+
+
 def allreduce_gradients(params, group=None, average=True):
-    """One flat-bucket all-reduce of every .grad (Solver 550 150 + Architect 407 464 fp32 ~ 3.8 MB:
-    latency-bound on NVSwitch, so a single bucket)."""
-    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+    """One-shot variant for callers without a GradBucket: flattens, all-reduces, copies back.  (The measured
+    loop uses GradBucket; this stays for ad-hoc modules.)"""
+    if _world(group) == 1:
         return
     grads = [p.grad for p in params if p.grad is not None]
     if not grads:

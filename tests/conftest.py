@@ -10,6 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "heist_golden.npz")
+GOLDEN_R2 = os.path.join(ROOT, "tests", "golden", "heist_golden_r2.npz")   # make_golden_r2.py: tie angles, big grids, trainer tapes
 
 
 def pytest_configure(config):
@@ -19,8 +20,8 @@ def pytest_configure(config):
 class Golden:
     """Fixtures produced by tests/golden/make_golden.py from the unmodified reference."""
 
-    def __init__(self):
-        self.z = np.load(GOLDEN, allow_pickle=False)
+    def __init__(self, path=GOLDEN):
+        self.z = np.load(path, allow_pickle=False)
         self.meta = json.loads(str(self.z["meta"]))
         self.traces = {t["name"]: t for t in self.meta["traces"]}
 
@@ -37,3 +38,8 @@ class Golden:
 @pytest.fixture(scope="session")
 def golden():
     return Golden()
+
+
+@pytest.fixture(scope="session")
+def golden2():
+    return Golden(GOLDEN_R2)

@@ -6,6 +6,8 @@ Rewards: float64 == against golden (and float32 == against the oracle's float32 
 State tensors / observation vectors: float32 ==.  GAE advantages / returns: float32 == (the
 north-star tolerance is 1e-5 relative; the op order is reproduced, so equality holds).
 """
+import json
+
 import numpy as np
 import pytest
 import torch
@@ -33,10 +35,31 @@ def _groups(golden):
 
 
 def test_golden_traces_bit_exact(golden):
+    _single_tick_traces(golden, 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_round2_traces_bit_exact(golden2, mode):
+    """tests/golden/heist_golden_r2.npz through step(): camera headings that accumulate to within a few ulp of
+    multiples of 30 degrees (rotation_speed 0.1 and 1/3; these rays take their direction from the host-libm table,
+    heist_common.cuh) and 32x32 / 64x64 budget-22 layouts -- in the cache, all-fp64 and filtered-march modes."""
+    _single_tick_traces(golden2, mode, only=(lambda n: True) if mode == 0 else (lambda n: n.startswith("tie") or n.endswith("_0")))
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_round2_traces_step_many(golden2, mode):
+    _step_many_traces(golden2, mode)
+
+
+def _single_tick_traces(golden, mode, only=lambda n: True):
     for (R, C, ms, T), names in _groups(golden).items():
+        names = [n for n in names if only(n)]
+        if not names:
+            continue
         N = len(names)
         env = BatchedHeistEnv(EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=ms), N,
                               max_walls=64, max_cams=8, max_guards=4, max_path=8)
+        env.set_mode(mode)
         lays = [golden.layout(n) for n in names]
         valid = env.set_layout_explicit([l[:3] for l in lays], budget=np.array([l[3] for l in lays]))
         env.check_errors()
@@ -93,9 +116,14 @@ def test_golden_traces_bit_exact(golden):
 
 def test_golden_traces_step_many(golden):
     """Same traces through the multi-step kernel with in-kernel auto-reset."""
+    _step_many_traces(golden, 0)
+
+
+def _step_many_traces(golden, mode):
     for (R, C, ms, T), names in _groups(golden).items():
         N = len(names)
         env = BatchedHeistEnv(EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=ms), N)
+        env.set_mode(mode)
         lays = [golden.layout(n) for n in names]
         env.set_layout_explicit([l[:3] for l in lays], budget=np.array([l[3] for l in lays]))
         env.reset()
@@ -407,6 +435,106 @@ def test_facade_reference_smoke_scripts():
     env.reset()
     s = env.get_state_tensor()
     assert f"{s[2].min():.3f}" == "-1.000" and f"{s[2].max():.3f}" == "0.790"
+
+
+def test_facade_replays_trainer_tapes(golden2):
+    """BASELINE config 1 drop-in: the exact call sequence the unmodified AdversarialTrainer._run_one_episode
+    (training.py:418-600) made on the reference's HeistEnvironment -- budget.scale_budget, set_layout, per attempt
+    reset / get_state_tensor / step / tick, is_level_valid (rewards.py:58), get_environment_state -- replayed on
+    the facade: every return value must equal what the reference returned (tests/golden/make_golden_r2.py)."""
+    tr = golden2.meta["trainer"]
+    cfg = EnvironmentConfig(grid_rows=tr["R"], grid_cols=tr["C"], max_steps=tr["max_steps"])
+    env = heist_b200.HeistEnvironment(cfg)
+    n_steps = 0
+    for k, ep in enumerate(tr["episodes"]):
+        for i, c in enumerate(ep["tape"]):
+            where = (k, i, c["call"])
+            arr = lambda key: golden2.z[f"trainer{k}/{i}/{key}"]
+
+            def check_obs(obs):
+                assert sorted(obs) == ["occupancy_grid", "solver_position", "time_feature", "vault_direction", "visibility_map"]
+                assert np.array_equal(obs["occupancy_grid"], arr("occ")) and np.array_equal(obs["visibility_map"], arr("vis")), where
+                vec = np.concatenate([obs["solver_position"], obs["vault_direction"], obs["time_feature"]])
+                assert vec.dtype == np.float32 and np.array_equal(vec, arr("vec")), where
+
+            if c["call"] == "scale_budget":
+                env.budget.scale_budget(c["arg"])
+                assert (env.budget.spent, env.budget.remaining) == (c["spent"], c["remaining"]), where
+            elif c["call"] == "set_layout":
+                guards = [{**g, "patrol_path": [tuple(p) for p in g["patrol_path"]]} for g in c["guards"]]
+                assert env.set_layout([tuple(w) for w in c["walls"]], c["cameras"], guards) == c["ret"], where
+                assert env.budget.spent == c["spent"], where
+                assert [len(env.walls), len(env.cameras), len(env.guards)] == c["n_placed"], where
+                assert [[w.row, w.col] for w in env.walls] == c["walls_placed"], where
+                assert repr(env) == c["repr"], where
+            elif c["call"] == "is_level_valid":
+                assert env.is_level_valid() == c["ret"], where
+            elif c["call"] == "reset":
+                check_obs(env.reset())
+            elif c["call"] == "step":
+                obs, r, d, info = env.step(c["arg"])
+                assert (r, d, info) == (c["reward"], c["done"], c["info"]), where
+                assert env.tick == c["tick_after"], where
+                check_obs(obs)
+                n_steps += 1
+            elif c["call"] == "get_state_tensor":
+                st = env.get_state_tensor()
+                assert st.dtype == np.float32 and np.array_equal(st, arr("state")), where
+            elif c["call"] == "get_environment_state":
+                got = json.loads(json.dumps(env.get_environment_state()))   # tuples -> lists, as in the fixture
+                assert sorted(got) == sorted(c["ret"]), where
+                for key in c["ret"]:
+                    assert got[key] == c["ret"][key], (where, key)
+    assert n_steps >= 30
+
+
+def test_ray_directions_match_host_libm_near_multiples_of_30():
+    """The directions the kernels use (ray_dir, heist_common.cuh) against the platform libm, which is what the
+    reference calls (security.py:71-75): every double within 40 ulp of a multiple of 30 degrees (|a| <= 1440), the
+    angles speed 0.1 / 0.3 / 1/3 accumulate to, the window around 0, and the window edges must be EQUAL; generic
+    angles (device sincos) are only reported."""
+    import ctypes as C
+    import math
+    lib = heist_b200.load_library()
+    env = BatchedHeistEnv(EnvironmentConfig(), 1)   # uploads the table
+    angles = []
+    for k in range(-48, 49):
+        c = k * 30.0
+        a = c
+        lo = [a := math.nextafter(a, -math.inf) for _ in range(40)]
+        a = c
+        hi = [a := math.nextafter(a, math.inf) for _ in range(40)]
+        angles += [c] + lo + hi + [c - 9.9e-12, c + 9.9e-12, c - 1e-11, c + 1e-11, c - 1.01e-11, c + 1.01e-11, c + 3e-13, c - 7e-13]
+    for speed in (0.1, 0.3, 1.0 / 3.0, -0.7):
+        h = 0.0
+        for t in range(4000):
+            h = (h + speed) % 360.0
+            for off in (0.0, -30.0, 45.0, -60.0):
+                a = h + off
+                if abs(a - round(a / 30.0) * 30.0) < 2e-11:
+                    angles.append(a)
+    n_table = len(angles)
+    rng = np.random.default_rng(5)
+    angles += list(rng.uniform(-720, 1080, 20000)) + [float(np.float32(x)) for x in rng.uniform(0, 360, 20000)]
+    a = torch.tensor(angles, dtype=torch.float64, device="cuda")
+    dx, dy = torch.empty_like(a), torch.empty_like(a)
+    rc = lib.heist_debug_ray_dirs(0, C.c_void_p(a.data_ptr()), len(angles), C.c_void_p(dx.data_ptr()), C.c_void_p(dy.data_ptr()), None)
+    assert rc == 0
+    dx, dy = dx.cpu().numpy(), dy.cpu().numpy()
+    ref_dx = np.array([math.cos(math.radians(x)) for x in angles])
+    ref_dy = np.array([-math.sin(math.radians(x)) for x in angles])
+    def in_window(x):   # the table's windows: [fl(|c| - 1e-11), fl(|c| + 1e-11)] around c = k * 30, |k| <= 48
+        c = abs(round(x / 30.0) * 30.0)
+        return c <= 1440.0 and c - 1e-11 <= abs(x) <= c + 1e-11
+
+    must = [i for i in range(len(angles)) if in_window(angles[i])]
+    assert len(must) >= 97 * 85 and sum(1 for i in must if angles[i] != round(angles[i] / 30.0) * 30.0 and abs(angles[i]) > 1e-9) > 8000
+    bad = [(angles[i], dx[i], ref_dx[i], dy[i], ref_dy[i]) for i in must if dx[i] != ref_dx[i] or dy[i] != ref_dy[i]]
+    assert not bad, bad[:5]
+    rest = np.array([i for i in range(len(angles)) if not in_window(angles[i])])
+    generic_diff = int((dx[rest] != ref_dx[rest]).sum() + (dy[rest] != ref_dy[rest]).sum())
+    print(f"ray_dir: {len(must)} near-multiple angles equal; other angles differing in the last ulp: {generic_diff} of {2 * len(rest)}")
+    env.close()
 
 
 @pytest.mark.parametrize("R,C,N,T,counts,nice", [

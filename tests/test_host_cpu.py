@@ -31,14 +31,14 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
     assert sorted(_ffi.EXPORTS) == names
-    assert lib.heist_abi_version() == 1
+    assert lib.heist_abi_version() == 2
 
 
 def test_struct_layouts_match_header():
     import ctypes as C
     assert C.sizeof(_ffi.HeistParams) == 12 * 4 + 3 * 8
     assert C.sizeof(_ffi.HeistLayoutArrays) == 13 * 8
-    assert C.sizeof(_ffi.HeistStateView) == 13 * 8
+    assert C.sizeof(_ffi.HeistStateView) == 14 * 8
 
 
 def test_argument_errors_do_not_need_a_gpu():
@@ -137,6 +137,31 @@ cnt = heist_b200.dist.allreduce_sum(torch.tensor([hi - lo], dtype=torch.int64))
 assert cnt.item() == 10
 mx = heist_b200.dist.allreduce_max(torch.tensor([float(rank)]))
 assert mx.item() == 1.0
+# persistent flat gradient bucket: .grad are views, one all-reduce, no copy-back
+net2 = torch.nn.Sequential(torch.nn.Linear(4, 3), torch.nn.Linear(3, 2))
+for p in net2.parameters():
+    dist.broadcast(p.data, 0)
+bucket = heist_b200.dist.GradBucket(net2.parameters())
+for it in range(2):
+    net2(x * (it + 1)).sum().backward()
+    mine = bucket.flat.clone()
+    bucket.wait(bucket.allreduce_async())
+    both = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(both, mine)
+    assert torch.allclose(bucket.flat, sum(both) / world)
+    assert all(p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.nbytes for p in net2.parameters())
+    assert torch.equal(torch.cat([p.grad.reshape(-1) for p in net2.parameters()]), bucket.flat)
+    bucket.zero()
+    assert all(float(p.grad.abs().sum()) == 0.0 for p in net2.parameters())
+# unequal shards (513 vs 512 envs x 64 ticks, minibatch 8192): both ranks must cut the same number of minibatches
+from heist_b200 import ppo
+n_local = (513 if rank == 0 else 512) * 64
+plan = ppo.minibatch_plan(n_local, 8192, 3, dist.group.WORLD)
+counts = torch.tensor([len(plan)]); both = [torch.zeros_like(counts) for _ in range(world)]
+dist.all_gather(both, counts)
+assert both[0].item() == both[1].item() == 15, both
+assert sum(len(i) for i in plan) == 3 * n_local and all(len(i) > 0 for i in plan)
+assert sorted(torch.cat(plan[:5]).tolist()) == list(range(n_local))
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
@@ -150,6 +175,28 @@ def test_gloo_world_size_2(tmp_path):
                               stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
     outs = [p.communicate(timeout=240)[0] for p in procs]
     assert all(p.returncode == 0 for p in procs), outs
+
+
+def test_stand_in_networks_have_the_reference_shapes():
+    """networks.py:13-131 / :134-239 -> 550 150 and 407 464 parameters; forward contracts."""
+    from heist_b200 import nets
+    s, a = nets.SolverNet(), nets.ArchitectNet()
+    assert sum(p.numel() for p in s.parameters()) == 550150
+    assert sum(p.numel() for p in a.parameters()) == 407464
+    logits, value, hidden = s(torch.zeros(2, 3, 20, 20))
+    assert logits.shape == (2, 5) and value.shape == (2, 1) and hidden[0].shape == (1, 2, 128)
+    pl, v, prm = a(nets.empty_grid_input(2, 20, 20, (1, 1), (18, 18), "cpu"))
+    assert pl.shape == (2, 4, 20, 20) and v.shape == (2, 1) and sorted(prm) == ["fov", "heading", "speed"]
+    assert 30 <= float(prm["fov"].min()) and float(prm["fov"].max()) <= 120
+
+
+def test_host_libm_small_argument_identities():
+    """heist_common.cuh ray_dir takes cos(x) = 1.0 and sin(x) = x for |x| <= radians(1e-11) (the window around
+    0 degrees cannot be tabulated): pin that the platform libm the reference calls (math.cos / math.sin) agrees."""
+    import math
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.uniform(-1, 1, 200000) * 10.0 ** rng.uniform(-320, -12.7, 200000), [0.0, -0.0, 5e-324, 1.7453292519943295e-13]])
+    assert all(math.cos(x) == 1.0 and math.sin(x) == x for x in xs.tolist())
 
 
 def test_ppo_host_helpers_on_cpu():

@@ -22,6 +22,59 @@ def make_env(golden, name):
 
 def test_all_traces_bit_exact(golden):
     assert len(golden.traces) >= 40
+    _check_traces(golden)
+
+
+def test_round2_traces_bit_exact(golden2):
+    """Headings a few ulp off multiples of 30 degrees (speed 0.1, 1/3), and the 32x32 / 64x64 budget-22 layouts."""
+    assert sum(n.startswith("tie") for n in golden2.traces) == 6 and sum(n.startswith("big") for n in golden2.traces) == 8
+    assert all(v >= 1 for v in golden2.meta["tie_near_ticks"].values())
+    _check_traces(golden2)
+
+
+def test_trainer_tapes(golden2):
+    """The call sequence AdversarialTrainer._run_one_episode made on the reference env (training.py:418-600):
+    the oracle reproduces every recorded return value."""
+    tr = golden2.meta["trainer"]
+    assert len(tr["episodes"]) >= 3 and sum(len(e["tape"]) for e in tr["episodes"]) >= 300
+    e, budget = None, 15
+    for k, ep in enumerate(tr["episodes"]):
+        for i, c in enumerate(ep["tape"]):
+            where = (k, i, c["call"])
+            arr = lambda key: golden2.z[f"trainer{k}/{i}/{key}"]
+            if c["call"] == "scale_budget":
+                budget = c["arg"]
+            elif c["call"] == "set_layout":
+                e = ho.OracleEnv(tr["R"], tr["C"], max_steps=tr["max_steps"], budget=budget)
+                guards = [{**g, "patrol_path": [tuple(p) for p in g["patrol_path"]]} for g in c["guards"]]
+                assert e.set_layout([tuple(w) for w in c["walls"]], c["cameras"], guards) == c["ret"], where
+                info = e.info()
+                assert info["spent"] == c["spent"] and [info["n_walls"], info["n_cams"], info["n_guards"]] == c["n_placed"], where
+            elif c["call"] == "is_level_valid":
+                assert e.is_level_valid() == c["ret"], where
+            elif c["call"] in ("reset", "step"):
+                if c["call"] == "reset":
+                    e.reset()
+                else:
+                    r, d, st = e.step(c["arg"])
+                    assert (r, d) == (c["reward"], c["done"]), where
+                    assert ["running", "detected", "vault_reached", "timeout", "already_done"][st] == c["info"]["status"], where
+                    assert e.info()["tick"] == c["tick_after"], where
+                s = e.state_tensor()
+                assert np.array_equal(s[0], arr("occ")) and np.array_equal(s[1], arr("vis")), where
+                assert np.array_equal(np.concatenate(e.obs_vectors()), arr("vec")), where
+            elif c["call"] == "get_state_tensor":
+                assert np.array_equal(e.state_tensor(), arr("state")), where
+            elif c["call"] == "get_environment_state":
+                st = c["ret"]
+                info = e.info()
+                assert [info["solver_r"], info["solver_c"]] == st["solver_pos"] and info["tick"] == st["tick"], where
+                assert np.array_equal(e.grid, np.asarray(st["grid"])), where
+                assert np.array_equal(e.visibility, np.asarray(st["visibility"], np.float32)), where
+                assert np.array_equal(e.cam_headings(), [cam["heading"] for cam in st["cameras"]]), where
+
+
+def _check_traces(golden):
     for name in golden.traces:
         e, valid, t = make_env(golden, name)
         assert valid == t["valid"], name
