@@ -55,16 +55,17 @@ struct HeistHandle {
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
     int mode;        // heist_set_mode: HEIST_MODE_*
-    size_t camvis_smem, seq_smem, cache_bytes;
+    size_t camvis_smem, cache_bytes;
     long long launches;   // kernels launched by reset / step / step_many (heist_launch_count)
     int *n_unc_host;      // pinned copy of d.n_uncached, refreshed (async) after every cache build
     cudaEvent_t ev_unc;   // ... complete when this event is
     int all_cached;       // -1 unknown, 0 some envs need the ray-march kernels, 1 none does (their launch is skipped)
-    double *heads;      size_t heads_cap;     // k_heads output, grow-only [blocks][N][Kc]
+    double *heads;      size_t heads_cap;     // k_heads output, grow-only [tick blocks][N][Kc]
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
     uint8_t *fin;       size_t fin_cap;       // k_seq -> k_finish: tick rebuilt its map [T][N]
     int32_t *last_t;    size_t last_cap;      // [chunks][N] last rebuilt tick of each chunk
+    size_t seq_smem;
     cudaStream_t s_seq, s_fin, s_cam2;        // side streams of the pipelined launch
     cudaEvent_t ev_fork, ev_join, ev_join2, ev_cam[64], ev_seq[64];
     // heist_step_many_host: device staging of the host buffers, copy streams of the pipelined launch
@@ -230,7 +231,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         const size_t need = N * d.Kc * ((size_t)VC_POINTS * 4 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
                             N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
         const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
-                              FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024 && d.L <= 32;
+                              FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024 && d.L <= 32;   // lane = waypoint
         const bool disabled = off && off[0] == '1';
         g_warn.clear();
         if (!disabled && need < free_b / 2 && seq_fits) {
@@ -260,23 +261,19 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);
-    h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.L);
 #define SET_FAST(RPL, W) \
     CUDA_TRY_H(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem));
     SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
 #undef SET_FAST
+    h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.L);
     if (d.vc_p) {
         CUDA_TRY_H(cudaFuncSetAttribute(k_seq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
         CUDA_TRY_H(cudaFuncSetAttribute(k_seq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
     }
     if (d.vc_p) {   // single-tick buffers up front, so that step / reset never allocate (CUDA-graph capture)
-        h->heads_cap = N * d.Kc; h->scratch_cap = N * d.RW; h->grec_cap = N * d.Kg; h->fin_cap = N;
+        h->heads_cap = N * d.Kc; h->scratch_cap = N * d.RW;
         CUDA_TRY_H(cudaMalloc(&h->heads, h->heads_cap * sizeof(double)));
         CUDA_TRY_H(cudaMalloc(&h->scratch, h->scratch_cap * sizeof(uint32_t)));
-        CUDA_TRY_H(cudaMalloc(&h->grec, h->grec_cap * sizeof(uint16_t)));
-        CUDA_TRY_H(cudaMalloc(&h->fin, h->fin_cap));
-        CUDA_TRY_H(cudaMalloc(&h->last_t, N * sizeof(int32_t)));
-        h->last_cap = N;
         {   // k_seq is the serial chain of a launch: its blocks go first
             int lo = 0, hi = 0;
             CUDA_TRY_H(cudaDeviceGetStreamPriorityRange(&lo, &hi));
@@ -396,12 +393,12 @@ static cudaError_t grow(T **buf, size_t *cap, size_t need) {
     return e;
 }
 
-// One chunk of ticks [t0, t0 + Tc) through the table-driven kernels.  s_cam / s_seq / s_fin may be one stream
-// (sequential) or three (pipelined: the camera cones of the next chunk are built while k_seq walks this one).
+// One chunk of ticks [t0, t0 + Tc) through the table-driven kernels.  s_cam / s_walk may be one stream (sequential)
+// or two (pipelined: the camera cones of the next chunk are built while k_walk walks this one).
 struct FastChunk {
     const int8_t *actions; float *reward; double *reward64; uint8_t *done, *status;
     uint32_t *cam; const double *heads; uint16_t *grec; uint8_t *fin; int32_t *last_t;
-    int Tc, autoreset, do_reset, only_last, store_heading; const uint8_t *mask;
+    int Tc, autoreset, do_reset, write_traj, store_heading; const uint8_t *mask;
 };
 
 static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
@@ -410,6 +407,17 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const unsigned g1 = (unsigned)(((long long)h->N * nblk + FAST_WARPS - 1) / FAST_WARPS);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
 #define GO(RPL, W) k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, c.Tc, nblk, c.heads, c.cam, m, c.do_reset)
+    if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
+    else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
+#undef GO
+    h->launches += 1;
+}
+
+static void launch_walk(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
+    const Dev &d = h->d;
+    const unsigned g2 = (unsigned)((h->N + WALK_WARPS - 1) / WALK_WARPS);
+#define GO(RPL, W) k_walk<RPL, W><<<g2, WALK_WARPS * 32, 0, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
+                                                                c.done, c.status, c.cam, c.write_traj, c.do_reset, c.mask, c.store_heading)
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
@@ -429,17 +437,17 @@ static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
 
 static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
-    const dim3 g3((unsigned)((h->N + 7) / 8), (unsigned)(c.only_last ? 1 : (c.Tc + FIN_TB - 1) / FIN_TB)), g4((unsigned)((h->N + 7) / 8), (unsigned)c.Tc);
+    const dim3 g3((unsigned)((h->N + 7) / 8), (unsigned)(!c.write_traj ? 1 : (c.Tc + FIN_TB - 1) / FIN_TB)), g4((unsigned)((h->N + 7) / 8), (unsigned)c.Tc);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
 #define GO(RPL, W)                                                                                       \
     do {                                                                                                 \
-        k_finish<RPL, W><<<g3, 256, 0, s>>>(d, c.Tc, c.cam, c.grec, c.fin, c.last_t, c.only_last, m);   \
-        if (!c.only_last && !c.autoreset) k_fill<W><<<g4, 256, 0, s>>>(d, c.Tc, c.cam, c.fin);          \
+        k_finish<RPL, W><<<g3, 256, 0, s>>>(d, c.Tc, c.cam, c.grec, c.fin, c.last_t, !c.write_traj, m);   \
+        if (!!c.write_traj && !c.autoreset) k_fill<W><<<g4, 256, 0, s>>>(d, c.Tc, c.cam, c.fin);          \
     } while (0)
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
-    h->launches += (!c.only_last && !c.autoreset) ? 2 : 1;
+    h->launches += (!!c.write_traj && !c.autoreset) ? 2 : 1;
 }
 
 // Host buffers of heist_step_many_host (pinned): copied chunk by chunk next to the kernels of the pipelined launch.
@@ -450,8 +458,8 @@ struct HostIO {
 #define FAST_PIPE_TC 32        // ticks per pipelined chunk (a multiple of FAST_TB)
 #define FAST_PIPE_MAX 64       // chunks (events) per launch
 
-// Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_seq ->
-// k_finish (heist_fast.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
+// Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_walk
+// (heist_fast.cuh, heist_walk.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
 static bool fast_pipelined(const HeistHandle *h, int total, int autoreset, int do_reset, const uint32_t *vis_traj) {
     const size_t N = h->N, NRW = N * h->d.RW;
     const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
@@ -467,14 +475,14 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
     const int total = do_reset ? 1 : T;
     const unsigned gh = (unsigned)((N * d.Kc + 127) / 128);
     FastChunk c;
-    c.autoreset = autoreset; c.do_reset = do_reset; c.only_last = vis_traj ? 0 : 1; c.mask = mask;
+    c.autoreset = autoreset; c.do_reset = do_reset; c.write_traj = vis_traj ? 1 : 0; c.mask = mask;
 
     // Pipelined: with auto-reset no env is ever left done at a chunk boundary, so the camera headings of the whole
-    // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_seq of chunk c.
+    // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_walk of chunk c.
     const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
     const bool pipelined = fast_pipelined(h, total, autoreset, do_reset, vis_traj);
     if (pipelined) {
-        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)total * N * d.Kc));
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)((total + FAST_TB - 1) / FAST_TB) * N * d.Kc));
         CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)total * N * d.Kg));
         CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)total * N));
         CUDA_TRY(grow(&h->last_t, &h->last_cap, (size_t)n_chunks * N));
@@ -503,7 +511,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             c.Tc = std::min(FAST_PIPE_TC, total - t0);
             c.actions = actions + off; c.reward = reward ? reward + off : nullptr; c.reward64 = reward64 ? reward64 + off : nullptr;
             c.done = done ? done + off : nullptr; c.status = status ? status + off : nullptr;
-            c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)t0 * N * d.Kc;
+            c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc;
             c.grec = h->grec + off * d.Kg; c.fin = h->fin + off; c.last_t = h->last_t + (size_t)i * N;
             launch_cam_vis(h, c, sc);
             if (timing) cudaEventRecord(te[0][i + 1], sc);
@@ -557,9 +565,12 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         const size_t off = (size_t)t0 * N;
         c.Tc = std::min(cap, total - t0);
         const int nblk = (c.Tc + FAST_TB - 1) / FAST_TB;
-        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)c.Tc * N * d.Kc));
-        CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)c.Tc * N * d.Kg));
-        CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)c.Tc * N));
+        CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)nblk * N * d.Kc));
+        if (nblk > 1) {
+            CUDA_TRY(grow(&h->grec, &h->grec_cap, (size_t)c.Tc * N * d.Kg));
+            CUDA_TRY(grow(&h->fin, &h->fin_cap, (size_t)c.Tc * N));
+            CUDA_TRY(grow(&h->last_t, &h->last_cap, N));
+        }
         if (!vis_traj) CUDA_TRY(grow(&h->scratch, &h->scratch_cap, (size_t)c.Tc * NRW));
         c.actions = actions ? actions + off : nullptr; c.reward = reward ? reward + off : nullptr;
         c.reward64 = reward64 ? reward64 + off : nullptr; c.done = done ? done + off : nullptr;
@@ -571,13 +582,13 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, heads_final, h->heads);
             h->launches += 1;
             c.store_heading = !heads_final;
-        } else {   // single ticks: k_cam_vis derives the heading itself, k_seq stores it
+        } else {   // a single tick block: k_cam_vis derives the headings itself, k_walk stores the last
             c.heads = nullptr;
             c.store_heading = 1;
         }
         launch_cam_vis(h, c, s);
-        launch_seq(h, c, s);
-        launch_finish(h, c, s);
+        if (nblk > 1) { launch_seq(h, c, s); launch_finish(h, c, s); }   // many ticks: thread-per-env chain + parallel completion
+        else launch_walk(h, c, s);                                      // a few ticks: one warp-per-env kernel
         CUDA_TRY(cudaGetLastError());
     }
     return 0;

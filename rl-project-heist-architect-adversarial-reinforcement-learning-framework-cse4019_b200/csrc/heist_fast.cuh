@@ -22,40 +22,28 @@
 #pragma once
 #include "heist_cache.cuh"
 #include "heist_step.cuh"
+#include "heist_walk.cuh"
 
 #define FAST_WARPS 4
 #define FAST_TB 8      // ticks per k_cam_vis warp
 
+// Per-camera constants of a k_cam_vis warp (shared memory).
 struct FastCam {
-    double heading, speed, fov, fx_scale, dom_lo;
-    const int32_t *P;       // boundary points (fixed point, heist_cache.cuh)
-    const uint16_t *MK;     // gap masks
-    int row, col, range, num_rays, n_points, sh;
+    double speed, fov, fx_scale, dom_lo;
+    double h0;              // heading at the block's first tick
+    const int2 *P2;         // gap g = boundary points 2g (its start), 2g + 1 (its end), fixed point (heist_cache.cuh)
+    const uint4 *MK4;       // ... and its window mask: uint4 2g, 2g + 1
+    int row, col, range, num_rays, n_gaps, sh;
 };
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
-    return (size_t)Kc * sizeof(FastCam) + 2 * (((size_t)RW * 4 + 15) & ~(size_t)15) + 32 + (size_t)FAST_TB * Kc * 16;
+    return (size_t)Kc * sizeof(FastCam) + (((size_t)RW * 4 + 15) & ~(size_t)15) + (size_t)FAST_TB * Kc * 16;
 }
 
-// OR a 16-bit window row (bit i = column col0 + i) into lane-row words
-template <int W>
-__device__ __forceinline__ void fast_or_row(uint32_t (&v)[W], unsigned bits, int col0) {
-    const unsigned long long b = col0 >= 0 ? ((unsigned long long)bits << col0) : ((unsigned long long)bits >> (-col0));
-    v[0] |= (uint32_t)b;
-    if (W == 2) v[W - 1] |= (uint32_t)(b >> 32);
-}
-
-// adv0: camera updates that precede tick 0 of a launch.  A step launch updates the cameras once per tick
-// (environment.py:251-252) -- except that an env which was already done when the launch began spends its first
-// tick on the "already done" early-out (:232-233); a reset launch keeps the headings (:205-208).
-__device__ __forceinline__ int fast_adv0(const Dev &D, int env, int do_reset) {
-    if (do_reset) return 0;
-    return (D.env_d[(size_t)env * 8 + 4] & F_DONE) ? 0 : 1;
-}
-
-// heads[t][env][k] = heading of camera k at tick t of this launch.  write_final: with auto-reset every
-// tick of the launch updates the cameras (environment.py:251-252), so the heading the launch ends on is the one
-// of its last tick and is stored here; otherwise k_seq stores it (an env may stop stepping early).
+// heads[b][env][k] = heading of camera k at the first tick of tick block b (FAST_TB ticks) of this launch; k_cam_vis
+// advances it through the block.  write_final: with auto-reset every tick of the launch updates the cameras
+// (environment.py:251-252), so the heading the launch ends on is the one of its last tick and is stored here;
+// otherwise k_walk stores it (an env may stop stepping early).
 __global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int write_final, double *__restrict__ heads) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D.N * D.Kc) return;
@@ -67,56 +55,81 @@ __global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int w
     for (int a = 0; a < adv0; ++a) h = py_mod360(__dadd_rn(h, speed));
     double last = h;
     for (int t = 0; t < T; ++t) {
-        heads[(size_t)t * D.N * D.Kc + i] = h;
+        if (t % FAST_TB == 0) heads[(size_t)(t / FAST_TB) * D.N * D.Kc + i] = h;
         last = h;
         h = py_mod360(__dadd_rn(h, speed));
     }
     if (write_final && T > 0) D.cam_heading[i] = last;
 }
 
-// rays below boundary point p: clamp(ceil((p - base) / 2^sh), 0, NR), p and base in fixed-point ray pitches
-__device__ __forceinline__ int fast_nrays(int p, int base_fx, int round_up, int sh, int NR) {
-    return max(0, min(NR, (p - base_fx + round_up) >> sh));
-}
-
-// Rare path of k_cam_vis, kept out of line: camera ray `ri` sits on (or within 1e-9 degree of) a rounding tie, or
-// outside the cached angle domain -> march it exactly like the reference does (security.py:69-99), the whole warp
-// on one ray: lane j evaluates sample j + 1 (at most 14 samples), a ballot finds the first blocked one.
-// `wall` is the env's wall bitmap in shared memory.
-__device__ __noinline__ void cam_exact_ray(VcGeo D, const uint32_t *wall, uint32_t *xvis, const FastCam *cam, double heading,
-                                           int ri, int lane) {
+// Rare path of k_cam_vis, kept out of line: the rays [r0, r1) of camera `cam` sit on (or within 1e-9 degree of) a
+// rounding tie, or outside the cached angle domain -> march them exactly like the reference does
+// (security.py:69-99), the whole warp on one ray: lane j evaluates sample j + 1 (at most 14 samples), a ballot finds
+// the first blocked one.  Marks go to xvis (shared memory, OR-ed into the tick's map afterwards).
+__device__ __noinline__ void cam_exact_rays(VcGeo D, const uint32_t *__restrict__ wall, uint32_t *xvis, const FastCam *cam,
+                                            double heading, int r0, int r1, int lane) {
     const int row = cam->row, col = cam->col, nsamp = 2 * cam->range;
     const double fov = cam->fov;
-    const double angle_deg = __dadd_rn(__dsub_rn(heading, __ddiv_rn(fov, 2.0)),
-                                       __ddiv_rn(__dmul_rn(fov, (double)ri), (double)cam->num_rays));
-    double dx, dy;
-    ray_dir(angle_deg, D.deg2rad, dx, dy);
-    const double dist = 0.5 * (double)(lane + 1);   // step - 1 + sub: exact multiples of 0.5
-    int r = 0, c = 0;
-    bool blocked = true;
-    if (lane < nsamp) {
-        c = vc_rint_even(__dadd_rn((double)col, __dmul_rn(dx, dist)));
-        r = vc_rint_even(__dadd_rn((double)row, __dmul_rn(dy, dist)));
-        blocked = r < 0 || r >= D.R || c < 0 || c >= D.C;
-        if (!blocked) blocked = (wall[r * D.W + (c >> 5)] >> (c & 31)) & 1u;
+    for (int ri = r0; ri < r1; ++ri) {
+        const double angle_deg = __dadd_rn(__dsub_rn(heading, __ddiv_rn(fov, 2.0)),
+                                           __ddiv_rn(__dmul_rn(fov, (double)ri), (double)cam->num_rays));
+        double dx, dy;
+        ray_dir(angle_deg, D.deg2rad, dx, dy);
+        const double dist = 0.5 * (double)(lane + 1);   // step - 1 + sub: exact multiples of 0.5
+        int r = 0, c = 0;
+        bool blocked = true;
+        if (lane < nsamp) {
+            c = vc_rint_even(__dadd_rn((double)col, __dmul_rn(dx, dist)));
+            r = vc_rint_even(__dadd_rn((double)row, __dmul_rn(dy, dist)));
+            blocked = r < 0 || r >= D.R || c < 0 || c >= D.C;
+            if (!blocked) blocked = (__ldg(wall + r * D.W + (c >> 5)) >> (c & 31)) & 1u;
+        }
+        const int first_blocked = __ffs(__ballot_sync(0xffffffffu, blocked)) - 1;   // lanes >= nsamp always are
+        if (lane < first_blocked && !(r == row && c == col))   // (r, c) != (self.row, self.col), security.py:93
+            atomicOr(&xvis[r * D.W + (c >> 5)], 1u << (c & 31));
     }
-    const int first_blocked = __ffs(__ballot_sync(0xffffffffu, blocked)) - 1;   // lanes >= nsamp always are
-    if (lane < first_blocked && !(r == row && c == col))   // (r, c) != (self.row, self.col), security.py:93
-        atomicOr(&xvis[r * D.W + (c >> 5)], 1u << (c & 31));
 }
 
-#define CV_PASSES 2   // 32-gap passes whose loads are in flight together (2 x 32 gaps = 128 segments)
+// ... for one (tick, camera) whose gap scan saw a band with a ray in it: the same scan again, boundary points only,
+// marching the rays of every such band.  Out of line and outside the hot loop, so that the hot loop holds no call
+// (a call there makes the compiler spill the loop's registers around it).
+__device__ __noinline__ void cam_exact_scan(VcGeo D, const uint32_t *__restrict__ wall, uint32_t *xvis, const FastCam *cam,
+                                            double heading, int s0, int bias, int lane) {
+    const int sh = cam->sh, NR = cam->num_rays + 1;
+    const int2 *P2 = cam->P2;
+    int carry = 0;
+    bool first = s0 > 0;
+    for (int g = (s0 >> 1) + lane;; g += 32) {
+        const int2 p = __ldg(P2 + min(g, VC_POINTS / 2 - 1));
+        const int lo = max(0, min(NR, (p.x + bias) >> sh)), hi = max(0, min(NR, (p.y + bias) >> sh));
+        int ph = __shfl_up_sync(0xffffffffu, hi, 1);
+        if (lane == 0) ph = first ? lo : carry;
+        first = false;
+        carry = __shfl_sync(0xffffffffu, hi, 31);
+        unsigned bh = __ballot_sync(0xffffffffu, lo > ph);
+        while (bh) {
+            const int src = __ffs(bh) - 1;
+            bh &= bh - 1;
+            const int r0 = __shfl_sync(0xffffffffu, ph, src), r1 = __shfl_sync(0xffffffffu, lo, src);
+            cam_exact_rays(D, wall, xvis, cam, heading, r0, r1, lane);
+        }
+        if (carry >= NR) break;
+    }
+}
 
 // Union of the camera cones of one env for FAST_TB consecutive ticks -> out[t][env][RW].
 // One pass = 32 consecutive gaps of a camera's table, lane j = gap g0 + j: it loads the gap's two boundary points
 // (one 8-byte load) and, independently, its 32-byte mask; the ray counts below the two points say whether the gap
-// holds a ray (then the mask is OR-ed in) and, with the upper count of lane j - 1, whether the band in front of
-// it does (rare: those rays are marched exactly).
+// holds a ray (then the mask is OR-ed in, branch-free) and, with the upper count of lane j - 1, whether the band in
+// front of it does (rare: those rays are marched exactly, out of line).  Two passes are in flight together (a
+// window of the bench workload spans 30-60 gaps).  The 8 mask words are OR-reduced over the warp (REDUX: the result
+// is warp-uniform) and every lane picks the 16-bit window row of the grid row it owns.
 template <int RPL, int W>
-__global__ void __launch_bounds__(FAST_WARPS * 32, 5)
+__global__ void __launch_bounds__(FAST_WARPS * 32, 6)
 k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, const uint8_t *__restrict__ mask,
           int do_reset) {
     extern __shared__ __align__(16) unsigned char smem[];
+    constexpr unsigned FULL = 0xffffffffu;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long wid = (long long)blockIdx.x * FAST_WARPS + warp;
     const int env = (int)(wid / nblk), b = (int)(wid - (long long)env * nblk);
@@ -125,49 +138,47 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
     unsigned char *sp = smem + (size_t)warp * camvis_warp_bytes(D.RW, D.Kc);
     FastCam *cams = reinterpret_cast<FastCam *>(sp);        sp += (size_t)D.Kc * sizeof(FastCam);
     uint32_t *xvis = reinterpret_cast<uint32_t *>(sp);      sp += ((size_t)D.RW * 4 + 15) & ~(size_t)15;
-    uint32_t *wall_s = reinterpret_cast<uint32_t *>(sp);    sp += ((size_t)D.RW * 4 + 15) & ~(size_t)15;
-    uint32_t *stage = reinterpret_cast<uint32_t *>(sp);      sp += 32;
     double *pre_head = reinterpret_cast<double *>(sp);       sp += (size_t)FAST_TB * D.Kc * 8;   // [tick][camera]
     int *pre_s0 = reinterpret_cast<int *>(sp);               sp += (size_t)FAST_TB * D.Kc * 4;
     int *pre_fx = reinterpret_cast<int *>(sp);
     const int n_cams = D.env_s[(size_t)env * 4];
     if (lane < n_cams) {
+        double h0;
         const size_t o = (size_t)env * D.Kc + lane;
         FastCam &Cm = cams[lane];
         const int16_t *ci = D.cam_i + o * 4;
         Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
-        Cm.heading = 0.0;
-        if (!heads) {   // single tick block: no k_heads launch, the heading of tick 0 is one update (or none) away
-            Cm.heading = D.cam_heading[o];
-            if (fast_adv0(D, env, do_reset)) Cm.heading = py_mod360(__dadd_rn(Cm.heading, Cm.speed));
+        if (heads) h0 = heads[((size_t)b * D.N + env) * D.Kc + lane];
+        else {   // single tick block: no k_heads launch, the heading of tick 0 is one update (or none) away
+            h0 = D.cam_heading[o];
+            if (fast_adv0(D, env, do_reset)) h0 = py_mod360(__dadd_rn(h0, Cm.speed));
         }
+        Cm.h0 = h0;
         Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
         Cm.dom_lo = D.vc_lo[o];
-        Cm.n_points = D.vc_meta[o * 2];
+        Cm.n_gaps = D.vc_meta[o * 2] >> 1;
         Cm.sh = D.vc_meta[o * 2 + 1];
         Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
-        Cm.P = D.vc_p + o * VC_POINTS;
-        Cm.MK = D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS;
+        Cm.P2 = reinterpret_cast<const int2 *>(D.vc_p + o * VC_POINTS);
+        Cm.MK4 = reinterpret_cast<const uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
     }
-    for (int i = lane; i < D.RW; i += 32) { xvis[i] = 0; wall_s[i] = D.wall[(size_t)env * D.RW + i]; }
+    for (int i = lane; i < D.RW; i += 32) xvis[i] = 0;
     const int t_begin = b * FAST_TB, t_end = min(T, (b + 1) * FAST_TB);
     __syncwarp();
-    // Per (tick, camera) of the block, in parallel lanes: the heading, the window start from the coarse index
-    // (segments below IX[q] hold no ray of that tick; start one earlier and on an even segment) and the first ray
-    // in fixed point (far outside the domain every ray is in a sentinel band anyway).
-    for (int idx = lane; idx < (heads ? (t_end - t_begin) * n_cams : n_cams); idx += 32) {
-        const int tt0 = heads ? idx / n_cams : 0, k = idx - tt0 * n_cams;
+    // Per (tick, camera) of the block, in parallel lanes: the heading (the block's first, advanced tick by tick), the
+    // window start from the coarse index (segments below IX[q] hold no ray of that tick; start one earlier and on an
+    // even segment) and the first ray in fixed point (far outside the domain every ray is in a sentinel band anyway).
+    for (int idx = lane; idx < (t_end - t_begin) * n_cams; idx += 32) {
+        const int tt = idx / n_cams, k = idx - tt * n_cams;
         const FastCam &Cm = cams[k];
         const uint16_t *IX = D.vc_idx + ((size_t)env * D.Kc + k) * VC_IDX;
-        double h = heads ? heads[((size_t)(t_begin + tt0) * D.N + env) * D.Kc + k] : Cm.heading;
-        for (int tt = tt0; tt < (heads ? tt0 + 1 : t_end - t_begin); ++tt) {
-            if (!heads && tt > 0) h = py_mod360(__dadd_rn(h, Cm.speed));
-            const double base = h - Cm.fov * 0.5;
-            const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
-            pre_head[tt * D.Kc + k] = h;
-            pre_s0[tt * D.Kc + k] = max(0, (int)IX[q] - 1) & ~1;
-            pre_fx[tt * D.Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
-        }
+        double h = Cm.h0;
+        for (int a = 0; a < tt; ++a) h = py_mod360(__dadd_rn(h, Cm.speed));
+        const double base = h - Cm.fov * 0.5;
+        const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
+        pre_head[tt * D.Kc + k] = h;
+        pre_s0[tt * D.Kc + k] = max(0, (int)IX[q] - 1) & ~1;
+        pre_fx[tt * D.Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
     }
     __syncwarp();
     for (int t = t_begin; t < t_end; ++t) {
@@ -180,67 +191,67 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         bool exact_used = false;
         for (int k = 0; k < n_cams; ++k) {
             const FastCam &Cm = cams[k];
-            const int base_fx = pre_fx[pi + k], s0 = pre_s0[pi + k], sh = Cm.sh, round_up = (1 << sh) - 1;
-            const double heading = pre_head[pi + k];
-            const int NR = Cm.num_rays + 1, n_points = Cm.n_points;
-            const int2 *P2 = reinterpret_cast<const int2 *>(Cm.P);      // gap g = points 2g (its start), 2g + 1 (its end)
-            const uint4 *MK4 = reinterpret_cast<const uint4 *>(Cm.MK);   // ... and uint4 2g, 2g + 1
-            const int n_gaps = n_points >> 1;
+            const int sh = Cm.sh, NR = Cm.num_rays + 1, n_gaps = Cm.n_gaps;
+            const int bias = ((1 << sh) - 1) - pre_fx[pi + k];   // rays below point p: clamp((p + bias) >> sh, 0, NR)
+            const int s0 = pre_s0[pi + k];
+            const int2 *P2 = Cm.P2;
+            const uint4 *MK4 = Cm.MK4;
             int carry = 0;             // rays below the end of the previous gap
             bool first = s0 > 0;       // the band in front of the first gap looked at lies before the window: no rays
+            unsigned bands = 0;
             uint32_t acc[VC_ROWS / 2];
 #pragma unroll
             for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
-            bool more = true;
-            for (int gb = s0 >> 1; more; gb += 32 * CV_PASSES) {
-                int2 pv[CV_PASSES];
-                uint4 m0[CV_PASSES], m1[CV_PASSES];
-#pragma unroll
-                for (int u = 0; u < CV_PASSES; ++u) {
-                    const int g = gb + 32 * u + lane;
-                    pv[u] = P2[min(g, VC_POINTS / 2 - 1)];   // padded above n_points with a point no ray reaches
-                    m0[u] = m1[u] = make_uint4(0, 0, 0, 0);
-                    if (g < n_gaps) { m0[u] = __ldg(MK4 + 2 * g); m1[u] = __ldg(MK4 + 2 * g + 1); }
+            for (int g = (s0 >> 1) + lane;; g += 64) {
+                const int2 p0 = __ldg(P2 + min(g, VC_POINTS / 2 - 1));        // padded above n_gaps with a point no ray reaches
+                const int2 p1 = __ldg(P2 + min(g + 32, VC_POINTS / 2 - 1));
+                uint4 ma0 = make_uint4(0, 0, 0, 0), ma1 = ma0, mb0 = ma0, mb1 = ma0;
+                if (g < n_gaps) { ma0 = __ldg(MK4 + 2 * g); ma1 = __ldg(MK4 + 2 * g + 1); }
+                if (g + 32 < n_gaps) { mb0 = __ldg(MK4 + 2 * g + 64); mb1 = __ldg(MK4 + 2 * g + 65); }
+                {
+                    const int lo = max(0, min(NR, (p0.x + bias) >> sh)), hi = max(0, min(NR, (p0.y + bias) >> sh));
+                    int ph = __shfl_up_sync(FULL, hi, 1);
+                    if (lane == 0) ph = first ? lo : carry;
+                    carry = __shfl_sync(FULL, hi, 31);
+                    const uint32_t sel = hi > lo ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
+                    acc[0] |= ma0.x & sel; acc[1] |= ma0.y & sel; acc[2] |= ma0.z & sel; acc[3] |= ma0.w & sel;
+                    acc[4] |= ma1.x & sel; acc[5] |= ma1.y & sel; acc[6] |= ma1.z & sel; acc[7] |= ma1.w & sel;
+                    bands |= __ballot_sync(FULL, lo > ph);   // bands that hold a ray (rare): marched exactly below
+                    if (carry >= NR) break;  // warp-uniform
                 }
-#pragma unroll
-                for (int u = 0; u < CV_PASSES; ++u) {
-                    if (!more) break;
-                    const int n_lo = fast_nrays(pv[u].x, base_fx, round_up, sh, NR), n_hi = fast_nrays(pv[u].y, base_fx, round_up, sh, NR);
-                    int prev_hi = __shfl_up_sync(0xffffffffu, n_hi, 1);
-                    if (lane == 0) prev_hi = first ? n_lo : carry;
-                    first = false;
-                    carry = __shfl_sync(0xffffffffu, n_hi, 31);
-                    if (n_hi > n_lo) {   // the gap holds a ray: every ray inside marks the same tiles
-                        acc[0] |= m0[u].x; acc[1] |= m0[u].y; acc[2] |= m0[u].z; acc[3] |= m0[u].w;
-                        acc[4] |= m1[u].x; acc[5] |= m1[u].y; acc[6] |= m1[u].z; acc[7] |= m1[u].w;
-                    }
-                    unsigned bh = __ballot_sync(0xffffffffu, n_lo > prev_hi);   // bands that hold a ray (rare)
-                    while (bh) {
-                        const int src = __ffs(bh) - 1;
-                        bh &= bh - 1;
-                        const int r0 = __shfl_sync(0xffffffffu, prev_hi, src), r1 = __shfl_sync(0xffffffffu, n_lo, src);
-                        for (int ri = r0; ri < r1; ++ri) cam_exact_ray(vc_geo(D), wall_s, xvis, &Cm, heading, ri, lane);
-                        exact_used = true;
-                    }
-                    if (carry >= NR) more = false;  // warp-uniform
+                {
+                    const int lo = max(0, min(NR, (p1.x + bias) >> sh)), hi = max(0, min(NR, (p1.y + bias) >> sh));
+                    int ph = __shfl_up_sync(FULL, hi, 1);
+                    if (lane == 0) ph = carry;
+                    carry = __shfl_sync(FULL, hi, 31);
+                    const uint32_t sel = hi > lo ? 0xffffffffu : 0u;
+                    acc[0] |= mb0.x & sel; acc[1] |= mb0.y & sel; acc[2] |= mb0.z & sel; acc[3] |= mb0.w & sel;
+                    acc[4] |= mb1.x & sel; acc[5] |= mb1.y & sel; acc[6] |= mb1.z & sel; acc[7] |= mb1.w & sel;
+                    bands |= __ballot_sync(FULL, lo > ph);
+                    if (carry >= NR) break;
                 }
+                first = false;
             }
 #pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(0xffffffffu, acc[i]);
-            if (lane == 0) {
-                reinterpret_cast<uint4 *>(stage)[0] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-                reinterpret_cast<uint4 *>(stage)[1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
-            }
-            __syncwarp();
-            const uint16_t *rows = reinterpret_cast<const uint16_t *>(stage);
+            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(FULL, acc[i]);
+            // lane = grid row: window row wr of the (now warp-uniform) mask, two 16-bit rows per word
+            const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
 #pragma unroll
             for (int a = 0; a < RPL; ++a) {
-                const int wr = lane + 32 * a - (Cm.row - Cm.range);
-                if (wr >= 0 && wr <= 2 * Cm.range) fast_or_row<W>(vis[a], rows[wr], Cm.col - Cm.range);
+                const int wr = lane + 32 * a - row0;
+                const uint32_t w01 = (wr & 2) ? acc[1] : acc[0], w23 = (wr & 2) ? acc[3] : acc[2];
+                const uint32_t w45 = (wr & 2) ? acc[5] : acc[4], w67 = (wr & 2) ? acc[7] : acc[6];
+                const uint32_t lo4 = (wr & 4) ? w23 : w01, hi4 = (wr & 4) ? w67 : w45;
+                const uint32_t word = (wr & 8) ? hi4 : lo4;
+                const unsigned bits = (wr & 1) ? (word >> 16) : (word & 0xffffu);
+                if (wr >= 0 && wr <= nrow) fast_or_row<W>(vis[a], bits, col0);
             }
-            __syncwarp();
+            if (bands) {   // warp-uniform
+                cam_exact_scan(vc_geo(D), D.wall + (size_t)env * D.RW, xvis, &Cm, pre_head[pi + k], s0, bias, lane);
+                exact_used = true;
+            }
         }
-        const bool ex = __any_sync(0xffffffffu, exact_used);
+        const bool ex = __any_sync(FULL, exact_used);
         if (ex) __syncwarp();
 #pragma unroll
         for (int a = 0; a < RPL; ++a) {
@@ -254,7 +265,7 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
                 }
             }
         }
-        __syncwarp();
+        if (ex) __syncwarp();
     }
 }
 
