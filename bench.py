@@ -44,14 +44,35 @@ def b_step_bytes(rows, cols, kc, kg):
     return 1 + (g + 32 * kc + 40 * kg + 16) + (8 * kc + 12 * kg + 16) + g + 5
 
 
+def csrc_stamp():
+    """sha256 over the kernel sources and the header: ties profiles/traffic.json to the code it was captured from."""
+    import hashlib
+    h = hashlib.sha256()
+    pkg = os.path.join(ROOT, "rl-project-heist-architect-adversarial-reinforcement-learning-framework-cse4019_b200", "csrc")
+    for f in sorted(os.listdir(pkg)) + ["../../include/heist_b200.h"]:
+        h.update(open(os.path.join(pkg, f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 def measured(key, field):
-    """Per-step figures from the committed ncu capture of this command (profiles/traffic.json), or None:
-    dram_bytes_per_launch = dram__bytes_read.sum + dram__bytes_write.sum, warp_inst_per_launch = smsp__inst_executed.sum,
-    summed over the kernels of one step."""
+    """Per-step figures REPLAYED from the committed ncu capture of this command (profiles/traffic.json, written by
+    profiles/make_traffic.py), or None when there is none or it was taken from other kernel sources (its `csrc`
+    stamp differs from csrc_stamp()): dram_bytes_per_launch = dram__bytes_read.sum + dram__bytes_write.sum,
+    warp_inst_per_launch = smsp__inst_executed.sum, summed over the kernels of one step."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key][field]
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+        return d[field] if d.get("csrc") == csrc_stamp() else None
     except Exception:
         return None
+
+
+def traffic_status(key):
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[key]
+    except Exception:
+        return "no capture committed"
+    return "replayed from profiles/traffic.json (ncu capture of this command at these kernel sources)" if d.get("csrc") == csrc_stamp() \
+        else "null: profiles/traffic.json was captured from other kernel sources (stale)"
 
 
 def hbm_peak():
@@ -163,90 +184,97 @@ def run_reference(args, rank, world):
 # ------------------------------------------------------------------------------------------------
 # GPU side
 # ------------------------------------------------------------------------------------------------
-def run_ours(args, rank, world, local_rank):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    import heist_b200
-    from heist_b200 import synthetic
+PY_REFERENCE = {"steps_per_s_per_core": 19.8, "what": "unmodified HeistEnvironment.step, 20x20, 2 cameras + 1 guard + 4 walls",
+                "where": "survey container (1 host core, CPython 3.12, numpy 2.3); the Python reference cannot travel to the GPU box",
+                "source": "BASELINE.md section 3"}
 
-    torch.cuda.set_device(local_rank)
-    dev = torch.device(f"cuda:{local_rank}")
-    cfg = heist_b200.EnvironmentConfig(grid_rows=args.rows, grid_cols=args.cols, max_steps=200,
-                                       architect_budget=args.budget)
-    env = heist_b200.BatchedHeistEnv(cfg, args.envs, device=dev)
-    env.set_mode(args.mode)
+
+class Timer:
+    """W warm-up + exactly K timed iterations of `body`, L2 flushed (untimed) before each, CUDA events on the
+    caller's stream, barrier + synchronize on both sides, MAX over ranks."""
+
+    def __init__(self, torch, dist, dev, world, flush):
+        self.torch, self.dist, self.dev, self.world, self.flush = torch, dist, dev, world, flush
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def run(self, body, warmup, steps):
+        torch = self.torch
+        for i in range(warmup):
+            self.flush.fill_(i & 0xFF)
+            body(i)
+        self.barrier()
+        evs = []
+        for i in range(steps):
+            self.flush.fill_(i & 0xFF)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            body(warmup + i)
+            e.record()
+            evs.append((s, e))
+        self.barrier()
+        ms = sum(s.elapsed_time(e) for s, e in evs)
+        t = torch.tensor([ms], dtype=torch.float64, device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+
+def rollout_leg(ctx, wl, steps, warmup, want_e2e, want_layout=False):
+    """One rollout workload (a BASELINE config) on this rank: build the env, sample valid layouts, time step_many.
+    Returns a dict of raw timings; the env is closed before returning."""
+    import numpy as np
+    torch, hb, synthetic, timer = ctx["torch"], ctx["hb"], ctx["synthetic"], ctx["timer"]
+    dev, rank = ctx["dev"], ctx["rank"]
+    cfg = hb.EnvironmentConfig(grid_rows=wl["rows"], grid_cols=wl["cols"], max_steps=200, architect_budget=wl["budget"])
+    env = hb.BatchedHeistEnv(cfg, wl["envs"], device=dev)
+    env.set_mode(wl.get("mode", 0))
     seed = synthetic.BASE_SEED + rank
-    am_host, cp_host = synthetic.make_valid_workload(env, seed, args.budget, exact_counts=args.exact_counts)
+    am_host, cp_host = synthetic.make_valid_workload(env, seed, wl["budget"], exact_counts=wl.get("exact_counts"))
     env.reset()
     envs_cached, cache_bytes = env.cache_stats()
     kc = float(env.env_static[:, 0].float().mean().item())
     kg = float(env.env_static[:, 1].float().mean().item())
     rng = np.random.default_rng(seed + 7919)
-    T, N = args.ticks, args.envs
-    n_iter = args.warmup + args.steps
-    # one action tensor per iteration, resident in HBM before the timed region (value) and in pinned host
-    # memory (e2e)
-    acts_host = [torch.from_numpy(synthetic.sample_actions(rng, T, N)).pin_memory() for _ in range(n_iter)]
+    T, N = wl["ticks"], wl["envs"]
+    n_iter = warmup + steps
+    # one action tensor per iteration, resident in HBM before the timed region (value) and in pinned host memory (e2e)
+    acts_host = [torch.from_numpy(synthetic.sample_actions(rng, T, N)) for _ in range(n_iter)]
     acts_dev = [a.to(dev) for a in acts_host]
     # every env step writes its packed observable state to HBM: reward, done, status and the visibility bitmap
     out = {"reward": torch.empty((T, N), dtype=torch.float32, device=dev),
            "done": torch.empty((T, N), dtype=torch.uint8, device=dev),
            "status": torch.empty((T, N), dtype=torch.uint8, device=dev),
            "vis_bits": torch.empty((T, N, env.R, env.W), dtype=torch.int32, device=dev)}
-    rew_host = torch.empty((T, N), dtype=torch.float32).pin_memory()
-    done_host = torch.empty((T, N), dtype=torch.uint8).pin_memory()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed_loop(body):
-        """W warm-up + exactly K timed iterations; L2 flushed (untimed) before each; device-timed."""
-        for i in range(args.warmup):
-            flush.fill_(i & 0xFF)
-            body(i)
-        barrier()
-        evs = []
-        for i in range(args.steps):
-            flush.fill_(i & 0xFF)
-            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            s.record()
-            body(args.warmup + i)
-            e.record()
-            evs.append((s, e))
-        barrier()
-        ms = sum(s.elapsed_time(e) for s, e in evs)
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if sampler:
-        sampler.start()
-
-    # (1) kernel-resident throughput: inputs already in HBM
     launches0 = env.launch_count()
-    ms_value = timed_loop(lambda i: env.step_many(acts_dev[i], autoreset=True, out=out))
-    launches_per_step = (env.launch_count() - launches0) // (args.warmup + args.steps)
-    steps_per_iter = T * N  # auto-reset: every (tick, env) is a live env step
-    total_steps = steps_per_iter * args.steps * world
-    value = total_steps / (ms_value * 1e-3)
+    ms_value = timer.run(lambda i: env.step_many(acts_dev[i], autoreset=True, out=out), warmup, steps)
+    res = {"ms_value": ms_value, "launches_per_step": (env.launch_count() - launches0) // n_iter, "kc": kc, "kg": kg,
+           "envs_cached": envs_cached, "cache_bytes": cache_bytes, "steps_per_iter": T * N, "cache_warning": env.cache_warning}
+    if want_e2e:   # end to end through the public API with HOST buffers: H2D actions, rollout, D2H reward + done
+        acts_pin = [a.pin_memory() for a in acts_host]
+        host_out = {"reward": torch.empty((T, N), dtype=torch.float32).pin_memory(),
+                    "done": torch.empty((T, N), dtype=torch.uint8).pin_memory()}
+        res["ms_e2e"] = timer.run(lambda i: env.step_many_host(acts_pin[i], host_out, autoreset=True, vis_out=out["vis_bits"]),
+                                  warmup, steps)
+    if want_layout and rank == 0:
+        res["extra"] = secondary_kernels(ctx, env, wl, out, am_host, cp_host)
+    env.close()
+    del env, out, acts_dev
+    torch.cuda.empty_cache()
+    return res
 
-    # (2) end to end through the public API with HOST buffers: H2D actions, rollout, D2H reward + done
-    host_out = {"reward": rew_host, "done": done_host}
 
-    def e2e_body(i):   # pinned host actions in, pinned host reward + done out (the copies ride along the launch)
-        env.step_many_host(acts_host[i], host_out, autoreset=True, vis_out=out["vis_bits"])
+def secondary_kernels(ctx, env, wl, out, am_host, cp_host):
+    """The other kernels of the path, timed alone (reported, not the headline): dense observation, GAE, the fused
+    single tick, and the per-layout work (decode + placement + BFS + visibility tables)."""
+    torch, hb, flush = ctx["torch"], ctx["hb"], ctx["timer"].flush
+    dev = ctx["dev"]
+    T, N, R, C = wl["ticks"], wl["envs"], wl["rows"], wl["cols"]
+    peak = ctx["peak"]
 
-    ms_e2e = timed_loop(e2e_body)
-    e2e_value = total_steps / (ms_e2e * 1e-3)
-    clocks = sampler.stop() if sampler else None
-
-    # (3) secondary HBM-streaming kernels of the path, timed alone (reported, not the headline)
     def time_kernel(fn, reps=20):
         for _ in range(3):
             fn()
@@ -260,29 +288,127 @@ def run_ours(args, rank, world, local_rank):
             tot += s.elapsed_time(e)
         return tot / reps
 
+    state = torch.empty((N, 3, R, C), dtype=torch.float32, device=dev)
+    ms_obs = time_kernel(lambda: env.observe(out=state))
+    g = 4 * R * ((C + 31) // 32)
+    obs_bytes = N * (12 * R * C + g + R * C + 4)
+    val = torch.randn((T, N), device=dev)
+    ms_gae = time_kernel(lambda: hb.compute_gae(out["reward"], val, out["done"]))
+    a1 = torch.zeros(N, dtype=torch.int8, device=dev)
+    ms_tick = time_kernel(lambda: env.step_observe(a1, autoreset=True, state_out=state))
+    am_dev, cp_dev = torch.as_tensor(am_host).to(dev), torch.as_tensor(cp_host).to(dev)
+    ms_layout = time_kernel(lambda: env.set_layout_from_asset_map(am_dev, cp_dev, wl["budget"]), reps=5)
+    env.reset()
+    return {"layout": {"ms": ms_layout, "us_per_env": 1e3 * ms_layout / N,
+                       "what": "heist_decode_validate: k_decode + k_set_layout (BFS) + k_build_cache + k_build_order, once per layout"},
+            "observe": {"ms": ms_obs, "achieved_gbs": obs_bytes / ms_obs / 1e6, "frac": obs_bytes / ms_obs / 1e6 / peak, "bytes": obs_bytes},
+            "gae": {"ms": ms_gae, "achieved_gbs": 17 * T * N / ms_gae / 1e6, "frac": 17 * T * N / ms_gae / 1e6 / peak, "bytes": 17 * T * N},
+            "step_observe_tick": {"us": 1e3 * ms_tick, "what": "heist_step_observe: one tick + auto-reset + dense state for all envs, eager launch",
+                                  "achieved_gbs": obs_bytes / ms_tick / 1e6, "frac": obs_bytes / ms_tick / 1e6 / peak}}
+
+
+def ppo_leg(ctx, envs, ticks, iters, warmup):
+    """BASELINE config 5: the full adversarial loop (heist_b200.loop.AdversarialLoop) with networks of the reference's
+    shapes, one process per GPU, NCCL gradient all-reduce.  Device-timed; MAX over ranks."""
+    torch, hb, dist = ctx["torch"], ctx["hb"], ctx["dist"]
+    dev, rank, world = ctx["dev"], ctx["rank"], ctx["world"]
+    from heist_b200 import nets
+    from heist_b200.loop import AdversarialLoop
+    torch.manual_seed(4242)   # identical initial weights on every rank
+    solver, architect = nets.SolverNet().to(dev), nets.ArchitectNet().to(dev)
+    torch.manual_seed(4242 + rank)
+    env = hb.BatchedHeistEnv(hb.EnvironmentConfig(), envs, device=dev)
+    loop = AdversarialLoop(env, solver, architect, ticks=ticks, budget=15, group=None)
+    phases, tot = {}, 0.0
+    for it in range(warmup + iters):
+        _, ms = loop.iteration(temperature=1.0)
+        if it >= warmup:
+            for k, v in ms.items():
+                phases[k] = phases.get(k, 0.0) + v / iters
+    t = torch.tensor([phases[k] for k in sorted(phases)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    phases = dict(zip(sorted(phases), [float(x) for x in t.tolist()]))
+    ar = loop.time_allreduce()
+    n_updates = loop.epochs * (-(-(ticks * envs) // loop.minibatch))
+    res = {"workload": f"config5: full adversarial PPO loop, 20x20, {envs} layouts/GPU x {ticks} ticks per iteration, policy in the loop, "
+                       f"SolverNet 550150 / ArchitectNet 407464 parameters (reference shapes, random init), {loop.epochs} epochs x "
+                       f"minibatch {loop.minibatch}, fp32 (TF32 convolutions)",
+           "n_gpus": world, "value": ticks * envs * world / (phases["total"] * 1e-3), "unit": "env-steps/s (policy in the loop, whole job)",
+           "ms_per_ppo_iteration": phases["total"], "ms_phases": {k: round(v, 3) for k, v in phases.items() if k != "total"},
+           "us_per_tick_with_policy": 1e3 * phases["rollout"] / ticks, "tick_graph_captured": loop.graphed,
+           "optimizer_steps_per_iteration": n_updates,
+           "allreduce": {"solver_us": ar["solver_us"], "architect_us": ar["architect_us"], "solver_bytes": ar["solver_bytes"],
+                         "architect_bytes": ar["architect_bytes"], "per_iteration_ms": (n_updates * ar["solver_us"] + ar["architect_us"]) * 1e-3,
+                         "how": "persistent flat bucket (GradBucket), NCCL ReduceOp.AVG, issued async and overlapped with the next "
+                                "minibatch's heist_expand_states; timed alone, device events"}}
+    if not loop.graphed:
+        res["tick_graph_error"] = getattr(loop, "graph_error", "")
+    env.close()
+    del loop, env
+    torch.cuda.empty_cache()
+    return res
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    import heist_b200
+    from heist_b200 import synthetic
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device(f"cuda:{local_rank}")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     peak, peak_src = hbm_peak()
-    extra = {}
-    if rank == 0:
-        state = torch.empty((N, 3, args.rows, args.cols), dtype=torch.float32, device=dev)
-        ms_obs = time_kernel(lambda: env.observe(out=state))
-        g = 4 * args.rows * ((args.cols + 31) // 32)
-        obs_bytes = N * (12 * args.rows * args.cols + g + args.rows * args.cols + 4)
-        val = torch.randn((T, N), device=dev)
-        ms_gae = time_kernel(lambda: heist_b200.compute_gae(out["reward"], val, out["done"]))
-        # per-layout work, outside the timed step: decode + placement + BFS + visibility tables + slot order
-        am_dev, cp_dev = torch.as_tensor(am_host).to(dev), torch.as_tensor(cp_host).to(dev)
-        ms_layout = time_kernel(lambda: env.set_layout_from_asset_map(am_dev, cp_dev, args.budget), reps=5)
-        env.reset()
-        extra = {"layout": {"ms": ms_layout, "us_per_env": 1e3 * ms_layout / N,
-                            "what": "heist_decode_validate: k_decode + k_set_layout (BFS) + k_build_cache + k_build_order, once per layout"},
-                 "observe": {"ms": ms_obs, "achieved_gbs": obs_bytes / ms_obs / 1e6, "frac": obs_bytes / ms_obs / 1e6 / peak,
-                             "bytes": obs_bytes},
-                 "gae": {"ms": ms_gae, "achieved_gbs": 17 * T * N / ms_gae / 1e6, "frac": 17 * T * N / ms_gae / 1e6 / peak,
-                         "bytes": 17 * T * N}}
+    ctx = {"torch": torch, "dist": dist, "hb": heist_b200, "synthetic": synthetic, "dev": dev, "rank": rank, "world": world,
+           "timer": Timer(torch, dist, dev, world, flush), "peak": peak}
+    wl = {"rows": args.rows, "cols": args.cols, "envs": args.envs, "budget": args.budget, "exact_counts": args.exact_counts,
+          "ticks": args.ticks, "mode": args.mode}
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    # (1) kernel-resident throughput (inputs already in HBM) and (2) end to end with host buffers
+    r = rollout_leg(ctx, wl, args.steps, args.warmup, want_e2e=True, want_layout=True)
+    clocks = sampler.stop() if sampler else None
+    T, N = args.ticks, args.envs
+    steps_per_iter = T * N  # auto-reset: every (tick, env) is a live env step
+    total_steps = steps_per_iter * args.steps * world
+    value = total_steps / (r["ms_value"] * 1e-3)
+    e2e_value = total_steps / (r["ms_e2e"] * 1e-3)
+
+    # (3) the other BASELINE configs under the same clock: 3 = stress (rank 0), 4 = 262144 envs 64x64 SHARDED over the
+    #     ranks (strong scaling), 5 = the full adversarial PPO loop with the NCCL gradient all-reduce
+    legs = {}
+    if args.legs and args.config == 2:
+        if rank == 0:
+            w3 = {"rows": 32, "cols": 32, "envs": 65536, "budget": 22, "exact_counts": (2, 4, 2), "ticks": 200, "mode": args.mode}
+            t3 = Timer(torch, dist, dev, 1, flush)
+            r3 = rollout_leg({**ctx, "timer": t3, "world": 1}, w3, 3, 3, want_e2e=False)
+            b3 = b_step_bytes(32, 32, r3["kc"], r3["kg"])
+            legs["config3"] = {"workload": "config3: 32x32 grid, 65536 envs on one GPU, budget 22 (4 cameras + 2 guards + 2 walls), T=200, auto-reset",
+                               "value": r3["steps_per_iter"] * 3 / (r3["ms_value"] * 1e-3), "unit": UNIT, "n_gpus": 1,
+                               "ms_per_step": r3["ms_value"] / 3, "steps": 3, "warmup": 3,
+                               "hbm_frac": b3 * r3["steps_per_iter"] * 3 / (r3["ms_value"] * 1e-3) / 1e9 / peak,
+                               "bytes_per_env_step": b3, "cache_bytes": r3["cache_bytes"], "envs_cached": r3["envs_cached"]}
+        ctx["timer"].barrier()
+        n4 = 262144 // world
+        w4 = {"rows": 64, "cols": 64, "envs": n4, "budget": 22, "exact_counts": (2, 4, 2), "ticks": 200, "mode": args.mode}
+        r4 = rollout_leg(ctx, w4, 3, 3, want_e2e=False)
+        b4 = b_step_bytes(64, 64, r4["kc"], r4["kg"])
+        legs["config4"] = {"workload": f"config4: 64x64 grid, 262144 envs sharded over {world} GPU(s) ({n4} per GPU), budget 22, T=200, auto-reset",
+                           "value": r4["steps_per_iter"] * 3 * world / (r4["ms_value"] * 1e-3), "unit": UNIT, "n_gpus": world,
+                           "scaling": "strong", "ms_per_step": r4["ms_value"] / 3, "steps": 3, "warmup": 3, "envs_per_gpu": n4,
+                           "hbm_frac_per_gpu": b4 * r4["steps_per_iter"] * 3 / (r4["ms_value"] * 1e-3) / 1e9 / peak,
+                           "bytes_per_env_step": b4, "cache_bytes_per_gpu": r4["cache_bytes"], "envs_cached_per_gpu": r4["envs_cached"]}
+        legs["config5"] = ppo_leg(ctx, 4096, 64, 2, 1)
 
     if rank != 0:
         return
-    ms_kernel = ms_value / args.steps
+    extra = r.get("extra", {})
+    ms_kernel = r["ms_value"] / args.steps
+    cache_bytes, envs_cached, kc, kg = r["cache_bytes"], r["envs_cached"], r["kc"], r["kg"]
+    launches_per_step = r["launches_per_step"]
     tkey = "step_cached" if (args.mode == 0 and cache_bytes) else "k_step_many"
     bstep = b_step_bytes(args.rows, args.cols, kc, kg)
     achieved = bstep * steps_per_iter / (ms_kernel * 1e-3) / 1e9
@@ -290,18 +416,28 @@ def run_ours(args, rank, world, local_rank):
             "warmup": args.warmup, "ms_per_step": ms_kernel, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": T * N, "d2h_bytes_per_step": 5 * T * N,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": r["ms_e2e"] / args.steps,
+                    "note": "pinned host actions in (1 B / env-step), pinned host reward + done out (5 B / env-step); status, the "
+                            "visibility bitmaps (80 B / env-step at 20x20) and observations stay on the device for an on-device "
+                            "policy -- a host-side consumer of the bitmaps would be PCIe-bound near 6e8 env-steps/s"},
             "gpu_launches": launches_per_step * args.steps,  # counted by the library (heist_launch_count)
             "roofline": {"bound": "hbm", "kernel": tkey, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": measured(tkey, "dram_bytes_per_launch"), "peak_source": peak_src,
-                         "bytes_per_env_step": bstep, "mean_cams": kc, "mean_guards": kg,
+                         "frac": achieved / peak, "traffic": measured(tkey, "dram_bytes_per_launch"), "traffic_status": traffic_status(tkey),
+                         "peak_source": peak_src, "bytes_per_env_step": bstep, "mean_cams": kc, "mean_guards": kg,
                          "launches_per_step": launches_per_step, "kernel_share": measured(tkey, "share"),
                          "note": "achieved = SURVEY 8d algorithmic bytes of the packed step x env-steps / duration of the whole "
-                                 "step (all of its kernels, pipelined over three streams, timed on the caller's stream); the "
-                                 "step is bound by L2-resident table lookups and warp-instruction issue, not by HBM "
-                                 "(DESIGN.md 4): frac is honest and small, traffic is the step's measured DRAM bytes"},
-            "cache": {"envs_cached": envs_cached, "envs": N, "bytes": cache_bytes},
+                                 "step (all of its kernels, pipelined over several streams, timed on the caller's stream); the "
+                                 "step is bound by table lookups and warp-instruction issue, not by HBM (DESIGN.md 4): frac is "
+                                 "honest and small, traffic is the step's DRAM bytes from the committed ncu capture"},
+            "cache": {"envs_cached": envs_cached, "envs": N, "bytes": cache_bytes, "warning": r["cache_warning"]},
             "clocks": clocks, "other_kernels": extra}
+    if "layout" in extra:   # env-steps/s with the per-layout work charged: one set_layout per solver_attempts x max_steps ticks
+        per_layout = 20 * 200   # training.py:515 (solver_attempts = 20) x max_steps
+        ms_amort = ms_kernel * (per_layout / T) + extra["layout"]["ms"]
+        line["amortised_value"] = {"value": per_layout * N * world / (ms_amort * 1e-3), "unit": UNIT,
+                                   "what": "value with heist_decode_validate (decode + BFS + visibility tables) charged once per "
+                                           "20 attempts x 200 ticks, the reference trainer's ratio (training.py:515)",
+                                   "layout_ms": extra["layout"]["ms"]}
     inst = measured(tkey, "warp_inst_per_launch")
     if inst and args.config == 2 and args.envs == 4096 and args.ticks == 200 and clocks and clocks.get("sm_mhz"):
         # informational: the bound that actually applies.  Warp-instructions per launch from the committed ncu
@@ -310,10 +446,13 @@ def run_ours(args, rank, world, local_rank):
         ach = inst / (ms_kernel * 1e-3)
         line["roofline_issue"] = {"bound": "warp-instruction issue", "achieved": ach, "peak": peak_issue,
                                   "unit": "warp-inst/s", "frac": ach / peak_issue,
-                                  "warp_inst_per_env_step": inst / steps_per_iter}
+                                  "warp_inst_per_env_step": inst / steps_per_iter, "source": traffic_status(tkey)}
+    if legs:
+        line["other_configs"] = legs
     if not args.no_cpu_baseline and world == 1:
-        rate, threads, sample, _, _ = cpu_rollout_rate(args, 256, args.cpu_seconds, seed)
-        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample}
+        rate, threads, sample, _, _ = cpu_rollout_rate(args, 256, args.cpu_seconds, synthetic.BASE_SEED + rank)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                                "python_reference": PY_REFERENCE}
     print(json.dumps(line), flush=True)
 
 
@@ -335,6 +474,8 @@ def main():
                     help="heist_set_mode: 0 = angular visibility cache (default), 1 = all-fp64 ray-march, 2 = filtered ray-march")
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", dest="legs", action="store_false",
+                    help="skip the other BASELINE configs (3, 4 sharded, 5 full PPO loop) that the default run adds as other_configs")
     args = ap.parse_args()
     if args.steps is None:
         args.steps = {2: 100, 3: 5, 4: 3}[args.config] if args.impl == "ours" else 5

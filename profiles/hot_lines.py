@@ -8,9 +8,13 @@ import collections, csv, glob, io, os, re, subprocess, sys, tempfile
 def main():
     rep, so, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern, "-c", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, data = rows[1], rows[2:]
+    for i, r in enumerate(data):   # several launches of the kernel in the report: the first one
+        if r and r[0] == "Kernel Name":
+            data = data[:i]
+            break
     ia, iex, ismp = hdr.index("Address"), hdr.index("Instructions Executed"), hdr.index("# Samples")
     ithr = hdr.index("Avg. Threads Executed")
     tmp = tempfile.mkdtemp()

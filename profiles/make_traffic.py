@@ -6,6 +6,8 @@ every launch.  One step = the kernels from the 4th k_heads launch (first timed s
 ray-march modes, the 4th k_step_many launch alone."""
 import collections, csv, json, os, sys
 
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
 
 def main():
     path = sys.argv[1]
@@ -17,9 +19,10 @@ def main():
     for r in rows[1:]:
         launches.setdefault(int(r[iid]), {"name": r[ik].split("(")[0].replace("void ", "")})[r[im]] = float(r[iv].replace(",", ""))
     seq = list(launches.values())
-    anchor = "k_heads" if key == "step_cached" else "k_step_many"
+    # one step of the cached path begins with the k_heads launch that has first = 1 (the L2 flush fill precedes it)
+    anchor = "at::native::vectorized_elementwise_kernel" if key == "step_cached" else "k_step_many"
     idx = [i for i, l in enumerate(seq) if l["name"].startswith(anchor)]
-    step = seq[idx[3]:idx[4]] if key == "step_cached" else [seq[idx[3]]]
+    step = seq[idx[-2]:idx[-1]] if key == "step_cached" else [seq[idx[3]]]
     step = [l for l in step if l["name"].startswith("k_")]
     tot_t = sum(l["gpu__time_duration.sum"] for l in step)
     share = collections.OrderedDict()
@@ -37,6 +40,7 @@ def main():
         "kernels_per_step": len(step),
         "serialized_us": round(tot_t / 1e3, 1),
         "share": {k: round(v, 3) for k, v in share.items()},
+        "csrc": __import__("bench").csrc_stamp(),   # bench.py replays these figures only for the same kernel sources
         "source": os.path.basename(path) + " (ncu launch list, kernels serialised: use shares and counters, not the absolute time)",
     }
     json.dump(data, open(out_path, "w"), indent=1)

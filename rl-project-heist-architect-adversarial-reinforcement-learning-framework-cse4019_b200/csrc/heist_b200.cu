@@ -55,12 +55,14 @@ struct HeistHandle {
     LayoutDev lz;  // decode output buffers
     size_t step_smem, layout_smem;
     int mode;        // heist_set_mode: HEIST_MODE_*
-    size_t camvis_smem, cache_bytes;
+    size_t camvis_smem, camvis_staged_smem, cache_bytes;
     long long launches;   // kernels launched by reset / step / step_many (heist_launch_count)
     int *n_unc_host;      // pinned copy of d.n_uncached, refreshed (async) after every cache build
     cudaEvent_t ev_unc;   // ... complete when this event is
     int all_cached;       // -1 unknown, 0 some envs need the ray-march kernels, 1 none does (their launch is skipped)
     double *heads;      size_t heads_cap;     // k_heads output, grow-only [tick blocks][N][Kc]
+    double *h_run;                            // [N][Kc] running headings between the chunks of a pipelined launch
+    cudaStream_t s_heads;  cudaEvent_t ev_heads[64];
     uint32_t *scratch;  size_t scratch_cap;   // cam_vis when the caller wants no visibility trajectory, grow-only
     uint16_t *grec;     size_t grec_cap;      // k_seq -> k_finish: guard (waypoint, heading slot) per tick [T][N][Kg]
     uint8_t *fin;       size_t fin_cap;       // k_seq -> k_finish: tick rebuilt its map [T][N]
@@ -104,6 +106,7 @@ extern "C" int heist_destroy(HeistHandle *h) {
     for (int i = 0; i < h->n_allocs; ++i) cudaFree(h->allocs[i]);
     if (h->heads) cudaFree(h->heads);
     if (h->scratch) cudaFree(h->scratch);
+    if (h->h_run) cudaFree(h->h_run);
     if (h->grec) cudaFree(h->grec);
     if (h->fin) cudaFree(h->fin);
     if (h->last_t) cudaFree(h->last_t);
@@ -111,12 +114,13 @@ extern "C" int heist_destroy(HeistHandle *h) {
     if (h->st_act) { cudaFree(h->st_act); cudaFree(h->st_rew); cudaFree(h->st_done); cudaFree(h->st_status); }
     if (h->ev_unc) cudaEventDestroy(h->ev_unc);
     // (a heist_create that failed half-way leaves some of these null)
-    cudaStream_t streams[] = {h->s_seq, h->s_fin, h->s_cam2, h->s_h2d, h->s_d2h};
+    cudaStream_t streams[] = {h->s_seq, h->s_fin, h->s_cam2, h->s_h2d, h->s_d2h, h->s_heads};
     for (cudaStream_t st : streams) if (st) cudaStreamDestroy(st);
     cudaEvent_t events[] = {h->ev_join3, h->ev_fork, h->ev_join, h->ev_join2};
     for (cudaEvent_t ev : events) if (ev) cudaEventDestroy(ev);
     for (int i = 0; i < 64; ++i) {
         if (h->ev_h2d[i]) cudaEventDestroy(h->ev_h2d[i]);
+        if (h->ev_heads[i]) cudaEventDestroy(h->ev_heads[i]);
         if (h->ev_cam[i]) cudaEventDestroy(h->ev_cam[i]);
         if (h->ev_seq[i]) cudaEventDestroy(h->ev_seq[i]);
     }
@@ -230,7 +234,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         const size_t HS = (size_t)d.L + 1;
         const size_t need = N * d.Kc * ((size_t)VC_POINTS * 4 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
                             N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
-        const bool seq_fits = SEQ_THREADS * seq_thread_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
+        const bool seq_fits = seq_warp_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
                               FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024 && d.L <= 32;   // lane = waypoint
         const bool disabled = off && off[0] == '1';
         g_warn.clear();
@@ -261,11 +265,16 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);
+    h->camvis_staged_smem = camvis_staged_bytes(d.RW, d.Kc, CVS_MAX_WARPS);
 #define SET_FAST(RPL, W) \
     CUDA_TRY_H(cudaFuncSetAttribute(k_cam_vis<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_smem));
     SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
 #undef SET_FAST
-    h->seq_smem = SEQ_THREADS * seq_thread_bytes(d.RW, d.L);
+#define SET_FAST(RPL, W) \
+    CUDA_TRY_H(cudaFuncSetAttribute(k_cam_vis_staged<RPL, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->camvis_staged_smem));
+    SET_FAST(1, 1) SET_FAST(1, 2) SET_FAST(2, 1) SET_FAST(2, 2)
+#undef SET_FAST
+    h->seq_smem = seq_warp_bytes(d.RW, d.L);
     if (d.vc_p) {
         CUDA_TRY_H(cudaFuncSetAttribute(k_seq<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
         CUDA_TRY_H(cudaFuncSetAttribute(k_seq<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->seq_smem));
@@ -279,6 +288,9 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
             CUDA_TRY_H(cudaDeviceGetStreamPriorityRange(&lo, &hi));
             CUDA_TRY_H(cudaStreamCreateWithPriority(&h->s_seq, cudaStreamNonBlocking, hi));
         }
+        CUDA_TRY_H(cudaMalloc(&h->h_run, N * d.Kc * sizeof(double)));
+        CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_heads, cudaStreamNonBlocking));
+        for (int i = 0; i < 64; ++i) CUDA_TRY_H(cudaEventCreateWithFlags(&h->ev_heads[i], cudaEventDisableTiming));
         CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_fin, cudaStreamNonBlocking));
         CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_cam2, cudaStreamNonBlocking));
         CUDA_TRY_H(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
@@ -406,6 +418,17 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const int nblk = (c.Tc + FAST_TB - 1) / FAST_TB;
     const unsigned g1 = (unsigned)(((long long)h->N * nblk + FAST_WARPS - 1) / FAST_WARPS);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
+    if (c.heads && nblk >= 2 && !c.do_reset) {   // many ticks: per-camera tables staged in shared memory
+        const int wpc = nblk <= CVS_MAX_WARPS ? nblk : 4;   // warps (tick blocks) per CTA
+        const dim3 g((unsigned)h->N, (unsigned)((nblk + wpc - 1) / wpc));
+        const size_t sm = camvis_staged_bytes(d.RW, d.Kc, wpc);
+#define GO(RPL, W) k_cam_vis_staged<RPL, W><<<g, wpc * 32, sm, s>>>(d, c.Tc, nblk, c.heads, c.cam)
+        if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
+        else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
+#undef GO
+        h->launches += 1;
+        return;
+    }
 #define GO(RPL, W) k_cam_vis<RPL, W><<<g1, FAST_WARPS * 32, h->camvis_smem, s>>>(d, c.Tc, nblk, c.heads, c.cam, m, c.do_reset)
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
@@ -426,8 +449,8 @@ static void launch_walk(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
 
 static void launch_seq(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
-    // envs per warp: about 1024 warps in flight (see k_seq)
-    const unsigned g2 = (unsigned)((h->N + SEQ_THREADS - 1) / SEQ_THREADS);
+    // a quad of lanes per env, 8 envs per warp (see k_seq)
+    const unsigned g2 = (unsigned)((h->N + SEQ_EPW - 1) / SEQ_EPW);
 #define GO(W) k_seq<W><<<g2, SEQ_THREADS, h->seq_smem, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
                                                               c.done, c.status, c.cam, c.grec, c.fin, c.last_t, c.do_reset, c.mask, c.store_heading)
     if (d.C > 32) GO(2); else GO(1);
@@ -455,15 +478,28 @@ struct HostIO {
     const int8_t *actions; float *reward; uint8_t *done, *status;
 };
 
-#define FAST_PIPE_TC 32        // ticks per pipelined chunk (a multiple of FAST_TB)
+#define FAST_PIPE_BLOCKS 5     // tick blocks (of FAST_TB ticks) per pipelined chunk, at most
 #define FAST_PIPE_MAX 64       // chunks (events) per launch
 
-// Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_walk
-// (heist_fast.cuh, heist_walk.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
+// A pipelined launch of `total` ticks is cut into n chunks of (almost) equal numbers of whole tick blocks, at most
+// FAST_PIPE_BLOCKS each (200 ticks = 25 blocks -> 5 chunks of 40 ticks): chunk i covers blocks [b0, b0 + nb).
+struct ChunkPlan {
+    int n, total_blocks;
+    int first_block(int i) const { const int q = total_blocks / n, r = total_blocks % n; return i * q + std::min(i, r); }
+};
+static ChunkPlan chunk_plan(int total) {
+    ChunkPlan p;
+    p.total_blocks = (total + FAST_TB - 1) / FAST_TB;
+    p.n = std::max(1, (p.total_blocks + FAST_PIPE_BLOCKS - 1) / FAST_PIPE_BLOCKS);
+    return p;
+}
+
+// Table-driven path for the envs the visibility cache covers (default mode only): k_heads -> k_cam_vis -> k_seq ->
+// k_finish (heist_fast.cuh).  do_reset: HeistEnvironment.reset for the masked envs (T ignored).
 static bool fast_pipelined(const HeistHandle *h, int total, int autoreset, int do_reset, const uint32_t *vis_traj) {
     const size_t N = h->N, NRW = N * h->d.RW;
-    const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
-    return !do_reset && autoreset && total > FAST_PIPE_TC && n_chunks <= FAST_PIPE_MAX && h->s_seq &&
+    const ChunkPlan p = chunk_plan(total);
+    return !do_reset && autoreset && p.n >= 2 && p.n <= FAST_PIPE_MAX && h->s_seq &&
            (vis_traj || (size_t)total * NRW * 4 <= ((size_t)1 << 30)) && (size_t)total * N * h->d.Kc * 8 <= ((size_t)4 << 30);
 }
 
@@ -479,7 +515,8 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
 
     // Pipelined: with auto-reset no env is ever left done at a chunk boundary, so the camera headings of the whole
     // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_walk of chunk c.
-    const int n_chunks = (total + FAST_PIPE_TC - 1) / FAST_PIPE_TC;
+    const ChunkPlan plan = chunk_plan(total);
+    const int n_chunks = plan.n;
     const bool pipelined = fast_pipelined(h, total, autoreset, do_reset, vis_traj);
     if (pipelined) {
         CUDA_TRY(grow(&h->heads, &h->heads_cap, (size_t)((total + FAST_TB - 1) / FAST_TB) * N * d.Kc));
@@ -491,10 +528,23 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         static const bool timing = getenv("HEIST_TIMING") != nullptr;   // debug: per-stage timeline of one launch
         cudaEvent_t te[3][FAST_PIPE_MAX + 1];
         if (timing) { for (int a = 0; a < 3; ++a) for (int i = 0; i <= n_chunks; ++i) cudaEventCreate(&te[a][i]); cudaEventRecord(te[0][0], s); }
-        k_heads<<<gh, 128, 0, s>>>(d, total, 0, 1, h->heads);
-        h->launches += 1;
+        // headings: the first chunk's on the caller's stream, the later ones on a side stream while the cameras of
+        // the chunks before them are being built (each continues from h_run where the previous one stopped)
+        auto chunk_ticks = [&](int i, int &t0) { t0 = plan.first_block(i) * FAST_TB; return std::min(total, plan.first_block(i + 1) * FAST_TB) - t0; };
+        {
+            int t0; const int tc = chunk_ticks(0, t0);
+            k_heads<<<gh, 128, 0, s>>>(d, tc, 0, 1, 0, h->heads, h->h_run);
+            h->launches += 1;
+        }
         c.store_heading = 0;
         CUDA_TRY(cudaEventRecord(h->ev_fork, s));
+        CUDA_TRY(cudaStreamWaitEvent(h->s_heads, h->ev_fork, 0));
+        for (int i = 1; i < n_chunks; ++i) {
+            int t0; const int tc = chunk_ticks(i, t0);
+            k_heads<<<gh, 128, 0, h->s_heads>>>(d, tc, 0, 0, i == n_chunks - 1, h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc, h->h_run);
+            h->launches += 1;
+            CUDA_TRY(cudaEventRecord(h->ev_heads[i], h->s_heads));
+        }
         CUDA_TRY(cudaStreamWaitEvent(h->s_seq, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_fin, h->ev_fork, 0));
         CUDA_TRY(cudaStreamWaitEvent(h->s_cam2, h->ev_fork, 0));
@@ -506,9 +556,10 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             // camera chunks are independent of each other: alternate two streams so that the tail of one chunk
             // overlaps the head of the next
             cudaStream_t sc = (i & 1) ? h->s_cam2 : s;
-            const int t0 = i * FAST_PIPE_TC;
+            int t0;
+            c.Tc = chunk_ticks(i, t0);
             const size_t off = (size_t)t0 * N;
-            c.Tc = std::min(FAST_PIPE_TC, total - t0);
+            if (i > 0) CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_heads[i], 0));
             c.actions = actions + off; c.reward = reward ? reward + off : nullptr; c.reward64 = reward64 ? reward64 + off : nullptr;
             c.done = done ? done + off : nullptr; c.status = status ? status + off : nullptr;
             c.cam = cam + (size_t)t0 * NRW; c.heads = h->heads + (size_t)(t0 / FAST_TB) * N * d.Kc;
@@ -537,7 +588,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         }
         CUDA_TRY(cudaEventRecord(h->ev_join, h->s_fin));   // s_fin's last kernel waited for s_seq's last
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join, 0));
-        CUDA_TRY(cudaEventRecord(h->ev_join2, h->s_cam2));
+        CUDA_TRY(cudaEventRecord(h->ev_join2, h->s_cam2));   // (s_heads' kernels were all waited for by camera chunks)
         CUDA_TRY(cudaStreamWaitEvent(s, h->ev_join2, 0));
         if (io) {   // (s_h2d's copies were consumed by s_seq, which s_fin -- joined above -- waited for)
             CUDA_TRY(cudaEventRecord(h->ev_join3, h->s_d2h));
@@ -579,7 +630,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
         c.grec = h->grec; c.fin = h->fin; c.last_t = h->last_t;
         const int heads_final = (autoreset && !do_reset) ? 1 : 0;   // k_heads can store the heading the chunk ends on
         if (nblk > 1) {
-            k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, heads_final, h->heads);
+            k_heads<<<gh, 128, 0, s>>>(d, c.Tc, do_reset, 1, heads_final, h->heads, nullptr);
             h->launches += 1;
             c.store_heading = !heads_final;
         } else {   // a single tick block: k_cam_vis derives the headings itself, k_walk stores the last

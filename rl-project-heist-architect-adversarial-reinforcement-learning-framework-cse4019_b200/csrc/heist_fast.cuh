@@ -40,25 +40,32 @@ __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
     return (size_t)Kc * sizeof(FastCam) + (((size_t)RW * 4 + 15) & ~(size_t)15) + (size_t)FAST_TB * Kc * 16;
 }
 
-// heads[b][env][k] = heading of camera k at the first tick of tick block b (FAST_TB ticks) of this launch; k_cam_vis
-// advances it through the block.  write_final: with auto-reset every tick of the launch updates the cameras
-// (environment.py:251-252), so the heading the launch ends on is the one of its last tick and is stored here;
-// otherwise k_walk stores it (an env may stop stepping early).
-__global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int write_final, double *__restrict__ heads) {
+// heads[b][env][k] = heading of camera k at the first tick of tick block b (FAST_TB ticks) of this stretch of T ticks;
+// k_cam_vis advances it through the block.  A launch is cut into stretches (the pipelined chunks): `first` starts
+// from the stored heading, later stretches continue from h_run, where each stretch leaves the heading of its next
+// tick.  write_final: with auto-reset every tick of the launch updates the cameras (environment.py:251-252), so the
+// heading the launch ends on is the one of its last tick and is stored here; otherwise k_seq / k_walk store it (an
+// env may stop stepping early).
+__global__ void __launch_bounds__(128) k_heads(Dev D, int T, int do_reset, int first, int write_final, double *__restrict__ heads,
+                                               double *__restrict__ h_run) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= D.N * D.Kc) return;
     const int env = i / D.Kc, k = i - env * D.Kc;
     if (!D.env_cached[env] || k >= D.env_s[(size_t)env * 4]) return;
-    double h = D.cam_heading[i];
     const double speed = D.cam_f[(size_t)i * 2 + 1];
-    const int adv0 = fast_adv0(D, env, do_reset);
-    for (int a = 0; a < adv0; ++a) h = py_mod360(__dadd_rn(h, speed));
+    double h;
+    if (first) {
+        h = D.cam_heading[i];
+        const int adv0 = fast_adv0(D, env, do_reset);
+        for (int a = 0; a < adv0; ++a) h = py_mod360(__dadd_rn(h, speed));
+    } else h = h_run[i];
     double last = h;
     for (int t = 0; t < T; ++t) {
         if (t % FAST_TB == 0) heads[(size_t)(t / FAST_TB) * D.N * D.Kc + i] = h;
         last = h;
         h = py_mod360(__dadd_rn(h, speed));
     }
+    if (h_run) h_run[i] = h;
     if (write_final && T > 0) D.cam_heading[i] = last;
 }
 
@@ -270,32 +277,241 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_seq: the sequential part of a launch, one THREAD per env (everything here is scalar per env: position,
-// rewards, guard indices; a warp per env would execute it 32 times over).  Per tick: move, guards advance,
-// detection from ONE word of cam_vis[t] OR the guards' cached masks at the Solver's row, vault / timeout,
-// rewards, auto-reset.  What k_finish needs to complete the maps -- the guards' (waypoint, heading slot) of every
-// tick -- is recorded.
+// k_cam_vis_staged: the many-tick variant.  A CTA owns one env and FAST_WARPS consecutive tick blocks (32 ticks:
+// cameras turn 5-35 degrees per tick, so such a stretch sweeps a camera's whole table); warp = tick block.  Per
+// camera the CTA first STAGES the camera's table -- boundary points and gap masks, ~10 KB, one coalesced copy --
+// in shared memory, then every warp scans the windows of its 8 ticks from there.  The scan's loads are then
+// shared-memory loads (~30 cycles instead of an L2 / HBM round trip per (tick, camera)), both 32-gap passes of an
+// iteration are evaluated together (independent instruction streams), and a table is read from HBM once per 32
+// ticks.  Rows are accumulated per tick in shared memory (lane = grid row).
+// ---------------------------------------------------------------------------------------------
+#define CVS_P2 640     // staged boundary-point pairs: VC_POINTS / 2 real slots + padding a scan can run into
+
+__host__ __device__ inline size_t camvis_staged_warp_bytes(int RW, int Kc) {
+    return (size_t)Kc * 8 + (size_t)FAST_TB * Kc * 16 + (((size_t)FAST_TB * RW * 4 + 15) & ~(size_t)15);
+}
+#define CVS_MAX_WARPS 8
+__host__ __device__ inline size_t camvis_staged_bytes(int RW, int Kc, int warps) {
+    return (size_t)Kc * sizeof(FastCam) + (size_t)CVS_P2 * 8 + (size_t)(VC_POINTS / 2) * 32 +
+           (size_t)warps * camvis_staged_warp_bytes(RW, Kc);
+}
+
+// Asynchronous global -> shared copies (LDGSTS): fire and forget, no register staging, so a burst of them is one
+// memory round trip instead of one per iteration.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void or_and(uint32_t &acc, uint32_t m, uint32_t sel) {   // acc |= m & sel, one LOP3
+    asm("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(acc) : "r"(m), "r"(sel));
+}
+
+// cam_exact_scan for a staged table (same scan, boundary points from shared memory)
+__device__ __noinline__ void cam_exact_scan_staged(VcGeo D, const uint32_t *__restrict__ wall, uint32_t *xvis, const FastCam *cam,
+                                                   const int2 *P2s, double heading, int s0, int bias, int lane) {
+    const int sh = cam->sh, NR = cam->num_rays + 1;
+    int carry = 0;
+    bool first = s0 > 0;
+    for (int g = (s0 >> 1) + lane;; g += 32) {
+        const int2 p = P2s[g];
+        const int lo = max(0, min(NR, (p.x + bias) >> sh)), hi = max(0, min(NR, (p.y + bias) >> sh));
+        int ph = __shfl_up_sync(0xffffffffu, hi, 1);
+        if (lane == 0) ph = first ? lo : carry;
+        first = false;
+        carry = __shfl_sync(0xffffffffu, hi, 31);
+        unsigned bh = __ballot_sync(0xffffffffu, lo > ph);
+        while (bh) {
+            const int src = __ffs(bh) - 1;
+            bh &= bh - 1;
+            const int r0 = __shfl_sync(0xffffffffu, ph, src), r1 = __shfl_sync(0xffffffffu, lo, src);
+            cam_exact_rays(D, wall, xvis, cam, heading, r0, r1, lane);
+        }
+        if (carry >= NR) break;
+    }
+}
+
+template <int RPL, int W>
+__global__ void __launch_bounds__(CVS_MAX_WARPS * 32, 3)
+k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    constexpr unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
+    const int env = blockIdx.x, b = blockIdx.y * (nthr >> 5) + warp;
+    if (!D.env_cached[env]) return;   // CTA-uniform
+    const int Kc = D.Kc, RW = D.RW;
+    unsigned char *sp = smem;
+    FastCam *cams = reinterpret_cast<FastCam *>(sp);   sp += (size_t)Kc * sizeof(FastCam);
+    int2 *P2s = reinterpret_cast<int2 *>(sp);           sp += (size_t)CVS_P2 * 8;
+    uint4 *M0s = reinterpret_cast<uint4 *>(sp);         sp += (size_t)(VC_POINTS / 2) * 16;   // first / second half of the masks,
+    uint4 *M1s = reinterpret_cast<uint4 *>(sp);         sp += (size_t)(VC_POINTS / 2) * 16;   // split: conflict-free LDS.128
+    sp += (size_t)warp * camvis_staged_warp_bytes(RW, Kc);
+    double *h0_s = reinterpret_cast<double *>(sp);      sp += (size_t)Kc * 8;
+    double *pre_head = reinterpret_cast<double *>(sp);  sp += (size_t)FAST_TB * Kc * 8;   // [tick][camera]
+    int *pre_s0 = reinterpret_cast<int *>(sp);          sp += (size_t)FAST_TB * Kc * 4;
+    int *pre_fx = reinterpret_cast<int *>(sp);          sp += (size_t)FAST_TB * Kc * 4;
+    uint32_t *vis_s = reinterpret_cast<uint32_t *>(sp);                                    // [tick][RW]
+    const int n_cams = D.env_s[(size_t)env * 4];
+    if (tid < n_cams) {
+        const size_t o = (size_t)env * Kc + tid;
+        FastCam &Cm = cams[tid];
+        const int16_t *ci = D.cam_i + o * 4;
+        Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
+        Cm.h0 = 0.0;
+        Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
+        Cm.dom_lo = D.vc_lo[o];
+        Cm.n_gaps = D.vc_meta[o * 2] >> 1;
+        Cm.sh = D.vc_meta[o * 2 + 1];
+        Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
+        Cm.P2 = reinterpret_cast<const int2 *>(D.vc_p + o * VC_POINTS);
+        Cm.MK4 = reinterpret_cast<const uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
+    }
+    const bool active = b < nblk;
+    const int t_begin = b * FAST_TB, t_end = active ? min(T, (b + 1) * FAST_TB) : t_begin;
+    const int n_t = t_end - t_begin;
+    if (active && lane < n_cams) h0_s[lane] = heads[((size_t)b * D.N + env) * Kc + lane];
+    for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
+    __syncthreads();
+    // Per (tick, camera) of the block, in parallel lanes: heading, window start from the coarse index, first ray in
+    // fixed point (see k_cam_vis).
+    for (int idx = lane; idx < n_t * n_cams; idx += 32) {
+        const int tt = idx / n_cams, k = idx - tt * n_cams;
+        const FastCam &Cm = cams[k];
+        const uint16_t *IX = D.vc_idx + ((size_t)env * Kc + k) * VC_IDX;
+        double h = h0_s[k];
+        for (int a = 0; a < tt; ++a) h = py_mod360(__dadd_rn(h, Cm.speed));
+        const double base = h - Cm.fov * 0.5;
+        const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
+        pre_head[tt * Kc + k] = h;
+        pre_s0[tt * Kc + k] = max(0, (int)IX[q] - 1) & ~1;
+        pre_fx[tt * Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
+    }
+    for (int k = 0; k < n_cams; ++k) {
+        const FastCam &Cm = cams[k];
+        const int n_gaps = Cm.n_gaps;
+        __syncthreads();   // the previous camera's table is no longer read (k = 0: cams / pre-phase visible)
+        {   // stage: points (8 B per gap) and masks (2 x 16 B per gap, de-interleaved); padding no ray reaches
+            const uint4 *src = reinterpret_cast<const uint4 *>(Cm.P2);
+            uint4 *dst = reinterpret_cast<uint4 *>(P2s);
+            for (int i = tid; i < (n_gaps + 1) / 2; i += nthr) cp_async16(dst + i, src + i);
+            for (int i = tid; i < 2 * n_gaps; i += nthr) cp_async16(((i & 1) ? M1s : M0s) + (i >> 1), Cm.MK4 + i);
+            // padding a scan can run into: it stops within 64 + 32 gaps of the last real one
+            for (int i = ((n_gaps + 1) & ~1) + tid; i < min(CVS_P2, n_gaps + 128); i += nthr) P2s[i] = make_int2(0x3fffffff, 0x3fffffff);
+            cp_async_wait_all();
+        }
+        __syncthreads();
+        const int sh = Cm.sh, NR = Cm.num_rays + 1;
+        const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
+        for (int tt = 0; tt < n_t; ++tt) {
+            const int bias = ((1 << sh) - 1) - pre_fx[tt * Kc + k];   // rays below point p: clamp((p + bias) >> sh, 0, NR)
+            const int s0 = pre_s0[tt * Kc + k];
+            int carry = 0;             // rays below the end of the previous gap
+            bool first = s0 > 0;       // the band in front of the first gap looked at lies before the window: no rays
+            unsigned bands = 0;
+            uint32_t acc[VC_ROWS / 2];
+#pragma unroll
+            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
+            for (int g = (s0 >> 1) + lane;; g += 64) {
+                const int2 p0 = P2s[g], p1 = P2s[g + 32];
+                const uint4 ma0 = M0s[min(g, VC_POINTS / 2 - 1)], ma1 = M1s[min(g, VC_POINTS / 2 - 1)];
+                const uint4 mb0 = M0s[min(g + 32, VC_POINTS / 2 - 1)], mb1 = M1s[min(g + 32, VC_POINTS / 2 - 1)];
+                const int lo0 = max(0, min(NR, (p0.x + bias) >> sh)), hi0 = max(0, min(NR, (p0.y + bias) >> sh));
+                const int lo1 = max(0, min(NR, (p1.x + bias) >> sh)), hi1 = max(0, min(NR, (p1.y + bias) >> sh));
+                int ph0 = __shfl_up_sync(FULL, hi0, 1), ph1 = __shfl_up_sync(FULL, hi1, 1);
+                const int c0 = __shfl_sync(FULL, hi0, 31), c1 = __shfl_sync(FULL, hi1, 31);
+                if (lane == 0) { ph0 = first ? lo0 : carry; ph1 = c0; }
+                const uint32_t sel0 = hi0 > lo0 ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
+                const uint32_t sel1 = hi1 > lo1 ? 0xffffffffu : 0u;
+                or_and(acc[0], ma0.x, sel0); or_and(acc[1], ma0.y, sel0); or_and(acc[2], ma0.z, sel0); or_and(acc[3], ma0.w, sel0);
+                or_and(acc[4], ma1.x, sel0); or_and(acc[5], ma1.y, sel0); or_and(acc[6], ma1.z, sel0); or_and(acc[7], ma1.w, sel0);
+                or_and(acc[0], mb0.x, sel1); or_and(acc[1], mb0.y, sel1); or_and(acc[2], mb0.z, sel1); or_and(acc[3], mb0.w, sel1);
+                or_and(acc[4], mb1.x, sel1); or_and(acc[5], mb1.y, sel1); or_and(acc[6], mb1.z, sel1); or_and(acc[7], mb1.w, sel1);
+                bands |= __ballot_sync(FULL, (lo0 > ph0) | (lo1 > ph1));   // bands that hold a ray (rare): marched exactly below
+                carry = c1;
+                first = false;
+                if (carry >= NR) break;  // warp-uniform
+            }
+#pragma unroll
+            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(FULL, acc[i]);
+            // lane = grid row: window row wr of the (now warp-uniform) mask, two 16-bit rows per word
+            uint32_t *rows = vis_s + tt * RW;
+#pragma unroll
+            for (int a = 0; a < RPL; ++a) {
+                const int wr = lane + 32 * a - row0;
+                const uint32_t w01 = (wr & 2) ? acc[1] : acc[0], w23 = (wr & 2) ? acc[3] : acc[2];
+                const uint32_t w45 = (wr & 2) ? acc[5] : acc[4], w67 = (wr & 2) ? acc[7] : acc[6];
+                const uint32_t lo4 = (wr & 4) ? w23 : w01, hi4 = (wr & 4) ? w67 : w45;
+                const uint32_t word = (wr & 8) ? hi4 : lo4;
+                const unsigned bits = (wr & 1) ? (word >> 16) : (word & 0xffffu);
+                if (wr >= 0 && wr <= nrow && bits) {
+                    uint32_t v[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) v[w] = 0;
+                    fast_or_row<W>(v, bits, col0);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                }
+            }
+            if (bands) {   // warp-uniform
+                __syncwarp();
+                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, rows, &Cm, P2s, pre_head[tt * Kc + k], s0, bias, lane);
+                __syncwarp();
+            }
+        }
+    }
+    __syncwarp();
+    {
+        uint32_t *dst = out + ((size_t)t_begin * D.N + env) * RW;
+        const size_t stride = (size_t)D.N * RW;
+        if (RW <= 32) {
+            if (lane < RW) {
+                dst += lane;
+#pragma unroll
+                for (int tt = 0; tt < FAST_TB; ++tt) if (tt < n_t) dst[tt * stride] = vis_s[tt * RW + lane];
+            }
+        } else {
+            for (int tt = 0; tt < n_t; ++tt, dst += stride)
+                for (int i = lane; i < RW; i += 32) dst[i] = vis_s[tt * RW + i];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// k_seq: the sequential part of a launch.  Everything here is scalar per env (position, rewards, guard indices), so
+// a warp per env would execute it 32 times over; a THREAD per env (round 1) put four guards' worth of unrolled,
+// divergent code on the per-tick dependency chain (~500 warp-instructions per tick).  Here a QUAD of lanes owns an
+// env: the four lanes carry the Solver's state redundantly and lane j of the quad owns guard j, so the guards of an
+// env advance and test the Solver's tile side by side, and one ballot joins the verdicts.  8 envs per warp.
+// Per tick: move, guards advance, detection from ONE word of cam_vis[t] OR the guards' cached masks at the Solver's
+// row, vault / timeout, rewards, auto-reset.  What k_finish needs to complete the maps -- the guards' (waypoint,
+// heading slot) of every tick -- is recorded.
 //
-// Few warps run this kernel (N / 32), each alone on its SM: its speed is the length of the per-tick dependency
-// chain, not throughput.  So nothing on that chain touches memory: the three wall rows around the Solver, each
-// guard's state, its current and next patrol word live in registers, and everything tick t + 1 will read from
-// global memory -- the cam_vis word(s) and the guards' mask rows at the Solver's next row -- is requested while
-// tick t is being decided (until an episode ends, the Solver's path and the patrols do not depend on what is
-// seen, so the next state is known); actions are requested four ticks ahead.  Every thread runs exactly T
-// iterations (an auto-reset is part of the tick that ended the episode), so the threads of a warp stay in step.
+// Few warps run this kernel (N / 8), one per scheduler: its speed is the length of the per-tick dependency chain,
+// not throughput.  So nothing on that chain waits for memory: the three wall rows around the Solver, the guard's
+// state, its current and next patrol word live in registers, and what tick t + 1 will read from global memory --
+// the cam_vis word and the guard's mask row at the Solver's next row -- is requested while tick t is being decided
+// (until an episode ends, the Solver's path and the patrols do not depend on what is seen, so the next state is
+// known); actions are requested four ticks ahead.  The camera rows themselves -- written to global memory by
+// k_cam_vis just before -- are STAGED in shared memory a stretch of ticks at a time (one pipelined burst of loads per
+// ~32 ticks), so the word the detection needs is a shared-memory load instead of an L2 round trip on every tick's
+// chain.  Every lane runs exactly T iterations (an auto-reset is part of the tick that ended the episode), so the
+// quads of a warp stay in step.
 // ---------------------------------------------------------------------------------------------
 #define SEQ_THREADS 32
-__host__ __device__ inline size_t seq_thread_bytes(int RW, int L) { return (size_t)RW * 4 + (size_t)VC_MAX_GUARDS * L * 4; }
-
-// guard cone + own tile of guard (o = env * Kg + g) at waypoint k with heading slot hs, grid row r
-// (visibility.py:44-59) -> OR into the W words of that row
-template <int W>
-__device__ __forceinline__ void guard_row(const Dev &D, size_t o, int k, int hs, int prow, int pcol, int rng, int r,
-                                          uint32_t (&v)[W]) {
-    const int wr = r - (prow - rng);
-    if (wr < 0 || wr > 2 * rng) return;
-    const unsigned bits = D.vg_mask[((o * D.L + k) * (size_t)(D.L + 1) + hs) * VC_ROWS + wr];
-    fast_or_row<W>(v, bits, pcol - rng);
+#define SEQ_EPW 8   // envs per warp
+#define SEQ_LIVE (1u << 22)      // per-tick record bits (k_seq pass A -> pass B)
+#define SEQ_DET (1u << 23)
+#define SEQ_VAULT (1u << 24)
+#define SEQ_TOUT (1u << 25)
+#define SEQ_REBUILT (1u << 26)
+#define SEQ_STAGE_BYTES 8192    // camera rows of the next ticks staged in shared memory
+__host__ __device__ inline int seq_stage_ticks(int RW) { return max(1, min(64, SEQ_STAGE_BYTES / (SEQ_EPW * RW * 4))); }
+__host__ __device__ inline size_t seq_warp_bytes(int RW, int L) {
+    return ((((size_t)RW * SEQ_EPW + (size_t)L * SEQ_THREADS) * 4 + 15) & ~(size_t)15) + (size_t)seq_stage_ticks(RW) * SEQ_EPW * RW * 4 +
+           (size_t)seq_stage_ticks(RW) * SEQ_EPW * 4 + SEQ_EPW * 4;
 }
 
 template <int W>
@@ -305,61 +521,68 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
       const uint32_t *__restrict__ cam_vis, uint16_t *__restrict__ grec, uint8_t *__restrict__ fin,
       int32_t *__restrict__ last_t, int do_reset, const uint8_t *__restrict__ mask, int store_heading) {
     extern __shared__ __align__(16) unsigned char smem[];
-    const int tid = threadIdx.x;
-    const int env = blockIdx.x * SEQ_THREADS + tid;
-    if (env >= D.N || !D.env_cached[env]) return;
-    if (do_reset && mask && !mask[env]) { last_t[env] = -1; return; }
-    constexpr int G = VC_MAX_GUARDS;
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x, q = lane >> 2, j = lane & 3;
+    const int env_raw = blockIdx.x * SEQ_EPW + q;
+    const bool exists = env_raw < D.N && D.env_cached[min(env_raw, D.N - 1)];
+    const int env = min(env_raw, D.N - 1);
+    const bool valid = exists && !(do_reset && mask && !mask[env]);   // (an idle quad still takes part in the ballots)
+    if (do_reset && exists && !valid && j == 0) last_t[env] = -1;
     const int R = D.R, C = D.C, N = D.N, RW = D.RW, L = D.L, Kg = D.Kg;
-    // shared-memory planes [word][thread]: wall rows, then per guard the patrol words  row | col << 8 | slot << 16
+    // shared memory: wall rows [word][quad]; patrol words [waypoint][lane]:  row | col << 8 | slot << 16
     // (slot: heading slot taken when LEAVING the waypoint, 255 = unchanged)
-    uint32_t *wall_s = reinterpret_cast<uint32_t *>(smem) + tid;
-    uint32_t *pw_s = wall_s + RW * SEQ_THREADS;
+    uint32_t *wall_s = reinterpret_cast<uint32_t *>(smem) + q;
+    uint32_t *pw_s = reinterpret_cast<uint32_t *>(smem) + RW * SEQ_EPW + lane;
+    uint32_t *cam_s = reinterpret_cast<uint32_t *>(smem + ((((size_t)RW * SEQ_EPW + (size_t)L * SEQ_THREADS) * 4 + 15) & ~(size_t)15));
+    const int TS = seq_stage_ticks(RW);
+    unsigned *rec_s = cam_s + (size_t)TS * SEQ_EPW * RW;          // [tick of the stage][quad]
+    int *init_s = reinterpret_cast<int *>(rec_s + TS * SEQ_EPW);  // [quad] initial distance (-1: quad idle)
+    const int env0 = blockIdx.x * SEQ_EPW, n_here = min(SEQ_EPW, N - env0);   // this warp's envs are contiguous
 
     // ---- load ----
-    const int4 es = *reinterpret_cast<const int4 *>(D.env_s + (size_t)env * 4);
+    const int4 es = valid ? *reinterpret_cast<const int4 *>(D.env_s + (size_t)env * 4) : make_int4(0, 0, 0, 0);
     const int n_cams = es.x, n_guards = es.y;
     const int4 d0 = *reinterpret_cast<const int4 *>(D.env_d + (size_t)env * 8);
     const int4 d1 = *reinterpret_cast<const int4 *>(D.env_d + (size_t)env * 8 + 4);
     EnvRegs E;
     E.r = d0.x & 0xffff; E.c = d0.x >> 16; E.tick = d0.y; E.prev = d0.z; E.init = d0.w;
     E.flags = d1.x & 0xff; E.n_vault = d1.y; E.n_detect = d1.z; E.n_timeout = d1.w;
-    for (int i = 0; i < RW; ++i) wall_s[i * SEQ_THREADS] = D.wall[(size_t)env * RW + i];
-    int gk[G], ghs[G], glen[G], gstp[G], grng[G], gkn[G];   // waypoint, heading slot, path length, stride, range, next waypoint
-    unsigned gw[G], gwn[G], gw0[G];                         // patrol word at gk, at gkn, at waypoint 0
-    const uint16_t *gmask[G];                               // the guard's mask table
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        gk[g] = ghs[g] = gkn[g] = 0; glen[g] = 1; gstp[g] = 0; grng[g] = 0; gw[g] = gwn[g] = gw0[g] = 0; gmask[g] = D.vg_mask;
-        if (g < n_guards) {
-            const size_t o = (size_t)env * Kg + g;
-            const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);   // len, speed, range, num_rays
-            glen[g] = gi.x; gstp[g] = gi.x >= 2 ? py_imod(gi.y, gi.x) : 0; grng[g] = gi.z;
-            gk[g] = D.guard_idx[o];
-            for (int k = 0; k < gi.x; ++k)
-                pw_s[(g * L + k) * SEQ_THREADS] = (unsigned)D.guard_path[(o * L + k) * 2] | ((unsigned)D.guard_path[(o * L + k) * 2 + 1] << 8) |
-                                                  ((unsigned)D.vg_hslot[o * L + k] << 16);
-            // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
-            // state view; it is reported (ERR_STATE) and treated as the default heading.
-            const double h = D.guard_heading[o];
-            int hs = -1;
-            const int nh = D.vg_nh[o];
-            for (int s = 0; s < nh; ++s)
-                if (__double_as_longlong(D.vg_hval[o * (L + 1) + s]) == __double_as_longlong(h)) { hs = s; break; }
-            if (hs < 0) { atomicOr(D.err, ERR_STATE); hs = 0; }
-            ghs[g] = hs;
-            gmask[g] = D.vg_mask + o * L * (size_t)(L + 1) * VC_ROWS;
-            gkn[g] = gk[g] + gstp[g]; if (gkn[g] >= glen[g]) gkn[g] -= glen[g];
-            gw[g] = pw_s[(g * L + gk[g]) * SEQ_THREADS]; gwn[g] = pw_s[(g * L + gkn[g]) * SEQ_THREADS]; gw0[g] = pw_s[(g * L) * SEQ_THREADS];
-        }
+    if (j == 0) init_s[q] = valid ? E.init : -1;
+    for (int i = j; i < RW; i += 4) wall_s[i * SEQ_EPW] = D.wall[(size_t)env * RW + i];
+    // my guard: waypoint, heading slot, path length, stride, range, next waypoint; patrol word at gk, gkn, waypoint 0
+    const bool has_g = valid && j < n_guards;
+    int gk = 0, ghs = 0, glen = 1, gstp = 0, grng = 0, gkn = 0;
+    unsigned gw = 0, gwn = 0, gw0 = 0;
+    const uint16_t *gmask = D.vg_mask;
+    const size_t go = (size_t)env * Kg + j;
+    if (has_g) {
+        const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + go * 4);   // len, speed, range, num_rays
+        glen = gi.x; gstp = gi.x >= 2 ? py_imod(gi.y, gi.x) : 0; grng = gi.z;
+        gk = D.guard_idx[go];
+        for (int k = 0; k < gi.x; ++k)
+            pw_s[k * SEQ_THREADS] = (unsigned)D.guard_path[(go * L + k) * 2] | ((unsigned)D.guard_path[(go * L + k) * 2 + 1] << 8) |
+                                    ((unsigned)D.vg_hslot[go * L + k] << 16);
+        // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
+        // state view; it is reported (ERR_STATE) and treated as the default heading.
+        const double h = D.guard_heading[go];
+        int hs = -1;
+        const int nh = D.vg_nh[go];
+        for (int s = 0; s < nh; ++s)
+            if (__double_as_longlong(D.vg_hval[go * (L + 1) + s]) == __double_as_longlong(h)) { hs = s; break; }
+        if (hs < 0) { atomicOr(D.err, ERR_STATE); hs = 0; }
+        ghs = hs;
+        gmask = D.vg_mask + go * L * (size_t)(L + 1) * VC_ROWS;
+        gkn = gk + gstp; if (gkn >= glen) gkn -= glen;
     }
+    __syncwarp();
+    if (has_g) { gw = pw_s[gk * SEQ_THREADS]; gwn = pw_s[gkn * SEQ_THREADS]; gw0 = pw_s[0]; }
     // wall rows E.r - 1, E.r, E.r + 1 (rows outside the grid block)
     uint32_t ww[3][W];
 #define SEQ_WALL_ROW(dst, row)                                                                                 \
     do {                                                                                                       \
         const int r_ = (row);                                                                                  \
         _Pragma("unroll") for (int w = 0; w < W; ++w)                                                          \
-            (dst)[w] = (r_ >= 0 && r_ < R) ? wall_s[(r_ * W + w) * SEQ_THREADS] : 0xffffffffu;                 \
+            (dst)[w] = (r_ >= 0 && r_ < R) ? wall_s[(r_ * W + w) * SEQ_EPW] : 0xffffffffu;                     \
     } while (0)
 #define SEQ_WALL_AROUND() do { SEQ_WALL_ROW(ww[0], E.r - 1); SEQ_WALL_ROW(ww[1], E.r); SEQ_WALL_ROW(ww[2], E.r + 1); } while (0)
     // would the move (dr, dc) from (E.r, E.c) be accepted (:239-246)?  Uses the register rows only.
@@ -381,19 +604,16 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0;                           \
         E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c); E.init = E.prev;               \
         SEQ_WALL_AROUND();                                                                   \
-        _Pragma("unroll") for (int g = 0; g < G; ++g) {                                      \
-            gk[g] = 0; gw[g] = gw0[g]; gkn[g] = gstp[g];                                     \
-            gwn[g] = pw_s[(g * L + gkn[g]) * SEQ_THREADS];                                   \
-        }                                                                                    \
-    } while (0)
-#define SEQ_RECORD(o_)                                                                                         \
-    do {                                                                                                       \
-        _Pragma("unroll") for (int g = 0; g < G; ++g)                                                          \
-            if (g < n_guards) grec[(o_) * Kg + g] = (uint16_t)(gk[g] | (ghs[g] << 8));                         \
+        gk = 0; gw = gw0; gkn = gstp;                                                        \
+        gwn = has_g ? pw_s[gkn * SEQ_THREADS] : 0u;                                          \
     } while (0)
     if (do_reset) {
-        SEQ_RESET_STATE();
-        fin[env] = 1; SEQ_RECORD((size_t)env); last = 0;
+        if (valid) {
+            SEQ_RESET_STATE();
+            if (j == 0) fin[env] = 1;
+            if (has_g) grec[(size_t)env * Kg + j] = (uint16_t)(gk | (ghs << 8));
+            last = 0;
+        }
         T = 0;
     }
     // actions: four registers used round-robin (slot t & 3 holds tick t and is refilled for tick t + 4 as soon as
@@ -407,19 +627,37 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         if (3 < T) a_q3 = actions[(size_t)3 * N + env];
         if (4 < T) a_q0 = actions[(size_t)4 * N + env];
     }
-    int pre_row = -1;
-    uint32_t pre[W];
-    unsigned pre_g[G], pre_key[G];   // mask row / (waypoint | slot << 8) it was fetched for
-#pragma unroll
-    for (int w = 0; w < W; ++w) pre[w] = 0;
-#pragma unroll
-    for (int g = 0; g < G; ++g) { pre_g[g] = 0; pre_key[g] = 0xffffffffu; }
-    for (int t = 0; t < T; ++t) {
+    unsigned pre_g = 0, pre_key = 0xffffffffu, pre_wr = 0xffffffffu;   // my guard's mask row prefetched for (waypoint | slot << 8, window row)
+    const bool vec_ok = ((((size_t)N * RW * 4) | ((size_t)env0 * RW * 4) | (uintptr_t)cam_vis) & 15) == 0 && ((n_here * RW) & 3) == 0;
+    for (int ts0 = 0; ts0 < T; ts0 += TS) {
+    const int n_st = min(TS, T - ts0);
+    {   // stage the camera rows of ticks [ts0, ts0 + n_st) of this warp's envs: per tick one contiguous run of words
+        const int words = n_here * RW;
+        __syncwarp();
+        if (vec_ok) {
+            const int q4 = words >> 2;
+            for (int tt = 0; tt < n_st; ++tt) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(cam_vis + ((size_t)(ts0 + tt) * N + env0) * RW);
+                uint4 *dst = reinterpret_cast<uint4 *>(cam_s + (size_t)tt * SEQ_EPW * RW);
+                for (int i = lane; i < q4; i += 32) cp_async16(dst + i, src + i);
+            }
+        } else {
+            for (int tt = 0; tt < n_st; ++tt) {
+                const uint32_t *src = cam_vis + ((size_t)(ts0 + tt) * N + env0) * RW;
+                uint32_t *dst = cam_s + (size_t)tt * SEQ_EPW * RW;
+                for (int i = lane; i < words; i += 32) cp_async4(dst + i, src + i);
+            }
+        }
+        cp_async_wait_all();
+        __syncwarp();
+    }
+    // ---- pass A, the chain: per tick only what the NEXT tick depends on; the rest goes into a one-word record ----
+    for (int t = ts0; t < ts0 + n_st; ++t) {
         const size_t o = (size_t)t * N + env;
-        bool rebuilt = false;
-        double rw = 0.0;
-        status = HEIST_ALREADY_DONE;
-        if (!(E.flags & F_DONE)) {   // a done env is not mutated (:232-233)
+        const uint32_t *cam_row = cam_s + ((size_t)(t - ts0) * SEQ_EPW + q) * RW;
+        const bool live = valid && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
+        bool mine = false;   // my share of the verdict: the cameras' (all four lanes agree) or my guard's
+        if (live) {
             // move (:239-246): blocked by the grid edge or a WALL tile
             const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
             if (SEQ_FREE(dr, nc)) {
@@ -434,76 +672,50 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
                 }
             }
             ++n_adv;   // cameras rotate (:251-252): their cones for this tick are cam_vis[t]
-#pragma unroll
-            for (int g = 0; g < G; ++g) {   // Guard.update (security.py:145-159)
-                if (g < n_guards && glen[g] >= 2) {
-                    const int hsl = (gw[g] >> 16) & 255;
-                    if (hsl != 255) ghs[g] = hsl;   // 255: the move is (0, 0), heading unchanged
-                    gk[g] = gkn[g]; gw[g] = gwn[g];
-                    gkn[g] = gk[g] + gstp[g]; if (gkn[g] >= glen[g]) gkn[g] -= glen[g];
-                    gwn[g] = pw_s[(g * L + gkn[g]) * SEQ_THREADS];
-                }
+            if (has_g && glen >= 2) {   // Guard.update (security.py:145-159)
+                const int hsl = (gw >> 16) & 255;
+                if (hsl != 255) ghs = hsl;   // 255: the move is (0, 0), heading unchanged
+                gk = gkn; gw = gwn;
+                gkn = gk + gstp; if (gkn >= glen) gkn -= glen;
+                gwn = pw_s[gkn * SEQ_THREADS];
             }
             // visibility at the Solver's tile: camera cones OR guard cones / own tiles
             uint32_t v[W];
-            const bool hit = E.r == pre_row;
-            if (hit) {
 #pragma unroll
-                for (int w = 0; w < W; ++w) v[w] = pre[w];
-            } else {
-#pragma unroll
-                for (int w = 0; w < W; ++w) v[w] = cam_vis[o * RW + E.r * W + w];
-            }
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if (g < n_guards) {
-                    const int prow = gw[g] & 255, pcol = (gw[g] >> 8) & 255, wr = E.r - (prow - grng[g]);
-                    if (wr >= 0 && wr <= 2 * grng[g]) {
-                        const unsigned bits = (hit && pre_key[g] == (unsigned)(gk[g] | (ghs[g] << 8)))
-                                                  ? pre_g[g] : gmask[g][(gk[g] * (L + 1) + ghs[g]) * VC_ROWS + wr];
-                        fast_or_row<W>(v, bits, pcol - grng[g]);
-                    }
+            for (int w = 0; w < W; ++w) v[w] = cam_row[E.r * W + w];
+            if (has_g) {
+                const int prow = gw & 255, pcol = (gw >> 8) & 255, wr = E.r - (prow - grng);
+                if (wr >= 0 && wr <= 2 * grng) {
+                    const unsigned bits = (pre_key == (unsigned)(gk | (ghs << 8)) && pre_wr == (unsigned)wr)
+                                              ? pre_g : gmask[(gk * (L + 1) + ghs) * VC_ROWS + wr];
+                    fast_or_row<W>(v, bits, pcol - grng);
                 }
             }
-            const bool detected = (v[(W == 2) ? (E.c >> 5) : 0] >> (E.c & 31)) & 1u;
-            // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297)
-            rw = D.reward_step;
+            mine = (v[(W == 2) ? (E.c >> 5) : 0] >> (E.c & 31)) & 1u;
+        }
+        const bool detected = (__ballot_sync(FULL, mine) >> (lane & ~3)) & 0xfu;   // any lane of my quad
+        // record of the tick for pass B: row | col << 7 | distance before the move << 14 | live, detected, vault,
+        // timeout, map rebuilt << 22..26
+        unsigned rec = 0;
+        if (live) {
+            rec = (unsigned)E.r | ((unsigned)E.c << 7) | ((unsigned)E.prev << 14) | SEQ_LIVE;
+            E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
             status = HEIST_RUNNING;
-            const int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
-            rw = __dadd_rn(rw, __dmul_rn((double)(E.prev - curr), 0.1));
-            E.prev = curr;
-            if (curr <= 3 && E.init > 3) rw = __dadd_rn(rw, __dmul_rn(0.05, (double)(3 - curr)));
-            if (detected) {
-                E.flags |= F_DETECTED | F_DONE;
-                rw = __dadd_rn(rw, D.reward_detection);
-                status = HEIST_DETECTED;
-            }
-            if (E.r == D.vault_r && E.c == D.vault_c) {
-                E.flags |= F_VAULT | F_DONE;
-                rw = __dadd_rn(rw, D.reward_vault);
-                status = HEIST_VAULT_REACHED;
-            }
+            if (detected) { E.flags |= F_DETECTED | F_DONE; rec |= SEQ_DET; status = HEIST_DETECTED; }                      // :273-281
+            if (E.r == D.vault_r && E.c == D.vault_c) { E.flags |= F_VAULT | F_DONE; rec |= SEQ_VAULT; status = HEIST_VAULT_REACHED; }   // :284-288
             E.tick += 1;
-            if (E.tick >= D.max_steps) {
-                E.flags |= F_DONE;
-                status = HEIST_TIMEOUT;
-                double cf = __dsub_rn(1.0, __ddiv_rn((double)curr, (double)max(E.init, 1)));
-                if (!(cf > 0.0)) cf = 0.0;
-                rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
-            }
+            if (E.tick >= D.max_steps) { E.flags |= F_DONE; rec |= SEQ_TOUT; status = HEIST_TIMEOUT; }                      // :291-297
             if (status == HEIST_VAULT_REACHED) E.n_vault++;        // training.py:535-540
             else if (status == HEIST_DETECTED) E.n_detect++;
             else if (status == HEIST_TIMEOUT) E.n_timeout++;
-            rebuilt = true;
+            rec |= SEQ_REBUILT;
+        } else status = HEIST_ALREADY_DONE;
+        if (valid) {
+            if (autoreset && (E.flags & F_DONE)) { SEQ_RESET_STATE(); rec |= SEQ_REBUILT; }   // the trainer's `if done: reset()`
+            // the visibility map of tick t is final: tell k_finish how to complete it
+            if (rec & SEQ_REBUILT) { last = t; if (has_g) grec[o * Kg + j] = (uint16_t)(gk | (ghs << 8)); }
+            if (j == 0) rec_s[(t - ts0) * SEQ_EPW + q] = rec;
         }
-        if (reward) reward[o] = (float)rw;
-        if (reward64) reward64[o] = rw;
-        if (done) done[o] = (E.flags & F_DONE) ? 1 : 0;
-        if (status_out) status_out[o] = (uint8_t)status;
-        if (autoreset && (E.flags & F_DONE)) { SEQ_RESET_STATE(); rebuilt = true; }   // the trainer's `if done: reset()`
-        // the visibility map of tick t is final: tell k_finish how to complete it
-        fin[o] = rebuilt ? 1 : 0;
-        if (rebuilt) { last = t; SEQ_RECORD(o); }
         // requests for tick t + 1
         {   // a_cur <- tick t + 1 (slot (t + 1) & 3), then that slot <- tick t + 5
             const bool refill = t + 5 < T;
@@ -515,55 +727,82 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
                 default: a_cur = a_q3; if (refill) a_q3 = *nxt; break;
             }
         }
-        pre_row = -1;
-        if (t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state
-            const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
-            pre_row = SEQ_FREE(dr, nc) ? E.r + dr : E.r;
-#pragma unroll
-            for (int w = 0; w < W; ++w) pre[w] = cam_vis[(o + N) * RW + pre_row * W + w];
-#pragma unroll
-            for (int g = 0; g < G; ++g) {
-                if (g < n_guards) {
-                    int k = gk[g], hs = ghs[g];
-                    unsigned word = gw[g];
-                    if (glen[g] >= 2) {
-                        const int hsl = (word >> 16) & 255;
-                        if (hsl != 255) hs = hsl;
-                        k = gkn[g]; word = gwn[g];
-                    }
-                    pre_key[g] = (unsigned)(k | (hs << 8));
-                    const int wr = pre_row - ((int)(word & 255) - grng[g]);
-                    pre_g[g] = 0;
-                    if (wr >= 0 && wr <= 2 * grng[g]) pre_g[g] = gmask[g][(k * (L + 1) + hs) * VC_ROWS + wr];
-                }
+        pre_key = 0xffffffffu;
+        if (has_g && t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state:
+            const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);   // my guard's mask row there
+            const int nrow = SEQ_FREE(dr, nc) ? E.r + dr : E.r;
+            int k = gk, hs = ghs;
+            unsigned word = gw;
+            if (glen >= 2) {
+                const int hsl = (word >> 16) & 255;
+                if (hsl != 255) hs = hsl;
+                k = gkn; word = gwn;
+            }
+            const int wr = nrow - ((int)(word & 255) - grng);
+            if (wr >= 0 && wr <= 2 * grng) {
+                pre_key = (unsigned)(k | (hs << 8)); pre_wr = (unsigned)wr;
+                pre_g = gmask[(k * (L + 1) + hs) * VC_ROWS + wr];
             }
         }
     }
+    __syncwarp();
+    // ---- pass B, off the chain: rewards and outputs of the stage's ticks, one lane per (tick, env) ----
+    for (int i = lane; i < n_st * SEQ_EPW; i += 32) {
+        const int qq = i & (SEQ_EPW - 1);
+        const int init = init_s[qq];
+        if (init < 0) continue;   // no env / not taking part in this launch
+        const unsigned rec = rec_s[i];
+        const size_t o = (size_t)(ts0 + (i >> 3)) * N + env0 + qq;
+        double rw = 0.0;
+        int st = HEIST_ALREADY_DONE, dn = 1;
+        if (rec & SEQ_LIVE) {
+            // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297): same operations, same order
+            const int r = rec & 127, c = (rec >> 7) & 127, prev = (rec >> 14) & 255;
+            const int curr = abs(r - D.vault_r) + abs(c - D.vault_c);
+            rw = D.reward_step;
+            rw = __dadd_rn(rw, __dmul_rn((double)(prev - curr), 0.1));
+            if (curr <= 3 && init > 3) rw = __dadd_rn(rw, __dmul_rn(0.05, (double)(3 - curr)));
+            st = HEIST_RUNNING;
+            if (rec & SEQ_DET) { rw = __dadd_rn(rw, D.reward_detection); st = HEIST_DETECTED; }
+            if (rec & SEQ_VAULT) { rw = __dadd_rn(rw, D.reward_vault); st = HEIST_VAULT_REACHED; }
+            if (rec & SEQ_TOUT) {
+                st = HEIST_TIMEOUT;
+                double cf = __dsub_rn(1.0, __ddiv_rn((double)curr, (double)max(init, 1)));
+                if (!(cf > 0.0)) cf = 0.0;
+                rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
+            }
+            dn = (rec & (SEQ_DET | SEQ_VAULT | SEQ_TOUT)) ? 1 : 0;
+        }
+        if (reward) reward[o] = (float)rw;
+        if (reward64) reward64[o] = rw;
+        if (done) done[o] = (uint8_t)dn;
+        if (status_out) status_out[o] = (uint8_t)st;
+        fin[o] = (rec & SEQ_REBUILT) ? 1 : 0;
+    }
+    }
 #undef SEQ_RESET_STATE
-#undef SEQ_RECORD
 #undef SEQ_WALL_ROW
 #undef SEQ_WALL_AROUND
 #undef SEQ_FREE
 
     // ---- store ----
-    last_t[env] = last;
-    *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
-    *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =
-        make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
-    for (int k = 0; k < (store_heading ? n_cams : 0); ++k) {   // headings after the camera updates this launch executed
-        const size_t co = (size_t)env * D.Kc + k;              // (otherwise stored by k_heads)
+    if (!valid) return;
+    if (j == 0) {
+        last_t[env] = last;
+        *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
+        *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =
+            make_int4(E.flags | (status << 8), E.n_vault, E.n_detect, E.n_timeout);
+    }
+    for (int k = j; k < (store_heading ? n_cams : 0); k += 4) {   // headings after the camera updates this launch executed
+        const size_t co = (size_t)env * D.Kc + k;                // (otherwise stored by k_heads)
         double h = D.cam_heading[co];
         const double speed = D.cam_f[co * 2 + 1];
         for (int a = 0; a < n_adv; ++a) h = py_mod360(__dadd_rn(h, speed));
         D.cam_heading[co] = h;
     }
-#pragma unroll
-    for (int g = 0; g < G; ++g) {
-        if (g < n_guards) {
-            const size_t go = (size_t)env * Kg + g;
-            D.guard_heading[go] = D.vg_hval[go * (L + 1) + ghs[g]];
-            D.guard_idx[go] = gk[g];
-        }
+    if (has_g) {
+        D.guard_heading[go] = D.vg_hval[go * (L + 1) + ghs];
+        D.guard_idx[go] = gk;
     }
 }
 
