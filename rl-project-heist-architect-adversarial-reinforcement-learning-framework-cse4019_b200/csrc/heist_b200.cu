@@ -19,6 +19,7 @@
 #include "heist_step.cuh"
 #include "heist_cache.cuh"
 #include "heist_fast.cuh"
+#include "heist_walk.cuh"
 #include "heist_stream.cuh"
 
 static thread_local std::string g_err;
@@ -411,6 +412,7 @@ struct FastChunk {
     const int8_t *actions; float *reward; double *reward64; uint8_t *done, *status;
     uint32_t *cam; const double *heads; uint16_t *grec; uint8_t *fin; int32_t *last_t;
     int Tc, autoreset, do_reset, write_traj, store_heading; const uint8_t *mask;
+    float *state;   // fused single tick only: dense (3, R, C) state written by k_walk
 };
 
 static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
@@ -439,8 +441,9 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
 static void launch_walk(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
     const unsigned g2 = (unsigned)((h->N + WALK_WARPS - 1) / WALK_WARPS);
-#define GO(RPL, W) k_walk<RPL, W><<<g2, WALK_WARPS * 32, 0, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
-                                                                c.done, c.status, c.cam, c.write_traj, c.do_reset, c.mask, c.store_heading)
+    const size_t sm = WALK_WARPS * walk_warp_bytes(d.RW, d.Kc);
+#define GO(RPL, W) k_walk<RPL, W><<<g2, WALK_WARPS * 32, sm, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
+                                                                 c.done, c.status, c.cam, c.write_traj, c.do_reset, c.mask, c.store_heading, c.state)
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
@@ -505,13 +508,13 @@ static bool fast_pipelined(const HeistHandle *h, int total, int autoreset, int d
 
 static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
                        uint8_t *done, uint8_t *status, uint32_t *vis_traj, int do_reset, const uint8_t *mask,
-                       cudaStream_t s, const HostIO *io = nullptr) {
+                       cudaStream_t s, const HostIO *io = nullptr, float *state = nullptr) {
     const Dev &d = h->d;
     const size_t N = h->N, NRW = N * d.RW;
     const int total = do_reset ? 1 : T;
     const unsigned gh = (unsigned)((N * d.Kc + 127) / 128);
     FastChunk c;
-    c.autoreset = autoreset; c.do_reset = do_reset; c.write_traj = vis_traj ? 1 : 0; c.mask = mask;
+    c.autoreset = autoreset; c.do_reset = do_reset; c.write_traj = vis_traj ? 1 : 0; c.mask = mask; c.state = nullptr;
 
     // Pipelined: with auto-reset no env is ever left done at a chunk boundary, so the camera headings of the whole
     // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_walk of chunk c.
@@ -637,8 +640,14 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             c.heads = nullptr;
             c.store_heading = 1;
         }
+        if (c.Tc == 1 && !vis_traj) {   // one tick (step, step_observe, reset): cones + tick (+ dense state) fused in k_walk
+            c.cam = nullptr; c.state = state;
+            launch_walk(h, c, s);
+            CUDA_TRY(cudaGetLastError());
+            continue;
+        }
         launch_cam_vis(h, c, s);
-        if (nblk > 1) { launch_seq(h, c, s); launch_finish(h, c, s); }   // many ticks: thread-per-env chain + parallel completion
+        if (nblk > 1) { launch_seq(h, c, s); launch_finish(h, c, s); }   // many ticks: quad-per-env chain + parallel completion
         else launch_walk(h, c, s);                                      // a few ticks: one warp-per-env kernel
         CUDA_TRY(cudaGetLastError());
     }
@@ -651,9 +660,11 @@ static inline bool use_cache(const HeistHandle *h) { return h->mode == HEIST_MOD
 // cache build copies to pinned memory; until that copy has landed (or while `s` is being captured) the answer is yes.
 static bool march_needed(HeistHandle *h, cudaStream_t s) {
     if (!use_cache(h)) return true;
+    // A launch that is being captured into a CUDA graph will be replayed after later set_layouts, whose envs may not
+    // all be covered by the cache: it always carries the ray-march kernel (which exits at once when no env needs it).
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return true; }
     if (h->all_cached < 0) {
-        cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-        if (cudaStreamIsCapturing(s, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) { cudaGetLastError(); return true; }
         if (cudaEventQuery(h->ev_unc) != cudaSuccess) { cudaGetLastError(); return true; }
         h->all_cached = *h->n_unc_host == 0 ? 1 : 0;
     }
@@ -680,12 +691,12 @@ extern "C" int heist_reset(HeistHandle *h, const uint8_t *mask, void *stream) {
 }
 
 static int launch_step(HeistHandle *h, const int8_t *actions, int T, int autoreset, float *reward, double *reward64,
-                       uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s) {
+                       uint8_t *done, uint8_t *status, uint32_t *vis_traj, cudaStream_t s, float *state = nullptr) {
     const int grid = env_blocks(h->N), block = HEIST_WARPS_PER_CTA * 32;
     const bool big = h->d.R > 32, exact = h->mode == HEIST_MODE_EXACT;
     Dev d = h->d;
     d.skip_cached = use_cache(h);
-    if (d.skip_cached) { int rc = launch_fast(h, actions, T, autoreset, reward, reward64, done, status, vis_traj, 0, nullptr, s); if (rc) return rc; }
+    if (d.skip_cached) { int rc = launch_fast(h, actions, T, autoreset, reward, reward64, done, status, vis_traj, 0, nullptr, s, nullptr, state); if (rc) return rc; }
     if (!march_needed(h, s)) return 0;
 #define GO(E, B) k_step_many<E, B><<<grid, block, h->step_smem, s>>>(d, actions, T, autoreset, reward, reward64, done, status, vis_traj)
     if (exact) { if (big) GO(true, true); else GO(true, false); }
@@ -773,11 +784,9 @@ extern "C" int heist_step_many_host(HeistHandle *h, const int8_t *actions_host, 
     return 0;
 }
 
-extern "C" int heist_observe(HeistHandle *h, float *state, void *stream) {
-    if (!h || !state) return fail(-1, "heist_observe: null argument");
-    CUDA_TRY(cudaSetDevice(h->device));
-    const Dev &d = h->d;
-    cudaStream_t s = (cudaStream_t)stream;
+static int launch_observe(HeistHandle *h, float *state, cudaStream_t s, int only_uncached) {
+    Dev d = h->d;
+    d.skip_cached = only_uncached;   // the fused tick has already written the states of the table-driven envs
     if (d.C % 4 == 0 && ((uintptr_t)state & 15) == 0) {
         const int nq = 3 * (d.RC / 4);
         const int bx = (nq + 255) / 256;                     // blocks per env, each <= 256 threads ...
@@ -794,12 +803,25 @@ extern "C" int heist_observe(HeistHandle *h, float *state, void *stream) {
     return 0;
 }
 
+extern "C" int heist_observe(HeistHandle *h, float *state, void *stream) {
+    if (!h || !state) return fail(-1, "heist_observe: null argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    return launch_observe(h, state, (cudaStream_t)stream, 0);
+}
+
 extern "C" int heist_step_observe(HeistHandle *h, const int8_t *actions, int autoreset, float *reward, uint8_t *done,
                                   uint8_t *status, float *state, void *stream) {
     if (!h || !actions || !state) return fail(-1, "heist_step_observe: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    { int rc = launch_step(h, actions, 1, autoreset, reward, nullptr, done, status, nullptr, (cudaStream_t)stream); if (rc) return rc; }
-    return heist_observe(h, state, stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    // Table-driven envs: ONE kernel does the tick, the auto-reset and the dense state (k_walk, fused mode).  A
+    // separate observe pass runs only for ray-marched envs (it exits at once when there are none), or for everything
+    // when the state cannot take 16-byte stores.
+    const bool fused = use_cache(h) && h->d.C % 4 == 0 && ((uintptr_t)state & 15) == 0;
+    const bool others = march_needed(h, s);
+    { int rc = launch_step(h, actions, 1, autoreset, reward, nullptr, done, status, nullptr, s, fused ? state : nullptr); if (rc) return rc; }
+    if (fused && !others) return 0;
+    return launch_observe(h, state, s, fused ? 1 : 0);
 }
 
 extern "C" int heist_expand_states(HeistHandle *h, const uint32_t *vis_bits, const int32_t *pos, const int32_t *env_idx,

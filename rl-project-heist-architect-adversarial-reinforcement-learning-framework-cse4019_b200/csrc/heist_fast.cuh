@@ -22,9 +22,25 @@
 #pragma once
 #include "heist_cache.cuh"
 #include "heist_step.cuh"
-#include "heist_walk.cuh"
 
 #define FAST_WARPS 4
+
+// OR a 16-bit window row (bit i = column col0 + i) into lane-row words
+template <int W>
+__device__ __forceinline__ void fast_or_row(uint32_t (&v)[W], unsigned bits, int col0) {
+    const unsigned long long b = col0 >= 0 ? ((unsigned long long)bits << col0) : ((unsigned long long)bits >> (-col0));
+    v[0] |= (uint32_t)b;
+    if (W == 2) v[W - 1] |= (uint32_t)(b >> 32);
+}
+
+// adv0: camera updates that precede tick 0 of a launch.  A step launch updates the cameras once per tick
+// (environment.py:251-252) -- except that an env which was already done when the launch began spends its first
+// tick on the "already done" early-out (:232-233); a reset launch keeps the headings (:205-208).
+__device__ __forceinline__ int fast_adv0(const Dev &D, int env, int do_reset) {
+    if (do_reset) return 0;
+    return (D.env_d[(size_t)env * 8 + 4] & F_DONE) ? 0 : 1;
+}
+
 #define FAST_TB 8      // ticks per k_cam_vis warp
 
 // Per-camera constants of a k_cam_vis warp (shared memory).
@@ -35,6 +51,20 @@ struct FastCam {
     const uint4 *MK4;       // ... and its window mask: uint4 2g, 2g + 1
     int row, col, range, num_rays, n_gaps, sh;
 };
+
+// Asynchronous global -> shared copies (LDGSTS): fire and forget, no register staging, so a burst of them is one
+// memory round trip instead of one per iteration.
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ void or_and(uint32_t &acc, uint32_t m, uint32_t sel) {   // acc |= m & sel, one LOP3
+    asm("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(acc) : "r"(m), "r"(sel));
+}
 
 __host__ __device__ inline size_t camvis_warp_bytes(int RW, int Kc) {
     return (size_t)Kc * sizeof(FastCam) + (((size_t)RW * 4 + 15) & ~(size_t)15) + (size_t)FAST_TB * Kc * 16;
@@ -124,6 +154,57 @@ __device__ __noinline__ void cam_exact_scan(VcGeo D, const uint32_t *__restrict_
     }
 }
 
+// One (tick, camera) from the tables in global memory: OR of the masks of the gaps that hold a ray -> acc[8]
+// (warp-reduced, i.e. identical in every lane); returns non-zero when a band holds a ray (see cam_exact_scan).
+__device__ __forceinline__ unsigned scan_window(const int2 *__restrict__ P2, const uint4 *__restrict__ MK4, int n_gaps, int s0, int bias,
+                                                int sh, int NR, int lane, uint32_t (&acc)[VC_ROWS / 2]) {
+    constexpr unsigned FULL = 0xffffffffu;
+    int carry = 0;             // rays below the end of the previous gap
+    bool first = s0 > 0;       // the band in front of the first gap looked at lies before the window: no rays
+    unsigned bands = 0;
+#pragma unroll
+    for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
+    for (int g = (s0 >> 1) + lane;; g += 64) {
+        const int g0 = min(g, VC_POINTS / 2 - 1), g1 = min(g + 32, VC_POINTS / 2 - 1);   // padded above n_gaps with a point no ray reaches
+        const int2 p0 = __ldg(P2 + g0), p1 = __ldg(P2 + g1);
+        const uint4 ma0 = __ldg(MK4 + 2 * g0), ma1 = __ldg(MK4 + 2 * g0 + 1), mb0 = __ldg(MK4 + 2 * g1), mb1 = __ldg(MK4 + 2 * g1 + 1);
+        const int lo0 = max(0, min(NR, (p0.x + bias) >> sh)), hi0 = max(0, min(NR, (p0.y + bias) >> sh));
+        const int lo1 = max(0, min(NR, (p1.x + bias) >> sh)), hi1 = max(0, min(NR, (p1.y + bias) >> sh));
+        int ph0 = __shfl_up_sync(FULL, hi0, 1), ph1 = __shfl_up_sync(FULL, hi1, 1);
+        const int c0 = __shfl_sync(FULL, hi0, 31), c1 = __shfl_sync(FULL, hi1, 31);
+        if (lane == 0) { ph0 = first ? lo0 : carry; ph1 = c0; }
+        const uint32_t sel0 = (hi0 > lo0 && g < n_gaps) ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
+        const uint32_t sel1 = (hi1 > lo1 && g + 32 < n_gaps) ? 0xffffffffu : 0u;
+        or_and(acc[0], ma0.x, sel0); or_and(acc[1], ma0.y, sel0); or_and(acc[2], ma0.z, sel0); or_and(acc[3], ma0.w, sel0);
+        or_and(acc[4], ma1.x, sel0); or_and(acc[5], ma1.y, sel0); or_and(acc[6], ma1.z, sel0); or_and(acc[7], ma1.w, sel0);
+        or_and(acc[0], mb0.x, sel1); or_and(acc[1], mb0.y, sel1); or_and(acc[2], mb0.z, sel1); or_and(acc[3], mb0.w, sel1);
+        or_and(acc[4], mb1.x, sel1); or_and(acc[5], mb1.y, sel1); or_and(acc[6], mb1.z, sel1); or_and(acc[7], mb1.w, sel1);
+        bands |= __ballot_sync(FULL, (lo0 > ph0) | (lo1 > ph1));   // bands that hold a ray (rare): marched exactly
+        carry = c1;
+        first = false;
+        if (carry >= NR) break;  // warp-uniform
+    }
+#pragma unroll
+    for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(FULL, acc[i]);
+    return bands;
+}
+
+// lane = grid row (rows lane, lane + 32): OR window row wr of the warp-uniform mask acc (two 16-bit rows per word,
+// window origin (row0, col0), rows 0..nrow) into the lane's row words
+template <int RPL, int W>
+__device__ __forceinline__ void place_rows(const uint32_t (&acc)[VC_ROWS / 2], int row0, int col0, int nrow, int lane, uint32_t (&rows)[RPL][W]) {
+#pragma unroll
+    for (int a = 0; a < RPL; ++a) {
+        const int wr = lane + 32 * a - row0;
+        const uint32_t w01 = (wr & 2) ? acc[1] : acc[0], w23 = (wr & 2) ? acc[3] : acc[2];
+        const uint32_t w45 = (wr & 2) ? acc[5] : acc[4], w67 = (wr & 2) ? acc[7] : acc[6];
+        const uint32_t lo4 = (wr & 4) ? w23 : w01, hi4 = (wr & 4) ? w67 : w45;
+        const uint32_t word = (wr & 8) ? hi4 : lo4;
+        const unsigned bits = (wr & 1) ? (word >> 16) : (word & 0xffffu);
+        if (wr >= 0 && wr <= nrow) fast_or_row<W>(rows[a], bits, col0);
+    }
+}
+
 // Union of the camera cones of one env for FAST_TB consecutive ticks -> out[t][env][RW].
 // One pass = 32 consecutive gaps of a camera's table, lane j = gap g0 + j: it loads the gap's two boundary points
 // (one 8-byte load) and, independently, its 32-byte mask; the ray counts below the two points say whether the gap
@@ -198,61 +279,11 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         bool exact_used = false;
         for (int k = 0; k < n_cams; ++k) {
             const FastCam &Cm = cams[k];
-            const int sh = Cm.sh, NR = Cm.num_rays + 1, n_gaps = Cm.n_gaps;
-            const int bias = ((1 << sh) - 1) - pre_fx[pi + k];   // rays below point p: clamp((p + bias) >> sh, 0, NR)
+            const int bias = ((1 << Cm.sh) - 1) - pre_fx[pi + k];   // rays below point p: clamp((p + bias) >> sh, 0, NR)
             const int s0 = pre_s0[pi + k];
-            const int2 *P2 = Cm.P2;
-            const uint4 *MK4 = Cm.MK4;
-            int carry = 0;             // rays below the end of the previous gap
-            bool first = s0 > 0;       // the band in front of the first gap looked at lies before the window: no rays
-            unsigned bands = 0;
             uint32_t acc[VC_ROWS / 2];
-#pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
-            for (int g = (s0 >> 1) + lane;; g += 64) {
-                const int2 p0 = __ldg(P2 + min(g, VC_POINTS / 2 - 1));        // padded above n_gaps with a point no ray reaches
-                const int2 p1 = __ldg(P2 + min(g + 32, VC_POINTS / 2 - 1));
-                uint4 ma0 = make_uint4(0, 0, 0, 0), ma1 = ma0, mb0 = ma0, mb1 = ma0;
-                if (g < n_gaps) { ma0 = __ldg(MK4 + 2 * g); ma1 = __ldg(MK4 + 2 * g + 1); }
-                if (g + 32 < n_gaps) { mb0 = __ldg(MK4 + 2 * g + 64); mb1 = __ldg(MK4 + 2 * g + 65); }
-                {
-                    const int lo = max(0, min(NR, (p0.x + bias) >> sh)), hi = max(0, min(NR, (p0.y + bias) >> sh));
-                    int ph = __shfl_up_sync(FULL, hi, 1);
-                    if (lane == 0) ph = first ? lo : carry;
-                    carry = __shfl_sync(FULL, hi, 31);
-                    const uint32_t sel = hi > lo ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
-                    acc[0] |= ma0.x & sel; acc[1] |= ma0.y & sel; acc[2] |= ma0.z & sel; acc[3] |= ma0.w & sel;
-                    acc[4] |= ma1.x & sel; acc[5] |= ma1.y & sel; acc[6] |= ma1.z & sel; acc[7] |= ma1.w & sel;
-                    bands |= __ballot_sync(FULL, lo > ph);   // bands that hold a ray (rare): marched exactly below
-                    if (carry >= NR) break;  // warp-uniform
-                }
-                {
-                    const int lo = max(0, min(NR, (p1.x + bias) >> sh)), hi = max(0, min(NR, (p1.y + bias) >> sh));
-                    int ph = __shfl_up_sync(FULL, hi, 1);
-                    if (lane == 0) ph = carry;
-                    carry = __shfl_sync(FULL, hi, 31);
-                    const uint32_t sel = hi > lo ? 0xffffffffu : 0u;
-                    acc[0] |= mb0.x & sel; acc[1] |= mb0.y & sel; acc[2] |= mb0.z & sel; acc[3] |= mb0.w & sel;
-                    acc[4] |= mb1.x & sel; acc[5] |= mb1.y & sel; acc[6] |= mb1.z & sel; acc[7] |= mb1.w & sel;
-                    bands |= __ballot_sync(FULL, lo > ph);
-                    if (carry >= NR) break;
-                }
-                first = false;
-            }
-#pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(FULL, acc[i]);
-            // lane = grid row: window row wr of the (now warp-uniform) mask, two 16-bit rows per word
-            const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
-#pragma unroll
-            for (int a = 0; a < RPL; ++a) {
-                const int wr = lane + 32 * a - row0;
-                const uint32_t w01 = (wr & 2) ? acc[1] : acc[0], w23 = (wr & 2) ? acc[3] : acc[2];
-                const uint32_t w45 = (wr & 2) ? acc[5] : acc[4], w67 = (wr & 2) ? acc[7] : acc[6];
-                const uint32_t lo4 = (wr & 4) ? w23 : w01, hi4 = (wr & 4) ? w67 : w45;
-                const uint32_t word = (wr & 8) ? hi4 : lo4;
-                const unsigned bits = (wr & 1) ? (word >> 16) : (word & 0xffffu);
-                if (wr >= 0 && wr <= nrow) fast_or_row<W>(vis[a], bits, col0);
-            }
+            const unsigned bands = scan_window(Cm.P2, Cm.MK4, Cm.n_gaps, s0, bias, Cm.sh, Cm.num_rays + 1, lane, acc);
+            place_rows<RPL, W>(acc, Cm.row - Cm.range, Cm.col - Cm.range, 2 * Cm.range, lane, vis);
             if (bands) {   // warp-uniform
                 cam_exact_scan(vc_geo(D), D.wall + (size_t)env * D.RW, xvis, &Cm, pre_head[pi + k], s0, bias, lane);
                 exact_used = true;
@@ -294,20 +325,6 @@ __host__ __device__ inline size_t camvis_staged_warp_bytes(int RW, int Kc) {
 __host__ __device__ inline size_t camvis_staged_bytes(int RW, int Kc, int warps) {
     return (size_t)Kc * sizeof(FastCam) + (size_t)CVS_P2 * 8 + (size_t)(VC_POINTS / 2) * 32 +
            (size_t)warps * camvis_staged_warp_bytes(RW, Kc);
-}
-
-// Asynchronous global -> shared copies (LDGSTS): fire and forget, no register staging, so a burst of them is one
-// memory round trip instead of one per iteration.
-__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async4(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
-
-__device__ __forceinline__ void or_and(uint32_t &acc, uint32_t m, uint32_t sel) {   // acc |= m & sel, one LOP3
-    asm("lop3.b32 %0, %0, %1, %2, 0xF8;" : "+r"(acc) : "r"(m), "r"(sel));
 }
 
 // cam_exact_scan for a staged table (same scan, boundary points from shared memory)

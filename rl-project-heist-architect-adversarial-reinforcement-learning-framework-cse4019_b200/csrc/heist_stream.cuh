@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(1024) k_observe_vec4(Dev D, float4 *__restrict
     const int quads = D.RC >> 2;
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= 3 * quads) return;
+    if (D.skip_cached && *D.n_uncached == 0) return;   // only the ray-marched envs are wanted, and there are none
     const int ch = (q >= quads) + (q >= 2 * quads);
     const int cell = (q - ch * quads) << 2;
     const int r = cell / D.C, c = cell - r * D.C;
@@ -32,6 +33,7 @@ __global__ void __launch_bounds__(1024) k_observe_vec4(Dev D, float4 *__restrict
     if (ch == 2) g = *reinterpret_cast<const float4 *>(D.pos_tab + cell);
 #pragma unroll 4
     for (int env = blockIdx.y; env < D.N; env += gridDim.y) {
+        if (D.skip_cached && D.env_cached[env]) continue;
         float4 v;
         if (ch == 0) {  // occupancy = grid.astype(float32) / 5   (:319)
             uchar4 t = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + cell);

@@ -18,33 +18,24 @@
 //   * lane = tick for the per-tick scalars: actions are fetched 32 ticks at a time (lane l holds tick t0 + l) and
 //     reward / done / status are collected the same way and stored once per 32 ticks.
 #pragma once
-#include "heist_cache.cuh"
-#include "heist_step.cuh"
+#include "heist_fast.cuh"
 
 #define WALK_WARPS 4
 #define WALK_PF 2     // camera rows are requested this many ticks ahead
-
-// OR a 16-bit window row (bit i = column col0 + i) into lane-row words
-template <int W>
-__device__ __forceinline__ void fast_or_row(uint32_t (&v)[W], unsigned bits, int col0) {
-    const unsigned long long b = col0 >= 0 ? ((unsigned long long)bits << col0) : ((unsigned long long)bits >> (-col0));
-    v[0] |= (uint32_t)b;
-    if (W == 2) v[W - 1] |= (uint32_t)(b >> 32);
-}
-
-// adv0: camera updates that precede tick 0 of a launch.  A step launch updates the cameras once per tick
-// (environment.py:251-252) -- except that an env which was already done when the launch began spends its first
-// tick on the "already done" early-out (:232-233); a reset launch keeps the headings (:205-208).
-__device__ __forceinline__ int fast_adv0(const Dev &D, int env, int do_reset) {
-    if (do_reset) return 0;
-    return (D.env_d[(size_t)env * 8 + 4] & F_DONE) ? 0 : 1;
+__host__ __device__ inline size_t walk_warp_bytes(int RW, int Kc) {   // fused mode: per-camera constants + exact-ray rows
+    return (((size_t)Kc * sizeof(FastCam) + (size_t)RW * 4) + 15) & ~(size_t)15;
 }
 
 template <int RPL, int W>
 __global__ void __launch_bounds__(WALK_WARPS * 32)
 k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
        double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
-       uint32_t *buf, int write_traj, int do_reset, const uint8_t *__restrict__ mask, int store_heading) {
+       uint32_t *buf, int write_traj, int do_reset, const uint8_t *__restrict__ mask, int store_heading,
+       float *__restrict__ state_out) {
+    // buf == nullptr: FUSED single tick (T <= 1) -- the camera cones of the tick are computed right here from the
+    // cache tables (one launch instead of k_cam_vis + k_walk), the new headings are stored, and, if state_out is
+    // given, the dense (3, R, C) state the policy reads next is written from the registers that hold the finished map.
+    extern __shared__ __align__(16) unsigned char smem[];
     constexpr unsigned FULL = 0xffffffffu;
     constexpr int G = VC_MAX_GUARDS;
     const int lane = threadIdx.x & 31;
@@ -128,13 +119,70 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
         for (int g = 0; g < G; ++g)
             if (g < n_guards) { gk[g] = 0; gw[g] = __shfl_sync(FULL, pw[g], 0); }
     };
+    uint32_t camrows[RPL][W];   // fused mode: the camera cones of the tick
+#pragma unroll
+    for (int a = 0; a < RPL; ++a)
+#pragma unroll
+        for (int w = 0; w < W; ++w) camrows[a][w] = 0u;
+    if (!buf) {
+        // Cameras of a live env rotate once before the cones are cast (:251-252); a reset, or the tick a done env
+        // spends on the "already done" early-out, keeps the headings (:205-208, :232-233).
+        const bool advance = !do_reset && T > 0 && !(E.flags & F_DONE);
+        unsigned char *sp = smem + (size_t)(threadIdx.x >> 5) * walk_warp_bytes(RW, D.Kc);
+        FastCam *cams = reinterpret_cast<FastCam *>(sp);
+        uint32_t *xvis = reinterpret_cast<uint32_t *>(sp + (size_t)D.Kc * sizeof(FastCam));
+        int my_s0 = 0, my_fx = 0;
+        if (lane < n_cams) {
+            const size_t o = (size_t)env * D.Kc + lane;
+            FastCam &Cm = cams[lane];
+            const int16_t *ci = D.cam_i + o * 4;
+            Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
+            double h = D.cam_heading[o];
+            if (advance) { h = py_mod360(__dadd_rn(h, Cm.speed)); D.cam_heading[o] = h; }
+            Cm.h0 = h;
+            Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
+            Cm.dom_lo = D.vc_lo[o];
+            Cm.n_gaps = D.vc_meta[o * 2] >> 1;
+            Cm.sh = D.vc_meta[o * 2 + 1];
+            Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
+            Cm.P2 = reinterpret_cast<const int2 *>(D.vc_p + o * VC_POINTS);
+            Cm.MK4 = reinterpret_cast<const uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
+            const double base = h - Cm.fov * 0.5;
+            const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
+            my_s0 = max(0, (int)D.vc_idx[o * VC_IDX + q] - 1) & ~1;
+            my_fx = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
+        }
+        for (int i = lane; i < RW; i += 32) xvis[i] = 0;
+        __syncwarp();
+        bool exact_used = false;
+        for (int k = 0; k < n_cams; ++k) {
+            const FastCam &Cm = cams[k];
+            const int s0 = __shfl_sync(FULL, my_s0, k);
+            const int bias = ((1 << Cm.sh) - 1) - __shfl_sync(FULL, my_fx, k);
+            uint32_t acc[VC_ROWS / 2];
+            const unsigned bands = scan_window(Cm.P2, Cm.MK4, Cm.n_gaps, s0, bias, Cm.sh, Cm.num_rays + 1, lane, acc);
+            place_rows<RPL, W>(acc, Cm.row - Cm.range, Cm.col - Cm.range, 2 * Cm.range, lane, camrows);
+            if (bands) {   // warp-uniform
+                cam_exact_scan(vc_geo(D), D.wall + (size_t)env * RW, xvis, &Cm, Cm.h0, s0, bias, lane);
+                exact_used = true;
+            }
+        }
+        if (exact_used) {
+            __syncwarp();
+#pragma unroll
+            for (int a = 0; a < RPL; ++a)
+#pragma unroll
+                for (int w = 0; w < W; ++w) { const int r = lane + 32 * a; if (r < R) camrows[a][w] |= xvis[r * W + w]; }
+        }
+        store_heading = 0;   // stored above
+    }
     auto load_rows = [&](uint32_t (&v)[RPL][W], int t) {
 #pragma unroll
         for (int a = 0; a < RPL; ++a)
 #pragma unroll
             for (int w = 0; w < W; ++w) {
                 const int r = lane + 32 * a;
-                v[a][w] = r < R ? buf[((size_t)t * N + env) * RW + r * W + w] : 0u;
+                v[a][w] = !buf ? camrows[a][w] : (r < R ? buf[((size_t)t * N + env) * RW + r * W + w] : 0u);
             }
     };
     auto store_rows = [&](const uint32_t (&v)[RPL][W], int t) {
@@ -244,7 +292,7 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
 #pragma unroll
                     for (int w = 0; w < W; ++w) cur[a][w] = v[a][w];
             }
-            if (write_traj) store_rows(cur, t);   // (a tick spent done without auto-reset keeps the frozen map)
+            if (write_traj && buf) store_rows(cur, t);   // (a tick spent done without auto-reset keeps the frozen map)
             if ((t & 31) == 31 || t == T - 1) {   // lane l: outputs of tick tb + l; then the next group's actions
                 const int tb = t & ~31;
                 if (tb + lane <= t) {
@@ -268,6 +316,46 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
             const int r = lane + 32 * a;
             if (r < R) D.vis[(size_t)env * RW + r * W + w] = cur[a][w];
         }
+    if (state_out) {
+        // HeistEnvironment.get_state_tensor (environment.py:347-374) from the finished map in registers: channel 0 the
+        // tile codes / 5, channel 1 the visibility map, channel 2 Solver +1 / vault -1 (vault wins) + distance
+        // gradient; one float4 (4 cells, C % 4 == 0) per store, same arithmetic as k_observe_vec4.
+        const int quads = D.RC >> 2, vcell = D.vault_r * C + D.vault_c, scell = E.r * C + E.c;
+        float4 *dst = reinterpret_cast<float4 *>(state_out) + (size_t)env * 3 * quads;
+        for (int q0 = 0; q0 < 3 * quads; q0 += 32) {   // (every lane takes every trip: the shuffles below need them all)
+            const int q = q0 + lane;
+            const bool on = q < 3 * quads;
+            const int ch = (q >= quads) + (q >= 2 * quads);
+            const int cell = on ? (q - ch * quads) << 2 : 0;
+            const int r = cell / C, c = cell - r * C;
+            uint32_t word = 0;
+#pragma unroll
+            for (int a = 0; a < RPL; ++a)
+#pragma unroll
+                for (int w2 = 0; w2 < W; ++w2) {
+                    const uint32_t x = __shfl_sync(FULL, cur[a][w2], r & 31);
+                    if ((r >> 5) == a && (c >> 5) == w2) word = x;
+                }
+            if (!on) continue;
+            float4 v;
+            if (ch == 0) {
+                const uchar4 t4 = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + cell);
+                v.x = __fmul_rn((float)t4.x, 0.2f); v.y = __fmul_rn((float)t4.y, 0.2f);
+                v.z = __fmul_rn((float)t4.z, 0.2f); v.w = __fmul_rn((float)t4.w, 0.2f);
+            } else if (ch == 1) {
+                const uint32_t bits = word >> (c & 31);
+                v.x = (float)(bits & 1u); v.y = (float)((bits >> 1) & 1u); v.z = (float)((bits >> 2) & 1u); v.w = (float)((bits >> 3) & 1u);
+            } else {
+                const float4 g = *reinterpret_cast<const float4 *>(D.pos_tab + cell);
+                const float b0 = (cell + 0 == vcell) ? -1.0f : ((cell + 0 == scell) ? 1.0f : 0.0f);
+                const float b1 = (cell + 1 == vcell) ? -1.0f : ((cell + 1 == scell) ? 1.0f : 0.0f);
+                const float b2 = (cell + 2 == vcell) ? -1.0f : ((cell + 2 == scell) ? 1.0f : 0.0f);
+                const float b3 = (cell + 3 == vcell) ? -1.0f : ((cell + 3 == scell) ? 1.0f : 0.0f);
+                v.x = __fadd_rn(b0, g.x); v.y = __fadd_rn(b1, g.y); v.z = __fadd_rn(b2, g.z); v.w = __fadd_rn(b3, g.w);
+            }
+            __stcs(dst + q, v);   // write-once stream
+        }
+    }
     if (lane == 0) {
         *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8) = make_int4(E.r | (E.c << 16), E.tick, E.prev, E.init);
         *reinterpret_cast<int4 *>(D.env_d + (size_t)env * 8 + 4) =

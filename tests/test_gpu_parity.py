@@ -785,6 +785,57 @@ def test_cache_coverage_and_fallback_mix():
     assert env2.cache_stats() == (0, 0)
 
 
+def test_fused_tick_graph_survives_layout_changes():
+    """heist_step_observe is one fused kernel for table-driven envs.  A CUDA graph captured while every env was
+    table-driven must stay correct after a set_layout that leaves some envs to the ray-march (the captured launch
+    carries the ray-march and its observe pass, which exit at once when no env needs them)."""
+    cfg = EnvironmentConfig(max_steps=25)
+    N, T = 32, 40
+    env = BatchedHeistEnv(cfg, N, max_cams=8, max_guards=8, max_path=8)
+
+    def layouts(mixed):
+        lays = []
+        for i in range(N):
+            cams = [{"row": 5, "col": 5 + (i % 7), "fov_angle": 60.0 + i, "heading": 15.0 * i, "rotation_speed": 15.0, "vision_range": 6}]
+            if mixed and i % 3 == 1:   # beyond the cache's range: this env is ray-marched
+                cams.append({"row": 12, "col": 12, "fov_angle": 90.0, "heading": 0.0, "rotation_speed": 15.0, "vision_range": 9})
+            guards = [{"patrol_path": [(15, 3), (15, 4), (15, 5), (14, 5)], "speed": 1, "vision_range": 4, "fov_angle": 90.0}]
+            lays.append(([(8, 8), (8, 9)], cams, guards))
+        return lays
+
+    acts = torch.as_tensor(synthetic.sample_actions(np.random.default_rng(11), T, N)).cuda()
+    a_static = torch.zeros(N, dtype=torch.int8, device="cuda")
+    state = torch.empty((N, 3, 20, 20), dtype=torch.float32, device="cuda")
+    env.set_layout_explicit(layouts(False), budget=np.full(N, 100, np.int32))
+    assert env.cache_stats()[0] == N
+    env.reset()
+    for _ in range(3):   # warm-up: resolves the asynchronous coverage count
+        env.step_observe(a_static, autoreset=True, state_out=state)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        rew, done, status, _ = env.step_observe(a_static, autoreset=True, state_out=state)
+    for mixed in (False, True, False):
+        lays = layouts(mixed)
+        env.set_layout_explicit(lays, budget=np.full(N, 100, np.int32))
+        assert env.cache_stats()[0] == (N - len([i for i in range(N) if i % 3 == 1]) if mixed else N)
+        env.reset()
+        oenvs = []
+        for w, c, gd in lays:
+            e = ho.OracleEnv(20, 20, max_steps=25, budget=100)
+            e.set_layout(w, c, gd)
+            oenvs.append(e)
+        ho.reset_all(oenvs)
+        for t in range(T):
+            a_static.copy_(acts[t])
+            g.replay()
+            ref = ho.rollout(oenvs, acts[t:t + 1].cpu().numpy(), autoreset=True, want_vis=True)
+            assert np.array_equal(rew.cpu().numpy(), ref["reward"][0]) and np.array_equal(status.cpu().numpy(), ref["status"][0]), (mixed, t)
+            assert np.array_equal(u32(env.visibility_bits), ref["vis_bits"][0]), (mixed, t)
+            assert np.array_equal(state.cpu().numpy(), np.stack([e.state_tensor() for e in oenvs])), (mixed, t)
+    env.check_errors()
+
+
 def test_debug_bounds_build_reports_no_out_of_range_access():
     """compute-sanitizer is closed on the GPU pool, so the march is also run from a -DHEIST_DEBUG_BOUNDS build that
     range-checks every cell-map access (tests/sanitizer_small.py: four grid classes, resets, exact-path rays)."""
