@@ -13,6 +13,8 @@
 
 #include <algorithm>
 #include <string>
+#include <utility>
+#include <vector>
 
 #include "heist_common.cuh"
 #include "heist_layout.cuh"
@@ -178,6 +180,56 @@ static cudaError_t upload_nice_table(int device, double deg2rad) {
     return e;
 }
 
+// Tie bands per vision range for k_build_cache (heist_cache.cuh): for every sample distance d = 0.5 j and every
+// rounding tie m + 0.5 with |tie| <= d, the angles at which col + cos(a) d (or row - sin(a) d) is within 2 mu of the
+// tie -- unpadded (start, end) pairs over ray angles [-93, 453], sorted by start.  One set per device for the life of
+// the process.
+static cudaError_t vc_upload_band_tables(int device) {
+    static double2 *tab_dev[64][VC_MAX_RANGE + 1];
+    static int tab_n[64][VC_MAX_RANGE + 1];
+    if (device < 0 || device >= 64) return cudaErrorInvalidDevice;
+    if (!tab_dev[device][1]) {
+        const double rad2deg = 180.0 / 3.14159265358979323846;
+        for (int range = 1; range <= VC_MAX_RANGE; ++range) {
+            std::vector<std::pair<double, double>> v;
+            for (int j = 1; j <= 2 * range; ++j) {
+                const double d = 0.5 * (double)j;
+                for (int mi = -8; mi < 8; ++mi) {
+                    const double tie = (double)mi + 0.5;
+                    if (fabs(tie) > d + VC_MU2) continue;
+                    const double t = tie / d, mu = VC_MU2 / d;
+                    for (int axis = 0; axis < 2; ++axis) {
+                        double c_lo = std::max(-1.0, t - mu), c_hi = std::min(1.0, t + mu);
+                        if (axis) { const double a = -c_hi; c_hi = -c_lo; c_lo = a; }   // dy = -sin(a) = -cos(a - 90)
+                        // cos(a - off) in [c_lo, c_hi]  <=>  a - off in +-[acos(c_hi), acos(c_lo)] + 360 n
+                        const double a_lo = acos(c_hi) * rad2deg, a_hi = acos(c_lo) * rad2deg, off = axis ? 90.0 : 0.0;
+                        for (int sgn = 0; sgn < 2; ++sgn) {
+                            const double b0 = sgn ? off - a_hi : off + a_lo, b1 = sgn ? off - a_lo : off + a_hi;
+                            for (int n = -1; n <= 2; ++n) {
+                                const double s0 = b0 + 360.0 * n, e0 = b1 + 360.0 * n;
+                                if (e0 < -93.0 || s0 > 453.0) continue;
+                                v.push_back(std::make_pair(s0, e0));
+                            }
+                        }
+                    }
+                }
+            }
+            std::sort(v.begin(), v.end());
+            std::vector<double2> h2(v.size());
+            for (size_t i = 0; i < v.size(); ++i) { h2[i].x = v[i].first; h2[i].y = v[i].second; }
+            double2 *dev = nullptr;
+            cudaError_t e = cudaMalloc(&dev, sizeof(double2) * h2.size());
+            if (e == cudaSuccess) e = cudaMemcpy(dev, h2.data(), sizeof(double2) * h2.size(), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { if (dev) cudaFree(dev); return e; }
+            tab_dev[device][range] = dev;
+            tab_n[device][range] = (int)h2.size();
+        }
+    }
+    cudaError_t e = cudaMemcpyToSymbol(c_vcb_tab, tab_dev[device], sizeof(tab_dev[device]));
+    if (e == cudaSuccess) e = cudaMemcpyToSymbol(c_vcb_n, tab_n[device], sizeof(tab_n[device]));
+    return e;
+}
+
 extern "C" int heist_create(const HeistParams *params, int num_envs, int device, HeistHandle **out) {
     if (!params || !out) return fail(-1, "heist_create: null argument");
     const HeistParams &p = *params;
@@ -263,6 +315,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
 #undef A
 
     CUDA_TRY_H(upload_nice_table(device, d.deg2rad));
+    CUDA_TRY_H(vc_upload_band_tables(device));
 
     h->step_smem = cta_smem_bytes(d.R, d.C, d.Kc, d.Kg);
     h->camvis_smem = FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc);

@@ -38,6 +38,13 @@
 #define VC_PAD 1e-9           // angular padding on each side of a band (degrees)
 #define VC_BUILD_THREADS 128
 
+// Tie bands per vision range (index = range 1 .. VC_MAX_RANGE), WITHOUT padding, over ray angles [-91, 451] degrees,
+// sorted by start: (start, end) pairs built once per device by the host at heist_create (vc_upload_band_tables in
+// heist_b200.cu).  The bands of a camera are this list cut to its angle domain and padded: the positions of the
+// rounding ties depend on the sample distances only, not on the layout -- so no per-layout acos and no sort.
+__constant__ const double2 *c_vcb_tab[VC_MAX_RANGE + 1];
+__constant__ int c_vcb_n[VC_MAX_RANGE + 1];
+
 #define RINT_MAGIC_C 6755399441055744.0  // 2^52 + 2^51
 __device__ __forceinline__ int vc_rint_even(double x) { return __double2loint(__dadd_rn(x, RINT_MAGIC_C)); }
 
@@ -69,20 +76,23 @@ __device__ __forceinline__ void vc_ray(const VcGeo &D, const uint32_t *__restric
     }
 }
 
-// Same march for a given direction angle (the representative of a gap).
+// Same march for the representative angle of a gap.  Inside a gap every sample of a ray stays at least mu = 4e-12
+// tile away from every rounding tie, whatever the last bits of cos / sin, so any evaluation that is accurate to
+// ~1e-13 gives the tiles the reference's arithmetic gives: sincospi (exact argument reduction, no slow path).
 template <typename Mark>
 __device__ __forceinline__ void vc_ray_angle(const VcGeo &D, const uint32_t *__restrict__ wall, int row, int col,
                                              double angle_deg, int nsamp, double unit, Mark mark) {
-    double dx, dy;
-    ray_dir(angle_deg, D.deg2rad, dx, dy);
+    double s, c;
+    sincospi(angle_deg * (1.0 / 180.0), &s, &c);
+    const double dx = c, dy = -s;
     const double dcol = (double)col, drow = (double)row;
     double dist = unit;
     for (int j = 1; j <= nsamp; ++j, dist += unit) {
-        const int c = vc_rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
+        const int cc = vc_rint_even(__dadd_rn(dcol, __dmul_rn(dx, dist)));
         const int r = vc_rint_even(__dadd_rn(drow, __dmul_rn(dy, dist)));
-        if (r < 0 || r >= D.R || c < 0 || c >= D.C) return;
-        if ((wall[r * D.W + (c >> 5)] >> (c & 31)) & 1u) return;
-        mark(r, c);
+        if (r < 0 || r >= D.R || cc < 0 || cc >= D.C) return;
+        if ((wall[r * D.W + (cc >> 5)] >> (cc & 31)) & 1u) return;
+        mark(r, cc);
     }
 }
 
@@ -96,23 +106,64 @@ __device__ __forceinline__ bool vc_guard_cacheable(double fov, int range, int nu
 }
 
 struct VcSmem {
-    double key[VC_RAW];   // band starts (sorted), later the merged boundary points
-    double end[VC_RAW];   // band ends
+    double key[VC_RAW];   // merged band starts (sorted)
+    double end[VC_RAW];   // ... and ends
+    unsigned first_flag[VC_BUILD_THREADS];   // merge scan: does the thread's first position open a band
+    unsigned short first_pos[VC_RAW];        // ... first position of merged band i
     uint4 gm[VC_POINTS / 2][2];       // gap masks before compaction
-    unsigned short members[VC_RAW];   // raw bands merged into band i
+    unsigned short members[VC_RAW];   // 1: merged band i comes from a single raw band (one tie crossing)
     unsigned short newidx[VC_RAW];    // band i -> index after dropping redundant bands (0xffff: dropped)
     unsigned mask[VC_ROWS];
+    uint32_t wall[HEIST_MAX_DIM * 2];   // the env's wall rows
+    double red_d[VC_BUILD_THREADS / 32];
+    int red_i[VC_BUILD_THREADS / 32];
     int n_raw, n_bands, ok;
 };
 
+// (j, tie) pairs with |tie| <= 0.5 * j: the tie crossings a sample at distance 0.5 * j can have (j = 1 .. 14)
+#define VC_MAX_ITEMS (2 * (1 + 1 + 2 + 2 + 3 + 3 + 4 + 4 + 5 + 5 + 6 + 6 + 7 + 7))
+__device__ __forceinline__ int vc_ties_upto(int j) {   // pairs with sample index < j:  sum_{i<j} 2 * ((i + 1) / 2)
+    const int h = (j - 1) >> 1;             // full (odd, even) couples below j
+    return 2 * (h * (h + 1)) + (((j - 1) & 1) ? 2 * (h + 1) : 0);
+}
+
+// block-wide EXCLUSIVE scans over VC_BUILD_THREADS threads (4 warps); `total` receives the reduction over all threads
+__device__ __forceinline__ double vc_block_exscan_max(double v, double *red, int tid) {
+    double inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const double u = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc = fmax(inc, u); }
+    double ex = __shfl_up_sync(0xffffffffu, inc, 1);
+    if ((tid & 31) == 0) ex = -1e308;
+    if ((tid & 31) == 31) red[tid >> 5] = inc;
+    __syncthreads();
+    for (int w = 0; w < (tid >> 5); ++w) ex = fmax(ex, red[w]);
+    __syncthreads();
+    return ex;
+}
+__device__ __forceinline__ int vc_block_exscan_sum(int v, int *red, int tid, int &total) {
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, inc, o); if ((tid & 31) >= o) inc += u; }
+    int ex = inc - v;
+    if ((tid & 31) == 31) red[tid >> 5] = inc;
+    __syncthreads();
+    total = 0;
+    for (int w = 0; w < VC_BUILD_THREADS / 32; ++w) { if (w < (tid >> 5)) ex += red[w]; total += red[w]; }
+    __syncthreads();
+    return ex;
+}
+
 // One CTA per env: tables of all its cameras and guards.  Launched after every k_set_layout.
-__global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
+__global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
     __shared__ VcSmem S;
     const int env = blockIdx.x, tid = threadIdx.x;
     const int n_cams = D.env_s[(size_t)env * 4 + 0], n_guards = D.env_s[(size_t)env * 4 + 1];
-    const uint32_t *wall = D.wall + (size_t)env * D.RW;
+    for (int i = tid; i < D.RW; i += VC_BUILD_THREADS) S.wall[i] = D.wall[(size_t)env * D.RW + i];
+    __syncthreads();
+    const uint32_t *wall = S.wall;
     const VcGeo geo = vc_geo(D);
     bool env_ok = n_guards <= VC_MAX_GUARDS;
+    constexpr int PER = VC_RAW / VC_BUILD_THREADS;   // sorted positions per thread in the merge scan
 
     for (int k = 0; k < n_cams; ++k) {
         const size_t o = (size_t)env * D.Kc + k;
@@ -129,72 +180,79 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
         const int sh = max(0, min(24, 28 - ilogb((dom_hi - dom_lo) * inv_step)));
         const double fx_scale = inv_step * (double)(1 << sh);
         const double pad = VC_PAD + 4.0 / fx_scale;
-        if (tid == 0) {
-            S.n_raw = 2; S.ok = 1;
-            S.key[0] = -1e300; S.end[0] = dom_lo;   // everything outside the domain is one band on each side:
-            S.key[1] = dom_hi; S.end[1] = 1e300;    // rays there (odd initial headings) take the exact path
+        // ---- 1. bands: the per-range list (sorted by start), cut to the domain, padded; everything outside the domain
+        // is one band on each side (rays there -- odd initial headings -- take the exact path) ----
+        const double2 *T = c_vcb_tab[range];
+        const int nT = c_vcb_n[range];
+        int i0, n_raw;
+        {   // candidates: starts in [dom_lo - 2, dom_hi + 2] (no band is wider than 1e-3 degree)
+            int lo = 0, hi = nT;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (T[m].x < dom_lo - 2.0) lo = m + 1; else hi = m; }
+            i0 = lo;
+            hi = nT;
+            while (lo < hi) { const int m = (lo + hi) >> 1; if (T[m].x <= dom_hi + 2.0) lo = m + 1; else hi = m; }
+            n_raw = lo - i0 + 2;   // + the two outside bands
         }
-        __syncthreads();
-        // ---- 1. bands: item = (sample j, axis, tie m + 0.5, mirror sign) x 4 periods ----
-        const int M = 2 * (VC_MAX_RANGE + 1);
-        const int items = nsamp * 2 * M * 2;
-        const double rad2deg = 180.0 / 3.14159265358979323846;
-        for (int it = tid; it < items; it += VC_BUILD_THREADS) {
-            const int sgn = it & 1, mi = (it >> 1) % M, ja = (it >> 1) / M, axis = ja & 1, j = (ja >> 1) + 1;
-            const double d = 0.5 * (double)j;
-            const double tie = (double)(mi - M / 2) + 0.5;
-            if (fabs(tie) > d + VC_MU2) continue;
-            const double t = tie / d, mu = VC_MU2 / d;
-            double c_lo = fmax(-1.0, t - mu), c_hi = fmin(1.0, t + mu);
-            if (axis) { const double a = -c_hi; c_hi = -c_lo; c_lo = a; }  // dy = -sin(a) = -cos(a - 90)
-            // cos(a - off) in [c_lo, c_hi]  <=>  a - off in +-[acos(c_hi), acos(c_lo)] + 360 n
-            const double a_lo = acos(c_hi) * rad2deg, a_hi = acos(c_lo) * rad2deg;
-            const double off = axis ? 90.0 : 0.0;
-            const double b0 = sgn ? off - a_hi : off + a_lo, b1 = sgn ? off - a_lo : off + a_hi;
-            for (int n = -1; n <= 2; ++n) {
-                const double s = b0 + 360.0 * n - pad, e = b1 + 360.0 * n + pad;
-                if (e < dom_lo || s > dom_hi) continue;
-                const int slot = atomicAdd(&S.n_raw, 1);
-                if (slot < VC_RAW) { S.key[slot] = s; S.end[slot] = e; }
-                else S.ok = 0;
-            }
-        }
-        __syncthreads();
-        bool ok = S.ok != 0;
-        const int n_raw = min(S.n_raw, VC_RAW);
-        // ---- 2. bitonic sort by start, then merge overlaps ----
-        int n_sort = 64;   // sort only as many slots as there are bands (next power of two)
-        while (n_sort < n_raw) n_sort <<= 1;
-        for (int i = n_raw + tid; i < n_sort; i += VC_BUILD_THREADS) { S.key[i] = 2e300; S.end[i] = 2e300; }
-        __syncthreads();
-        for (int size = 2; size <= n_sort; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                for (int i = tid; i < n_sort / 2; i += VC_BUILD_THREADS) {
-                    const int lo = 2 * i - (i & (stride - 1)), hi = lo + stride;
-                    const bool up = (lo & size) == 0;
-                    const double a = S.key[lo], b = S.key[hi];
-                    if ((a > b) == up) {
-                        S.key[lo] = b; S.key[hi] = a;
-                        const double ea = S.end[lo]; S.end[lo] = S.end[hi]; S.end[hi] = ea;
-                    }
+        bool ok = n_raw <= VC_RAW;
+        if (!ok) n_raw = 2;
+        // ---- 2b. merge overlaps, in parallel: with the bands sorted by start, position p opens a new merged band iff its
+        // start exceeds the running maximum of the ends before it (exclusive max-scan); the band index is the running
+        // count of such positions (sum-scan); a band's end is the running maximum at its last position ----
+        int nb0;
+        {
+            double st[PER], en[PER];
+            double mine = -1e308;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int p = tid * PER + u;
+                st[u] = 1e308; en[u] = -1e308;   // (a position without a band never opens one and leaves the maximum alone)
+                if (p == 0) { st[u] = -1e300; en[u] = dom_lo; }
+                else if (p == n_raw - 1) { st[u] = dom_hi; en[u] = 1e300; }
+                else if (p < n_raw) {
+                    const double2 be = T[i0 + p - 1];
+                    const double s = be.x - pad, e = be.y + pad;
+                    if (!(e < dom_lo || s > dom_hi)) { st[u] = s; en[u] = e; }
                 }
-                __syncthreads();
+                mine = fmax(mine, en[u]);
             }
-        }
-        if (tid == 0) {
-            int nb = 0, mem = 1;
-            double cs = S.key[0], ce = S.end[0];
-            for (int i = 1; i < n_raw; ++i) {
-                const double s = S.key[i], e = S.end[i];
-                if (s <= ce) { ce = fmax(ce, e); ++mem; }
-                else { S.key[nb] = cs; S.end[nb] = ce; S.members[nb] = (unsigned short)mem; ++nb; cs = s; ce = e; mem = 1; }
+            __syncthreads();   // (the previous camera's key / end are no longer read)
+            const double before = vc_block_exscan_max(mine, S.red_d, tid);
+            unsigned flags = 0;
+            int cnt = 0;
+            double pm = before;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int p = tid * PER + u;
+                if (p < n_raw && st[u] < 1e308 && (p == 0 || st[u] > pm)) { flags |= 1u << u; ++cnt; }
+                pm = fmax(pm, en[u]);
             }
-            S.key[nb] = cs; S.end[nb] = ce; S.members[nb] = (unsigned short)mem; ++nb;
-            S.n_bands = nb;
+            unsigned *first_flag = S.first_flag;
+            unsigned short *first_pos = S.first_pos;
+            first_flag[tid] = flags & 1u;
+            int total;
+            int bid = vc_block_exscan_sum(cnt, S.red_i, tid, total) - 1;   // band of the position before this thread's first
+            const int bid0 = bid;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int p = tid * PER + u;
+                if (p < n_raw && (flags & (1u << u))) { ++bid; S.key[bid] = st[u]; first_pos[bid] = (unsigned short)p; }
+            }
+            __syncthreads();
+            bid = bid0;
+            pm = before;
+#pragma unroll
+            for (int u = 0; u < PER; ++u) {
+                const int p = tid * PER + u;
+                if (p >= n_raw) break;
+                if (flags & (1u << u)) ++bid;
+                pm = fmax(pm, en[u]);
+                const bool next_opens = (p + 1 >= n_raw) || (u + 1 < PER ? (flags >> (u + 1)) & 1u : first_flag[tid + 1]);
+                if (next_opens) { S.end[bid] = pm; S.members[bid] = (unsigned short)(p - (int)first_pos[bid] + 1); }
+            }
+            __syncthreads();
+            nb0 = total;   // gap g lies between band g and band g + 1
         }
-        __syncthreads();
-        const int nb0 = S.n_bands;   // gap g lies between band g and band g + 1
-        if (2 * (nb0 - 1) > VC_POINTS) ok = false;
+        if (2 * (nb0 - 1) > VC_POINTS - 2) ok = false;   // (one pair of padding points must remain: the scans rely on it)
         if (!ok) { env_ok = false; if (tid == 0) D.vc_meta[o * 2] = -1; __syncthreads(); continue; }
         // ---- 3. one representative ray per gap -> window mask ----
         for (int g = tid; g < nb0 - 1; g += VC_BUILD_THREADS) {
@@ -216,23 +274,35 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS) k_build_cache(Dev D) {
         // ---- 3b. drop redundant bands.  A band that comes from ONE tie crossing separates two gaps whose tile
         // sequences differ in that one sample only; a ray inside it takes one of the two sequences.  When both
         // gaps mark the same tiles the ray does too, whichever way it rounds: band and gaps merge into one gap.
-        // (Bands merged from several crossings could mix the neighbours' sequences and are kept.)
-        if (tid == 0) {
-            int kept = 1;   // band 0 (left sentinel) stays
-            S.newidx[0] = 0;
-            for (int b = 1; b < nb0; ++b) {
+        // (Bands merged from several crossings could mix the neighbours' sequences and are kept.)  Every band
+        // decides for itself (the test reads the ORIGINAL gap masks); the new indices are a sum-scan of the keepers.
+        {
+            constexpr int PB = (VC_RAW + VC_BUILD_THREADS - 1) / VC_BUILD_THREADS;
+            unsigned keepm = 0;
+            int cnt = 0;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int bnd = tid * PB + u;
+                if (bnd >= nb0) break;
                 bool drop = false;
-                if (b < nb0 - 1 && S.members[b] == 1) {
-                    const uint4 a0 = S.gm[b - 1][0], a1 = S.gm[b - 1][1], c0 = S.gm[b][0], c1 = S.gm[b][1];
+                if (bnd >= 1 && bnd < nb0 - 1 && S.members[bnd] == 1) {
+                    const uint4 a0 = S.gm[bnd - 1][0], a1 = S.gm[bnd - 1][1], c0 = S.gm[bnd][0], c1 = S.gm[bnd][1];
                     drop = a0.x == c0.x && a0.y == c0.y && a0.z == c0.z && a0.w == c0.w && a1.x == c1.x && a1.y == c1.y &&
                            a1.z == c1.z && a1.w == c1.w;
                 }
-                S.newidx[b] = drop ? (unsigned short)0xffff : (unsigned short)kept;
-                if (!drop) ++kept;
+                if (!drop) { keepm |= 1u << u; ++cnt; }
             }
-            S.n_bands = kept;
+            int total;
+            int ni = vc_block_exscan_sum(cnt, S.red_i, tid, total);
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const int bnd = tid * PB + u;
+                if (bnd >= nb0) break;
+                S.newidx[bnd] = (keepm & (1u << u)) ? (unsigned short)ni++ : (unsigned short)0xffff;
+            }
+            if (tid == 0) S.n_bands = total;
+            __syncthreads();
         }
-        __syncthreads();
         const int nb = S.n_bands;
         const int n_points = 2 * (nb - 1);   // p[2g] = end of band g, p[2g+1] = start of band g + 1
         {   // compact bands and gap masks in place (new index <= old index; whole chunk read before it is written)
