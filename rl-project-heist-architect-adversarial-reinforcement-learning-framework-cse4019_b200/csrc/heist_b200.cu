@@ -919,7 +919,15 @@ extern "C" int heist_gae(const float *rew, const float *val, const uint8_t *done
     const float gl = (float)(gamma * gae_lambda);  // self.gamma * self.gae_lambda is a Python double product
     // Columns are the only parallelism (the scan is sequential in t for bit-exactness).  With few columns use
     // one warp per CTA spread over all SMs and a deep load prefetch; with many, wider CTAs and less prefetch.
-    if (n_cols <= 32768)
+    if (n_cols <= 16384 && gae_staged_bytes(T) <= (size_t)200 * 1024) {   // few columns: stage each warp's block in shared memory
+        static size_t attr_set[64];   // largest dynamic shared memory configured so far, per device
+        const size_t sm = gae_staged_bytes(T);
+        if (device >= 0 && device < 64 && sm > attr_set[device]) {
+            CUDA_TRY(cudaFuncSetAttribute(k_gae_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)200 * 1024)));
+            attr_set[device] = (size_t)200 * 1024;
+        }
+        k_gae_staged<<<(n_cols + 31) / 32, 32, sm, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
+    } else if (n_cols <= 32768)
         k_gae<32, 32><<<(n_cols + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
     else if (n_cols <= 131072)
         k_gae<16, 64><<<(n_cols + 63) / 64, 64, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);

@@ -317,9 +317,10 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
 // ticks.  Rows are accumulated per tick in shared memory (lane = grid row).
 // ---------------------------------------------------------------------------------------------
 #define CVS_P2 640     // staged boundary-point pairs: VC_POINTS / 2 real slots + padding a scan can run into
+#define CVS_GPL 8      // gaps a lane takes per pass (4 lanes per tick: 32 consecutive gaps per tick and pass)
 
 __host__ __device__ inline size_t camvis_staged_warp_bytes(int RW, int Kc) {
-    return (size_t)Kc * 8 + (size_t)FAST_TB * Kc * 16 + (((size_t)FAST_TB * RW * 4 + 15) & ~(size_t)15);
+    return (size_t)Kc * 8 + (size_t)FAST_TB * Kc * 16 + (size_t)FAST_TB * 32 + (((size_t)FAST_TB * RW * 4 + 15) & ~(size_t)15);
 }
 #define CVS_MAX_WARPS 8
 __host__ __device__ inline size_t camvis_staged_bytes(int RW, int Kc, int warps) {
@@ -370,6 +371,7 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
     double *pre_head = reinterpret_cast<double *>(sp);  sp += (size_t)FAST_TB * Kc * 8;   // [tick][camera]
     int *pre_s0 = reinterpret_cast<int *>(sp);          sp += (size_t)FAST_TB * Kc * 4;
     int *pre_fx = reinterpret_cast<int *>(sp);          sp += (size_t)FAST_TB * Kc * 4;
+    uint32_t *mask_s = reinterpret_cast<uint32_t *>(sp); sp += (size_t)FAST_TB * 32;      // [tick] window mask of the camera in hand
     uint32_t *vis_s = reinterpret_cast<uint32_t *>(sp);                                    // [tick][RW]
     const int n_cams = D.env_s[(size_t)env * 4];
     if (tid < n_cams) {
@@ -416,68 +418,93 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
             for (int i = tid; i < (n_gaps + 1) / 2; i += nthr) cp_async16(dst + i, src + i);
             for (int i = tid; i < 2 * n_gaps; i += nthr) cp_async16(((i & 1) ? M1s : M0s) + (i >> 1), Cm.MK4 + i);
             // padding a scan can run into: it stops within 64 + 32 gaps of the last real one
-            for (int i = ((n_gaps + 1) & ~1) + tid; i < min(CVS_P2, n_gaps + 128); i += nthr) P2s[i] = make_int2(0x3fffffff, 0x3fffffff);
+            for (int i = ((n_gaps + 1) & ~1) + tid; i < CVS_P2; i += nthr) P2s[i] = make_int2(0x3fffffff, 0x3fffffff);
             cp_async_wait_all();
         }
         __syncthreads();
+        if (!active) continue;   // (no barrier inside: idle warps go straight to the next camera's barrier)
         const int sh = Cm.sh, NR = Cm.num_rays + 1;
         const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
-        for (int tt = 0; tt < n_t; ++tt) {
-            const int bias = ((1 << sh) - 1) - pre_fx[tt * Kc + k];   // rays below point p: clamp((p + bias) >> sh, 0, NR)
-            const int s0 = pre_s0[tt * Kc + k];
-            int carry = 0;             // rays below the end of the previous gap
-            bool first = s0 > 0;       // the band in front of the first gap looked at lies before the window: no rays
-            unsigned bands = 0;
-            uint32_t acc[VC_ROWS / 2];
+        // The scan.  With the table in shared memory, per-lane addressing is cheap, so the warp scans the windows of ALL
+        // its ticks at once: lane = (tick tt, q); in a pass the four lanes of a tick take the gaps gbase + 4 i + q,
+        // i < CVS_GPL (32 consecutive gaps per tick and pass, the four lanes on four neighbouring table entries).  Per
+        // gap: ray counts below its two boundary points from the tick's first-ray position; the gap holds a ray iff
+        // they differ (its 32-byte mask is OR-ed in, branch-free).  Rays inside BANDS are found by counting: every ray
+        // lies either in a gap or in a band, so the bands hold one iff the gaps' counts do not add up to all rays.
+        const int tt = lane >> 2, q = lane & 3;
+        const bool have = tt < n_t;
+        int bias = 0, s0 = 0;
+        if (have) { bias = ((1 << sh) - 1) - pre_fx[tt * Kc + k]; s0 = pre_s0[tt * Kc + k]; }   // rays below point p: clamp((p + bias) >> sh, 0, NR)
+        uint32_t acc[VC_ROWS / 2];
 #pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
-            for (int g = (s0 >> 1) + lane;; g += 64) {
-                const int2 p0 = P2s[g], p1 = P2s[g + 32];
-                const uint4 ma0 = M0s[min(g, VC_POINTS / 2 - 1)], ma1 = M1s[min(g, VC_POINTS / 2 - 1)];
-                const uint4 mb0 = M0s[min(g + 32, VC_POINTS / 2 - 1)], mb1 = M1s[min(g + 32, VC_POINTS / 2 - 1)];
-                const int lo0 = max(0, min(NR, (p0.x + bias) >> sh)), hi0 = max(0, min(NR, (p0.y + bias) >> sh));
-                const int lo1 = max(0, min(NR, (p1.x + bias) >> sh)), hi1 = max(0, min(NR, (p1.y + bias) >> sh));
-                int ph0 = __shfl_up_sync(FULL, hi0, 1), ph1 = __shfl_up_sync(FULL, hi1, 1);
-                const int c0 = __shfl_sync(FULL, hi0, 31), c1 = __shfl_sync(FULL, hi1, 31);
-                if (lane == 0) { ph0 = first ? lo0 : carry; ph1 = c0; }
-                const uint32_t sel0 = hi0 > lo0 ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
-                const uint32_t sel1 = hi1 > lo1 ? 0xffffffffu : 0u;
-                or_and(acc[0], ma0.x, sel0); or_and(acc[1], ma0.y, sel0); or_and(acc[2], ma0.z, sel0); or_and(acc[3], ma0.w, sel0);
-                or_and(acc[4], ma1.x, sel0); or_and(acc[5], ma1.y, sel0); or_and(acc[6], ma1.z, sel0); or_and(acc[7], ma1.w, sel0);
-                or_and(acc[0], mb0.x, sel1); or_and(acc[1], mb0.y, sel1); or_and(acc[2], mb0.z, sel1); or_and(acc[3], mb0.w, sel1);
-                or_and(acc[4], mb1.x, sel1); or_and(acc[5], mb1.y, sel1); or_and(acc[6], mb1.z, sel1); or_and(acc[7], mb1.w, sel1);
-                bands |= __ballot_sync(FULL, (lo0 > ph0) | (lo1 > ph1));   // bands that hold a ray (rare): marched exactly below
-                carry = c1;
-                first = false;
-                if (carry >= NR) break;  // warp-uniform
+        for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
+        int in_gaps = 0;          // rays found inside my gaps (rays below the first gap looked at, or past the last real
+        bool more = have;         //   one, are outside the window start's guarantee / the cached domain: they count as band rays)
+        for (int gbase = s0 >> 1;; gbase += 4 * CVS_GPL) {
+            const int g0 = min(gbase, CVS_P2 - 4 * CVS_GPL) + q;   // (only a finished tick can be clamped)
+            int hi_last = 0;
+#pragma unroll
+            for (int i = 0; i < CVS_GPL; ++i) {
+                const int g = g0 + 4 * i;
+                const int2 p = P2s[g];
+                const uint4 m0 = M0s[min(g, VC_POINTS / 2 - 1)], m1 = M1s[min(g, VC_POINTS / 2 - 1)];
+                const int lo = max(0, min(NR, (p.x + bias) >> sh)), hi = max(0, min(NR, (p.y + bias) >> sh));
+                const int cnt = more ? hi - lo : 0;
+                in_gaps += cnt;
+                const uint32_t sel = cnt > 0 ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
+                or_and(acc[0], m0.x, sel); or_and(acc[1], m0.y, sel); or_and(acc[2], m0.z, sel); or_and(acc[3], m0.w, sel);
+                or_and(acc[4], m1.x, sel); or_and(acc[5], m1.y, sel); or_and(acc[6], m1.z, sel); or_and(acc[7], m1.w, sel);
+                hi_last = hi;
             }
+            const int carry = __shfl_sync(FULL, hi_last, lane | 3);   // rays below the end of the tick's last gap of this pass
+            more = more && carry < NR;
+            if (!__any_sync(FULL, more)) break;
+        }
+        in_gaps += __shfl_xor_sync(FULL, in_gaps, 1);
+        in_gaps += __shfl_xor_sync(FULL, in_gaps, 2);
+        const bool band = have && in_gaps != NR;
+        // the four quarters of a tick -> one mask per tick, in shared memory
 #pragma unroll
-            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = __reduce_or_sync(FULL, acc[i]);
-            // lane = grid row: window row wr of the (now warp-uniform) mask, two 16-bit rows per word
-            uint32_t *rows = vis_s + tt * RW;
+        for (int i = 0; i < VC_ROWS / 2; ++i) {
+            acc[i] |= __shfl_xor_sync(FULL, acc[i], 1);
+            acc[i] |= __shfl_xor_sync(FULL, acc[i], 2);
+        }
+        const unsigned bands = __ballot_sync(FULL, band);
+        if (q == 0) {
+            reinterpret_cast<uint4 *>(mask_s)[tt * 2] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+            reinterpret_cast<uint4 *>(mask_s)[tt * 2 + 1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+        }
+        __syncwarp();
+        // lane = grid row: window row wr of every tick's mask (two 16-bit rows per word) into the tick's row words
+        for (int t2 = 0; t2 < n_t; ++t2) {
+            uint32_t *rows = vis_s + t2 * RW;
+            const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + t2 * VC_ROWS;
 #pragma unroll
             for (int a = 0; a < RPL; ++a) {
                 const int wr = lane + 32 * a - row0;
-                const uint32_t w01 = (wr & 2) ? acc[1] : acc[0], w23 = (wr & 2) ? acc[3] : acc[2];
-                const uint32_t w45 = (wr & 2) ? acc[5] : acc[4], w67 = (wr & 2) ? acc[7] : acc[6];
-                const uint32_t lo4 = (wr & 4) ? w23 : w01, hi4 = (wr & 4) ? w67 : w45;
-                const uint32_t word = (wr & 8) ? hi4 : lo4;
-                const unsigned bits = (wr & 1) ? (word >> 16) : (word & 0xffffu);
-                if (wr >= 0 && wr <= nrow && bits) {
-                    uint32_t v[W];
+                if (wr >= 0 && wr <= nrow) {
+                    const unsigned bits = mrow[wr];
+                    if (bits) {
+                        uint32_t v[W];
 #pragma unroll
-                    for (int w = 0; w < W; ++w) v[w] = 0;
-                    fast_or_row<W>(v, bits, col0);
+                        for (int w = 0; w < W; ++w) v[w] = 0;
+                        fast_or_row<W>(v, bits, col0);
 #pragma unroll
-                    for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                        for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                    }
                 }
             }
-            if (bands) {   // warp-uniform
-                __syncwarp();
-                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, rows, &Cm, P2s, pre_head[tt * Kc + k], s0, bias, lane);
-                __syncwarp();
+        }
+        if (bands) {   // warp-uniform; rare
+            __syncwarp();
+            for (int t2 = 0; t2 < n_t; ++t2) {
+                if (!((bands >> (4 * t2)) & 0xfu)) continue;
+                const int b2 = ((1 << sh) - 1) - pre_fx[t2 * Kc + k];
+                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2s, pre_head[t2 * Kc + k],
+                                      pre_s0[t2 * Kc + k], b2, lane);
             }
         }
+        __syncwarp();
     }
     __syncwarp();
     {
