@@ -534,7 +534,7 @@ struct HostIO {
     const int8_t *actions; float *reward; uint8_t *done, *status;
 };
 
-#define FAST_PIPE_BLOCKS 5     // tick blocks (of FAST_TB ticks) per pipelined chunk, at most
+#define FAST_PIPE_BLOCKS 7     // tick blocks (of FAST_TB ticks) per pipelined chunk, at most
 #define FAST_PIPE_MAX 64       // chunks (events) per launch
 
 // A pipelined launch of `total` ticks is cut into n chunks of (almost) equal numbers of whole tick blocks, at most

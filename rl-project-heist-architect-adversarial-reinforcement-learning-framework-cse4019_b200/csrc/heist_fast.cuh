@@ -555,7 +555,7 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
 __host__ __device__ inline int seq_stage_ticks(int RW) { return max(1, min(64, SEQ_STAGE_BYTES / (SEQ_EPW * RW * 4))); }
 __host__ __device__ inline size_t seq_warp_bytes(int RW, int L) {
     return ((((size_t)RW * SEQ_EPW + (size_t)L * SEQ_THREADS) * 4 + 15) & ~(size_t)15) + (size_t)seq_stage_ticks(RW) * SEQ_EPW * RW * 4 +
-           (size_t)seq_stage_ticks(RW) * SEQ_EPW * 4 + SEQ_EPW * 4;
+           (size_t)seq_stage_ticks(RW) * SEQ_EPW * 4 + SEQ_EPW * 4 + (((size_t)seq_stage_ticks(RW) * SEQ_EPW + 15) & ~(size_t)15);
 }
 
 template <int W>
@@ -581,6 +581,7 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     const int TS = seq_stage_ticks(RW);
     unsigned *rec_s = cam_s + (size_t)TS * SEQ_EPW * RW;          // [tick of the stage][quad]
     int *init_s = reinterpret_cast<int *>(rec_s + TS * SEQ_EPW);  // [quad] initial distance (-1: quad idle)
+    int8_t *act_s = reinterpret_cast<int8_t *>(init_s + SEQ_EPW);  // [tick of the stage][quad] actions
     const int env0 = blockIdx.x * SEQ_EPW, n_here = min(SEQ_EPW, N - env0);   // this warp's envs are contiguous
 
     // ---- load ----
@@ -620,62 +621,40 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     }
     __syncwarp();
     if (has_g) { gw = pw_s[gk * SEQ_THREADS]; gwn = pw_s[gkn * SEQ_THREADS]; gw0 = pw_s[0]; }
-    // wall rows E.r - 1, E.r, E.r + 1 (rows outside the grid block)
-    uint32_t ww[3][W];
-#define SEQ_WALL_ROW(dst, row)                                                                                 \
-    do {                                                                                                       \
-        const int r_ = (row);                                                                                  \
-        _Pragma("unroll") for (int w = 0; w < W; ++w)                                                          \
-            (dst)[w] = (r_ >= 0 && r_ < R) ? wall_s[(r_ * W + w) * SEQ_EPW] : 0xffffffffu;                     \
-    } while (0)
-#define SEQ_WALL_AROUND() do { SEQ_WALL_ROW(ww[0], E.r - 1); SEQ_WALL_ROW(ww[1], E.r); SEQ_WALL_ROW(ww[2], E.r + 1); } while (0)
-    // would the move (dr, dc) from (E.r, E.c) be accepted (:239-246)?  Uses the register rows only.
-    auto wall_word = [&](int dr, int nc) -> uint32_t {   // selects, not indexing: the rows stay in registers
-        uint32_t lo = dr < 0 ? ww[0][0] : (dr > 0 ? ww[2][0] : ww[1][0]);
-        if (W == 2) { const uint32_t hi = dr < 0 ? ww[0][W - 1] : (dr > 0 ? ww[2][W - 1] : ww[1][W - 1]); if (nc >> 5) lo = hi; }
-        return lo;
+    // Pass A below is written branch-free (selects and predicated loads / stores): the quads of a warp are in
+    // different situations every tick, and every divergent branch would put both of its sides -- plus the
+    // reconvergence bookkeeping -- on the one dependency chain this kernel consists of.
+    const unsigned gw_reset_next = has_g ? pw_s[gstp * SEQ_THREADS] : 0u;   // patrol word after the first move from waypoint 0
+    const int start_dist = abs(D.start_r - D.vault_r) + abs(D.start_c - D.vault_c);
+    // is (nr, nc) inside the grid and not a WALL tile (:242-245)?  One shared-memory word.
+    auto free_tile = [&](int nr, int nc) -> bool {
+        const bool inb = (unsigned)nr < (unsigned)R && (unsigned)nc < (unsigned)C;
+        const int rr = inb ? nr : 0, cc = inb ? nc : 0;
+        const uint32_t word = wall_s[(rr * W + (W == 2 ? (cc >> 5) : 0)) * SEQ_EPW];
+        return inb && !((word >> (cc & 31)) & 1u);
     };
-#define SEQ_FREE(dr, nc) ((nc) >= 0 && (nc) < C && !((wall_word((dr), (nc)) >> ((nc) & 31)) & 1u))
-    SEQ_WALL_AROUND();
 
     int status = HEIST_RUNNING;
     int n_adv = 0;           // camera updates executed by this launch
     int last = -1;           // last tick of this launch whose visibility map was rebuilt
-    // HeistEnvironment.reset (environment.py:183-214): headings persist, guards back to waypoint 0.  The map after a
-    // reset is completed by k_finish from the recorded guard state; nothing is detected on a reset.
-#define SEQ_RESET_STATE()                                                                    \
-    do {                                                                                     \
-        E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0;                           \
-        E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c); E.init = E.prev;               \
-        SEQ_WALL_AROUND();                                                                   \
-        gk = 0; gw = gw0; gkn = gstp;                                                        \
-        gwn = has_g ? pw_s[gkn * SEQ_THREADS] : 0u;                                          \
-    } while (0)
     if (do_reset) {
+        // HeistEnvironment.reset (environment.py:183-214): headings persist, guards back to waypoint 0.  The map after
+        // a reset is completed by k_finish from the recorded guard state; nothing is detected on a reset.
         if (valid) {
-            SEQ_RESET_STATE();
+            E.r = D.start_r; E.c = D.start_c; E.tick = 0; E.flags = 0; E.prev = start_dist; E.init = start_dist;
+            gk = 0; gw = gw0; gkn = gstp; gwn = gw_reset_next;
             if (j == 0) fin[env] = 1;
             if (has_g) grec[(size_t)env * Kg + j] = (uint16_t)(gk | (ghs << 8));
             last = 0;
         }
         T = 0;
     }
-    // actions: four registers used round-robin (slot t & 3 holds tick t and is refilled for tick t + 4 as soon as
-    // it has been read: no register is read in the iteration that follows its load -- they stream from HBM, one new
-    // sector per tick, and a load takes longer than a tick)
-    int a_cur = 0, a_q0 = 0, a_q1 = 0, a_q2 = 0, a_q3 = 0;
-    if (T > 0) {
-        a_cur = actions[env];
-        if (1 < T) a_q1 = actions[(size_t)1 * N + env];
-        if (2 < T) a_q2 = actions[(size_t)2 * N + env];
-        if (3 < T) a_q3 = actions[(size_t)3 * N + env];
-        if (4 < T) a_q0 = actions[(size_t)4 * N + env];
-    }
-    unsigned pre_g = 0, pre_key = 0xffffffffu, pre_wr = 0xffffffffu;   // my guard's mask row prefetched for (waypoint | slot << 8, window row)
     const bool vec_ok = ((((size_t)N * RW * 4) | ((size_t)env0 * RW * 4) | (uintptr_t)cam_vis) & 15) == 0 && ((n_here * RW) & 3) == 0;
+    const bool act_vec = (((size_t)N | (size_t)env0 | (uintptr_t)actions) & 3) == 0 && n_here == SEQ_EPW;
+    const bool moving = has_g && glen >= 2;
     for (int ts0 = 0; ts0 < T; ts0 += TS) {
     const int n_st = min(TS, T - ts0);
-    {   // stage the camera rows of ticks [ts0, ts0 + n_st) of this warp's envs: per tick one contiguous run of words
+    {   // stage the camera rows and the actions of ticks [ts0, ts0 + n_st) of this warp's (contiguous) envs
         const int words = n_here * RW;
         __syncwarp();
         if (vec_ok) {
@@ -692,6 +671,13 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
                 for (int i = lane; i < words; i += 32) cp_async4(dst + i, src + i);
             }
         }
+        if (act_vec) {   // 8 action bytes per tick = two words
+            for (int i = lane; i < n_st * 2; i += 32)
+                cp_async4(reinterpret_cast<uint32_t *>(act_s) + i, actions + (size_t)(ts0 + (i >> 1)) * N + env0 + 4 * (i & 1));
+        } else {
+            for (int i = lane; i < n_st * SEQ_EPW; i += 32)
+                act_s[i] = (i & (SEQ_EPW - 1)) < n_here ? actions[(size_t)(ts0 + (i >> 3)) * N + env0 + (i & (SEQ_EPW - 1))] : (int8_t)0;
+        }
         cp_async_wait_all();
         __syncwarp();
     }
@@ -699,95 +685,63 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     for (int t = ts0; t < ts0 + n_st; ++t) {
         const size_t o = (size_t)t * N + env;
         const uint32_t *cam_row = cam_s + ((size_t)(t - ts0) * SEQ_EPW + q) * RW;
+        const int a_cur = act_s[(t - ts0) * SEQ_EPW + q];
         const bool live = valid && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
-        bool mine = false;   // my share of the verdict: the cameras' (all four lanes agree) or my guard's
-        if (live) {
-            // move (:239-246): blocked by the grid edge or a WALL tile
-            const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
-            if (SEQ_FREE(dr, nc)) {
-                E.c = nc;
-                if (dr) {   // rows shift by one; the new outer row is only needed from the next tick on
-                    E.r += dr;
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        if (dr > 0) { ww[0][w] = ww[1][w]; ww[1][w] = ww[2][w]; } else { ww[2][w] = ww[1][w]; ww[1][w] = ww[0][w]; }
-                    }
-                    if (dr > 0) SEQ_WALL_ROW(ww[2], E.r + 1); else SEQ_WALL_ROW(ww[0], E.r - 1);
-                }
-            }
-            ++n_adv;   // cameras rotate (:251-252): their cones for this tick are cam_vis[t]
-            if (has_g && glen >= 2) {   // Guard.update (security.py:145-159)
-                const int hsl = (gw >> 16) & 255;
-                if (hsl != 255) ghs = hsl;   // 255: the move is (0, 0), heading unchanged
-                gk = gkn; gw = gwn;
-                gkn = gk + gstp; if (gkn >= glen) gkn -= glen;
-                gwn = pw_s[gkn * SEQ_THREADS];
-            }
-            // visibility at the Solver's tile: camera cones OR guard cones / own tiles
-            uint32_t v[W];
-#pragma unroll
-            for (int w = 0; w < W; ++w) v[w] = cam_row[E.r * W + w];
-            if (has_g) {
-                const int prow = gw & 255, pcol = (gw >> 8) & 255, wr = E.r - (prow - grng);
-                if (wr >= 0 && wr <= 2 * grng) {
-                    const unsigned bits = (pre_key == (unsigned)(gk | (ghs << 8)) && pre_wr == (unsigned)wr)
-                                              ? pre_g : gmask[(gk * (L + 1) + ghs) * VC_ROWS + wr];
-                    fast_or_row<W>(v, bits, pcol - grng);
-                }
-            }
-            mine = (v[(W == 2) ? (E.c >> 5) : 0] >> (E.c & 31)) & 1u;
+        // move (:239-246): blocked by the grid edge or a WALL tile
+        const int nr = E.r + (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
+        const bool go_there = live && free_tile(nr, nc);
+        E.r = go_there ? nr : E.r;
+        E.c = go_there ? nc : E.c;
+        n_adv += live;   // cameras rotate (:251-252): their cones for this tick are cam_vis[t]
+        {   // Guard.update (security.py:145-159)
+            const bool adv = live && moving;
+            const int hsl = (gw >> 16) & 255;
+            ghs = (adv && hsl != 255) ? hsl : ghs;   // 255: the move is (0, 0), heading unchanged
+            gk = adv ? gkn : gk;
+            gw = adv ? gwn : gw;
+            int k2 = gk + gstp;
+            k2 = k2 >= glen ? k2 - glen : k2;
+            gkn = adv ? k2 : gkn;
+            gwn = pw_s[gkn * SEQ_THREADS];
         }
+        // visibility at the Solver's tile: camera cones (all four lanes agree) OR my guard's cone / own tile
+        const uint32_t cw = cam_row[E.r * W + (W == 2 ? (E.c >> 5) : 0)];
+        bool mine = (cw >> (E.c & 31)) & 1u;
+        {
+            const int prow = gw & 255, pcol = (gw >> 8) & 255;
+            const int wr = E.r - (prow - grng), wc = E.c - (pcol - grng);
+            const bool in_win = has_g && (unsigned)wr <= (unsigned)(2 * grng) && (unsigned)wc <= (unsigned)(2 * grng);
+            unsigned bits = 0;
+            if (in_win) bits = __ldg(gmask + (gk * (L + 1) + ghs) * VC_ROWS + wr);
+            mine = mine || ((bits >> (wc & 15)) & 1u);
+        }
+        mine = mine && live;
         const bool detected = (__ballot_sync(FULL, mine) >> (lane & ~3)) & 0xfu;   // any lane of my quad
         // record of the tick for pass B: row | col << 7 | distance before the move << 14 | live, detected, vault,
         // timeout, map rebuilt << 22..26
-        unsigned rec = 0;
-        if (live) {
-            rec = (unsigned)E.r | ((unsigned)E.c << 7) | ((unsigned)E.prev << 14) | SEQ_LIVE;
-            E.prev = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
-            status = HEIST_RUNNING;
-            if (detected) { E.flags |= F_DETECTED | F_DONE; rec |= SEQ_DET; status = HEIST_DETECTED; }                      // :273-281
-            if (E.r == D.vault_r && E.c == D.vault_c) { E.flags |= F_VAULT | F_DONE; rec |= SEQ_VAULT; status = HEIST_VAULT_REACHED; }   // :284-288
-            E.tick += 1;
-            if (E.tick >= D.max_steps) { E.flags |= F_DONE; rec |= SEQ_TOUT; status = HEIST_TIMEOUT; }                      // :291-297
-            if (status == HEIST_VAULT_REACHED) E.n_vault++;        // training.py:535-540
-            else if (status == HEIST_DETECTED) E.n_detect++;
-            else if (status == HEIST_TIMEOUT) E.n_timeout++;
-            rec |= SEQ_REBUILT;
-        } else status = HEIST_ALREADY_DONE;
-        if (valid) {
-            if (autoreset && (E.flags & F_DONE)) { SEQ_RESET_STATE(); rec |= SEQ_REBUILT; }   // the trainer's `if done: reset()`
-            // the visibility map of tick t is final: tell k_finish how to complete it
-            if (rec & SEQ_REBUILT) { last = t; if (has_g) grec[o * Kg + j] = (uint16_t)(gk | (ghs << 8)); }
-            if (j == 0) rec_s[(t - ts0) * SEQ_EPW + q] = rec;
-        }
-        // requests for tick t + 1
-        {   // a_cur <- tick t + 1 (slot (t + 1) & 3), then that slot <- tick t + 5
-            const bool refill = t + 5 < T;
-            const int8_t *nxt = actions + o + (size_t)5 * N;
-            switch ((t + 1) & 3) {   // warp-uniform
-                case 0: a_cur = a_q0; if (refill) a_q0 = *nxt; break;
-                case 1: a_cur = a_q1; if (refill) a_q1 = *nxt; break;
-                case 2: a_cur = a_q2; if (refill) a_q2 = *nxt; break;
-                default: a_cur = a_q3; if (refill) a_q3 = *nxt; break;
-            }
-        }
-        pre_key = 0xffffffffu;
-        if (has_g && t + 1 < T && !(E.flags & F_DONE)) {   // tick t + 1 will be a step from exactly this state:
-            const int dr = (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);   // my guard's mask row there
-            const int nrow = SEQ_FREE(dr, nc) ? E.r + dr : E.r;
-            int k = gk, hs = ghs;
-            unsigned word = gw;
-            if (glen >= 2) {
-                const int hsl = (word >> 16) & 255;
-                if (hsl != 255) hs = hsl;
-                k = gkn; word = gwn;
-            }
-            const int wr = nrow - ((int)(word & 255) - grng);
-            if (wr >= 0 && wr <= 2 * grng) {
-                pre_key = (unsigned)(k | (hs << 8)); pre_wr = (unsigned)wr;
-                pre_g = gmask[(k * (L + 1) + hs) * VC_ROWS + wr];
-            }
-        }
+        const bool at_vault = live && E.r == D.vault_r && E.c == D.vault_c;                     // :284-288
+        E.tick += live;
+        const bool tout = live && E.tick >= D.max_steps;                                         // :291-297
+        unsigned rec = live ? ((unsigned)E.r | ((unsigned)E.c << 7) | ((unsigned)E.prev << 14) | SEQ_LIVE | SEQ_REBUILT) : 0u;
+        rec |= (detected ? SEQ_DET : 0u) | (at_vault ? SEQ_VAULT : 0u) | (tout ? SEQ_TOUT : 0u);
+        E.prev = live ? abs(E.r - D.vault_r) + abs(E.c - D.vault_c) : E.prev;
+        E.flags |= (detected ? (F_DETECTED | F_DONE) : 0) | (at_vault ? (F_VAULT | F_DONE) : 0) | (tout ? F_DONE : 0);
+        status = !live ? HEIST_ALREADY_DONE : (tout ? HEIST_TIMEOUT : (at_vault ? HEIST_VAULT_REACHED : (detected ? HEIST_DETECTED : HEIST_RUNNING)));
+        E.n_vault += status == HEIST_VAULT_REACHED;        // training.py:535-540
+        E.n_detect += status == HEIST_DETECTED;
+        E.n_timeout += status == HEIST_TIMEOUT;
+        // the trainer's `if done: reset()` (environment.py:183-214): headings persist, guards back to waypoint 0
+        const bool rs = valid && autoreset && (E.flags & F_DONE);
+        E.r = rs ? D.start_r : E.r; E.c = rs ? D.start_c : E.c;
+        E.tick = rs ? 0 : E.tick; E.prev = rs ? start_dist : E.prev; E.init = rs ? start_dist : E.init;
+        E.flags = rs ? 0 : E.flags;
+        gk = rs ? 0 : gk; gw = rs ? gw0 : gw; gkn = rs ? gstp : gkn; gwn = rs ? gw_reset_next : gwn;
+        rec |= rs ? SEQ_REBUILT : 0u;
+        // the visibility map of tick t is final: tell k_finish how to complete it
+        const bool rebuilt = rec & SEQ_REBUILT;
+        last = rebuilt ? t : last;
+        if (rebuilt && has_g) grec[o * Kg + j] = (uint16_t)(gk | (ghs << 8));
+        if (valid && j == 0) rec_s[(t - ts0) * SEQ_EPW + q] = rec;
     }
     __syncwarp();
     // ---- pass B, off the chain: rewards and outputs of the stage's ticks, one lane per (tick, env) ----
@@ -824,10 +778,6 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         fin[o] = (rec & SEQ_REBUILT) ? 1 : 0;
     }
     }
-#undef SEQ_RESET_STATE
-#undef SEQ_WALL_ROW
-#undef SEQ_WALL_AROUND
-#undef SEQ_FREE
 
     // ---- store ----
     if (!valid) return;
