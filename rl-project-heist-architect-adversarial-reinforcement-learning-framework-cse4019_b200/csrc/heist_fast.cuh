@@ -408,6 +408,10 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         pre_s0[tt * Kc + k] = max(0, (int)IX[q] - 1) & ~1;
         pre_fx[tt * Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
     }
+    uint32_t vr[FAST_TB];   // one-word grids: the ticks' rows (lane = grid row) stay in registers
+#pragma unroll
+    for (int t2 = 0; t2 < FAST_TB; ++t2) vr[t2] = 0;
+    bool any_exact = false;   // exactly marched rays put their tiles into vis_s
     for (int k = 0; k < n_cams; ++k) {
         const FastCam &Cm = cams[k];
         const int n_gaps = Cm.n_gaps;
@@ -475,27 +479,41 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
             reinterpret_cast<uint4 *>(mask_s)[tt * 2 + 1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
         }
         __syncwarp();
-        // lane = grid row: window row wr of every tick's mask (two 16-bit rows per word) into the tick's row words
-        for (int t2 = 0; t2 < n_t; ++t2) {
-            uint32_t *rows = vis_s + t2 * RW;
-            const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + t2 * VC_ROWS;
+        // lane = grid row: window row wr of every tick's mask (two 16-bit rows per word) into the tick's row words --
+        // registers for grids of one word per row and lane (up to 32 x 32), shared memory otherwise
+        if (RPL == 1 && W == 1) {
+            const int wr = lane - row0;
+            if (wr >= 0 && wr <= nrow) {
+                const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + wr;
 #pragma unroll
-            for (int a = 0; a < RPL; ++a) {
-                const int wr = lane + 32 * a - row0;
-                if (wr >= 0 && wr <= nrow) {
-                    const unsigned bits = mrow[wr];
-                    if (bits) {
-                        uint32_t v[W];
+                for (int t2 = 0; t2 < FAST_TB; ++t2) {
+                    const unsigned bits = mrow[t2 * VC_ROWS];   // (ticks beyond n_t hold stale masks: never written out)
+                    vr[t2] |= col0 >= 0 ? (bits << col0) : (bits >> (-col0));
+                }
+            }
+        } else {
+            for (int t2 = 0; t2 < n_t; ++t2) {
+                uint32_t *rows = vis_s + t2 * RW;
+                const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + t2 * VC_ROWS;
 #pragma unroll
-                        for (int w = 0; w < W; ++w) v[w] = 0;
-                        fast_or_row<W>(v, bits, col0);
+                for (int a = 0; a < RPL; ++a) {
+                    const int wr = lane + 32 * a - row0;
+                    if (wr >= 0 && wr <= nrow) {
+                        const unsigned bits = mrow[wr];
+                        if (bits) {
+                            uint32_t v[W];
 #pragma unroll
-                        for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                            for (int w = 0; w < W; ++w) v[w] = 0;
+                            fast_or_row<W>(v, bits, col0);
+#pragma unroll
+                            for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                        }
                     }
                 }
             }
         }
         if (bands) {   // warp-uniform; rare
+            any_exact = true;
             __syncwarp();
             for (int t2 = 0; t2 < n_t; ++t2) {
                 if (!((bands >> (4 * t2)) & 0xfu)) continue;
@@ -510,11 +528,12 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
     {
         uint32_t *dst = out + ((size_t)t_begin * D.N + env) * RW;
         const size_t stride = (size_t)D.N * RW;
-        if (RW <= 32) {
+        if (RPL == 1 && W == 1) {
             if (lane < RW) {
                 dst += lane;
 #pragma unroll
-                for (int tt = 0; tt < FAST_TB; ++tt) if (tt < n_t) dst[tt * stride] = vis_s[tt * RW + lane];
+                for (int tt = 0; tt < FAST_TB; ++tt)
+                    if (tt < n_t) dst[tt * stride] = any_exact ? (vr[tt] | vis_s[tt * RW + lane]) : vr[tt];
             }
         } else {
             for (int tt = 0; tt < n_t; ++tt, dst += stride)
@@ -821,6 +840,13 @@ k_finish(Dev D, int T, uint32_t *buf, const uint16_t *__restrict__ grec, const u
     if (t0 < 0) return;
     constexpr int G = VC_MAX_GUARDS;
     const int n_guards = D.env_s[(size_t)env * 4 + 1], L = D.L, Kg = D.Kg, RW = D.RW;
+    if (n_guards == 0) {
+        // no guards: the camera rows ARE the finished maps; only the env's current map has to be refreshed from
+        // the last rebuilt tick (by the block that holds it)
+        if (lt >= t0 && lt < t1)
+            for (int i = lane; i < RW; i += 32) D.vis[(size_t)env * RW + i] = buf[((size_t)lt * D.N + env) * RW + i];
+        return;
+    }
     unsigned pw[G];            // lane k: waypoint k of guard g  (row | col << 8 | range << 16)
     const uint16_t *gmask[G];
 #pragma unroll
