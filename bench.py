@@ -296,6 +296,39 @@ def secondary_kernels(ctx, env, wl, out, am_host, cp_host):
     ms_gae = time_kernel(lambda: hb.compute_gae(out["reward"], val, out["done"]))
     a1 = torch.zeros(N, dtype=torch.int8, device=dev)
     ms_tick = time_kernel(lambda: env.step_observe(a1, autoreset=True, state_out=state))
+
+    def graphed_us(fn, n=20, reps=10):
+        """Device time per call when n calls replay from one CUDA graph (how a policy loop drives single ticks:
+        no host launch gaps, tables warm in L2)."""
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                fn()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(reps):
+            g.replay()
+        e.record()
+        torch.cuda.synchronize()
+        return 1e3 * s.elapsed_time(e) / (reps * n)
+
+    try:
+        env.set_mode(env.MODE_TABLES)   # every env of the workload is table-driven: the tick is exactly one kernel
+        us_tick_graph = graphed_us(lambda: env.step_observe(a1, autoreset=True, state_out=state))
+        env.set_mode(wl.get("mode", 0))
+        us_gae_graph = graphed_us(lambda: hb.compute_gae(out["reward"], val, out["done"]))
+    except Exception as ex:   # reported, never fatal for the headline
+        us_tick_graph = us_gae_graph = None
+        sys.stderr.write(f"[bench] graph timing skipped: {ex}\n")
     am_dev, cp_dev = torch.as_tensor(am_host).to(dev), torch.as_tensor(cp_host).to(dev)
     ms_layout = time_kernel(lambda: env.set_layout_from_asset_map(am_dev, cp_dev, wl["budget"]), reps=5)
     env.reset()
@@ -303,8 +336,11 @@ def secondary_kernels(ctx, env, wl, out, am_host, cp_host):
                        "what": "heist_decode_validate: k_decode + k_set_layout (BFS) + k_build_cache + k_build_order, once per layout"},
             "observe": {"ms": ms_obs, "achieved_gbs": obs_bytes / ms_obs / 1e6, "frac": obs_bytes / ms_obs / 1e6 / peak, "bytes": obs_bytes},
             "gae": {"ms": ms_gae, "achieved_gbs": 17 * T * N / ms_gae / 1e6, "frac": 17 * T * N / ms_gae / 1e6 / peak, "bytes": 17 * T * N},
-            "step_observe_tick": {"us": 1e3 * ms_tick, "what": "heist_step_observe: one tick + auto-reset + dense state for all envs, eager launch",
-                                  "achieved_gbs": obs_bytes / ms_tick / 1e6, "frac": obs_bytes / ms_tick / 1e6 / peak}}
+            "step_observe_tick": {"us": 1e3 * ms_tick, "what": "heist_step_observe: one tick + auto-reset + dense state for all envs (one fused "
+                                  "kernel); us = eager launch after an L2 flush, us_graph = per tick when 20 ticks replay from a CUDA graph (HEIST_MODE_TABLES)",
+                                  "us_graph": us_tick_graph, "achieved_gbs": obs_bytes / ms_tick / 1e6, "frac": obs_bytes / ms_tick / 1e6 / peak,
+                                  "frac_graph": (obs_bytes / (us_tick_graph * 1e-3) / 1e6 / peak) if us_tick_graph else None},
+            "gae_graph_us": us_gae_graph}
 
 
 def ppo_leg(ctx, envs, ticks, iters, warmup):

@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--budget", type=int, default=15)
     ap.add_argument("--reference", default=None)
     ap.add_argument("--eager", action="store_true", help="no CUDA-graph tick")
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast inside the two networks")
     a = ap.parse_args()
     rank, world, local = heist_b200.dist.init_from_env()
     torch.cuda.set_device(local)
@@ -49,7 +50,8 @@ def main():
             if world > 1:
                 torch.distributed.broadcast(p.data, 0)
     env = heist_b200.BatchedHeistEnv(cfg, a.envs, device=dev)
-    loop = AdversarialLoop(env, solver, architect, ticks=a.ticks, budget=a.budget, graph_tick=not a.eager)
+    loop = AdversarialLoop(env, solver, architect, ticks=a.ticks, budget=a.budget, graph_tick=not a.eager,
+                           amp_dtype=torch.bfloat16 if a.amp else None)
     for it in range(a.iters):
         stats, ms = loop.iteration(temperature=max(0.5, 2.0 - 1.5 * it / max(a.iters, 1)))   # training.py:451
         cnt = heist_b200.dist.allreduce_sum(torch.stack([stats["valid"], stats["vault"], stats["detected"], stats["timeout"]]))

@@ -213,16 +213,23 @@ int heist_gae(const float *rew, const float *val, const uint8_t *done, int T, in
 int heist_architect_reward(HeistHandle *h, double *reward_out, double *solve_rate_out, void *stream);
 
 /*
- * Verification knob.  All three modes produce bit-identical results; tests compare them.
+ * Verification / deployment knob.  All modes produce bit-identical results; tests compare them.
  *   HEIST_MODE_DEFAULT  visibility from the per-layout angular cache (table-driven kernel); envs whose assets the
  *                       cache does not cover (vision_range > 7, fov outside (0, 180], ...) are ray-marched
  *   HEIST_MODE_EXACT    every ray sample through the fp64 reference arithmetic (security.py:69-99)
  *   HEIST_MODE_MARCH    filtered fixed-point ray-march with exact fallback for every env (no cache)
  * Setting HEIST_NO_VIS_CACHE=1 in the environment before heist_create makes DEFAULT behave like MARCH.
+ *   HEIST_MODE_TABLES   like DEFAULT, but the caller GUARANTEES that every env's assets are covered by the cache (true for
+ *                       every layout the Architect decode produces: vision_range 6, fov 30..120, <= 4 guards): launches
+ *                       then never carry the ray-march kernels -- a single tick is exactly one kernel, which is what a
+ *                       CUDA graph of a policy loop wants.  A set_layout that breaks the guarantee raises the sticky
+ *                       device error "layout not covered by the visibility cache" (heist_check_errors); the uncovered
+ *                       envs do not advance.
  */
 #define HEIST_MODE_DEFAULT 0
 #define HEIST_MODE_EXACT 1
 #define HEIST_MODE_MARCH 2
+#define HEIST_MODE_TABLES 3
 int heist_set_mode(HeistHandle *h, int mode);
 
 /*

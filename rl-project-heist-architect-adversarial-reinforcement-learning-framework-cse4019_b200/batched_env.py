@@ -147,11 +147,13 @@ class BatchedHeistEnv:
             t = torch.as_tensor(np.ascontiguousarray(x), dtype=dtype).to(self.device)
         return t.contiguous()
 
-    MODE_DEFAULT, MODE_EXACT, MODE_MARCH = 0, 1, 2
+    MODE_DEFAULT, MODE_EXACT, MODE_MARCH, MODE_TABLES = 0, 1, 2, 3
 
     def set_mode(self, mode):
         """Verification knob (include/heist_b200.h): 0 = angular visibility cache + ray-march for what it does not
-        cover, 1 = all-fp64 ray-march, 2 = filtered ray-march everywhere.  All modes are bit-identical."""
+        cover, 1 = all-fp64 ray-march, 2 = filtered ray-march everywhere, 3 = tables only (the caller guarantees that the
+        cache covers every layout -- Architect-decoded ones always are -- so a tick is exactly one kernel: CUDA graphs).
+        All modes are bit-identical."""
         _ffi.check(self._lib.heist_set_mode(self._h, int(mode)), "heist_set_mode")
 
     def cache_stats(self):

@@ -390,7 +390,9 @@ static cudaError_t build_cache(HeistHandle *h, cudaStream_t s) {
     }
     cudaError_t e = cudaMemsetAsync(h->d.n_uncached, 0, sizeof(int), s);
     if (e != cudaSuccess) return e;
-    k_build_cache<<<h->N, VC_BUILD_THREADS, 0, s>>>(h->d);
+    Dev d = h->d;
+    d.strict_tables = h->mode == HEIST_MODE_TABLES;
+    k_build_cache<<<h->N, VC_BUILD_THREADS, 0, s>>>(d);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     h->all_cached = -1;
     if ((e = cudaMemcpyAsync(h->n_unc_host, h->d.n_uncached, sizeof(int), cudaMemcpyDeviceToHost, s)) != cudaSuccess) return e;
@@ -707,12 +709,15 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
     return 0;
 }
 
-static inline bool use_cache(const HeistHandle *h) { return h->mode == HEIST_MODE_DEFAULT && h->d.vc_p != nullptr; }
+static inline bool use_cache(const HeistHandle *h) {
+    return (h->mode == HEIST_MODE_DEFAULT || h->mode == HEIST_MODE_TABLES) && h->d.vc_p != nullptr;
+}
 
 // Does any env need the ray-march kernels next to the table-driven ones?  Learnt without a sync from the count the
 // cache build copies to pinned memory; until that copy has landed (or while `s` is being captured) the answer is yes.
 static bool march_needed(HeistHandle *h, cudaStream_t s) {
     if (!use_cache(h)) return true;
+    if (h->mode == HEIST_MODE_TABLES) return false;   // the caller guarantees coverage (violations are reported by set_layout)
     // A launch that is being captured into a CUDA graph will be replayed after later set_layouts, whose envs may not
     // all be covered by the cache: it always carries the ray-march kernel (which exits at once when no env needs it).
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -781,7 +786,8 @@ extern "C" int heist_cache_stats(HeistHandle *h, int32_t *envs_cached, int64_t *
 
 extern "C" int heist_set_mode(HeistHandle *h, int mode) {
     if (!h) return fail(-1, "heist_set_mode: null handle");
-    if (mode < HEIST_MODE_DEFAULT || mode > HEIST_MODE_MARCH) return fail(-10, "heist_set_mode: unknown mode %d", mode);
+    if (mode < HEIST_MODE_DEFAULT || mode > HEIST_MODE_TABLES) return fail(-10, "heist_set_mode: unknown mode %d", mode);
+    if (mode == HEIST_MODE_TABLES && !h->d.vc_p) return fail(-13, "heist_set_mode: HEIST_MODE_TABLES needs the visibility cache, which this handle does not have (%s)", g_warn.c_str());
     h->mode = mode;
     return 0;
 }
@@ -919,14 +925,16 @@ extern "C" int heist_gae(const float *rew, const float *val, const uint8_t *done
     const float gl = (float)(gamma * gae_lambda);  // self.gamma * self.gae_lambda is a Python double product
     // Columns are the only parallelism (the scan is sequential in t for bit-exactness).  With few columns use
     // one warp per CTA spread over all SMs and a deep load prefetch; with many, wider CTAs and less prefetch.
-    if (n_cols <= 16384 && gae_staged_bytes(T) <= (size_t)200 * 1024) {   // few columns: stage each warp's block in shared memory
-        static size_t attr_set[64];   // largest dynamic shared memory configured so far, per device
+    const bool rows16 = (n_cols % GAE_CW) == 0 && ((((uintptr_t)rew | (uintptr_t)val) & 15) == 0) && (((uintptr_t)done & 7) == 0) &&
+                        ((n_cols * 4) % 16) == 0;
+    if (n_cols <= 16384 && rows16 && gae_staged_bytes(T) <= (size_t)200 * 1024) {   // few columns: blocks staged in shared memory
+        static size_t attr_set[64];   // dynamic shared memory limit configured so far, per device
         const size_t sm = gae_staged_bytes(T);
-        if (device >= 0 && device < 64 && sm > attr_set[device]) {
+        if (sm > 48 * 1024 && device >= 0 && device < 64 && !attr_set[device]) {
             CUDA_TRY(cudaFuncSetAttribute(k_gae_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)200 * 1024)));
-            attr_set[device] = (size_t)200 * 1024;
+            attr_set[device] = 1;
         }
-        k_gae_staged<<<(n_cols + 31) / 32, 32, sm, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
+        k_gae_staged<<<n_cols / GAE_CW, 32, sm, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
     } else if (n_cols <= 32768)
         k_gae<32, 32><<<(n_cols + 31) / 32, 32, 0, (cudaStream_t)stream>>>(rew, val, done, T, n_cols, g, gl, adv, ret);
     else if (n_cols <= 131072)
@@ -970,12 +978,13 @@ extern "C" int heist_check_errors(HeistHandle *h, void *stream) {
     CUDA_TRY(cudaMemcpy(&flags, h->d.err, sizeof(int), cudaMemcpyDeviceToHost));
     if (flags) {
         CUDA_TRY(cudaMemset(h->d.err, 0, sizeof(int)));
-        return fail(-100 - flags, "device-side error:%s%s%s%s%s",
+        return fail(-100 - flags, "device-side error:%s%s%s%s%s%s",
                     (flags & ERR_CAPACITY) ? " capacity exceeded (max_walls/max_cams/max_guards/max_path)" : "",
                     (flags & ERR_WAYPOINT) ? " guard waypoint outside the grid" : "",
                     (flags & ERR_RAYS) ? " fov/vision_range too large" : "",
                     (flags & ERR_BOUNDS) ? " cell-map access out of range (debug build)" : "",
-                    (flags & ERR_STATE) ? " guard heading in the state view is not one of its path's headings" : "");
+                    (flags & ERR_STATE) ? " guard heading in the state view is not one of its path's headings" : "",
+                    (flags & ERR_UNCOVERED) ? " layout not covered by the visibility cache (HEIST_MODE_TABLES)" : "");
     }
     return 0;
 }

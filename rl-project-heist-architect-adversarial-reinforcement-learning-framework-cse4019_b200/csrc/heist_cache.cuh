@@ -384,6 +384,6 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
     }
     if (tid == 0) {
         D.env_cached[env] = env_ok ? 1 : 0;
-        if (!env_ok) atomicAdd(D.n_uncached, 1);
+        if (!env_ok) { atomicAdd(D.n_uncached, 1); if (D.strict_tables) atomicOr(D.err, ERR_UNCOVERED); }
     }
 }

@@ -68,9 +68,10 @@ struct Dev {
     uint8_t *env_cached;  // [N] every asset of the env is served by the cache
     int *n_uncached;      // [1] envs left to the ray-march kernel
     int skip_cached;      // launch flag: the ray-march kernel leaves cached envs to k_fast
+    int strict_tables;    // launch flag (HEIST_MODE_TABLES): an env the cache does not cover is an error
 };
 
-enum { ERR_CAPACITY = 1, ERR_WAYPOINT = 2, ERR_RAYS = 4, ERR_BOUNDS = 8, ERR_STATE = 16 };
+enum { ERR_CAPACITY = 1, ERR_WAYPOINT = 2, ERR_RAYS = 4, ERR_BOUNDS = 8, ERR_STATE = 16, ERR_UNCOVERED = 32 };
 enum { F_DONE = 1, F_DETECTED = 2, F_VAULT = 4 };
 
 // Python `x % 360.0` (floatobject.c float_rem): fmod, then shift negative remainders up.

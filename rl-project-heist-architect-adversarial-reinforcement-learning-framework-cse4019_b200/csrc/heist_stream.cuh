@@ -159,38 +159,41 @@ k_gae(const float *__restrict__ rew, const float *__restrict__ val, const uint8_
     }
 }
 
-// Few columns (a 4 096-env rollout is 128 warps): the scan is then latency-bound -- each warp alone on an SM, waiting
-// for its own loads batch after batch.  k_gae_staged first pulls the warp's whole [T][32 columns] block of rewards,
-// values and done flags into shared memory with one burst of asynchronous copies (every load in flight at once),
-// then runs the same sequential recurrence from shared memory and streams the results out.
-__device__ __forceinline__ void gae_cp_async4(void *dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+// Few columns (a 4 096-env rollout): the scan is then latency-bound -- a handful of warps, each waiting for its own
+// loads batch after batch.  k_gae_staged gives a warp only CW = 8 columns (4x the warps), first pulls the warp's
+// whole [T][CW] block of rewards, values and done flags into shared memory with one burst of 16-byte asynchronous
+// copies (every load in flight at once), then runs the same sequential recurrence from shared memory in lanes
+// 0 .. CW-1 and streams the results out.  Needs n % CW == 0 and 16-byte aligned rows (else the plain kernels).
+#define GAE_CW 8
+__device__ __forceinline__ void gae_cp_async(void *dst_smem, const void *src, int bytes16) {
+    if (bytes16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+    else asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((unsigned)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
 }
-__host__ __device__ inline size_t gae_staged_bytes(int T) { return (size_t)T * 32 * 12; }
+__host__ __device__ inline size_t gae_staged_bytes(int T) { return (size_t)T * GAE_CW * 9 + 16; }
 
 __global__ void __launch_bounds__(32)
 k_gae_staged(const float *__restrict__ rew, const float *__restrict__ val, const uint8_t *__restrict__ done, int T, int n,
              float g, float gl, float *__restrict__ adv, float *__restrict__ ret) {
     extern __shared__ __align__(16) unsigned char gsm[];
-    float *rs = reinterpret_cast<float *>(gsm), *vs = rs + (size_t)T * 32;
-    uint32_t *ds = reinterpret_cast<uint32_t *>(vs + (size_t)T * 32);   // done flags, 4 columns per word per row: [T][8]
-    const int lane = threadIdx.x, j0 = blockIdx.x * 32, j = j0 + lane;
-    const bool on = j < n;
-    const bool d4 = ((n & 3) == 0) && ((((uintptr_t)done) & 3) == 0);   // rows of done flags are word-aligned
-    for (int t = 0; t < T; ++t) {
-        const size_t i = (size_t)t * n + j;
-        if (on) { gae_cp_async4(rs + t * 32 + lane, rew + i); gae_cp_async4(vs + t * 32 + lane, val + i); }
-        if (d4) { if (lane < 8 && j0 + 4 * lane < n) gae_cp_async4(ds + t * 8 + lane, done + (size_t)t * n + j0 + 4 * lane); }
-        else if (on) reinterpret_cast<uint8_t *>(ds + t * 8)[lane] = done[i];
+    float *rs = reinterpret_cast<float *>(gsm), *vs = rs + (size_t)T * GAE_CW;   // [T][CW]
+    uint8_t *ds = reinterpret_cast<uint8_t *>(vs + (size_t)T * GAE_CW);           // [T][CW]
+    const int lane = threadIdx.x, j0 = blockIdx.x * GAE_CW;
+    // a row of the block is CW floats = 32 bytes = two 16-byte pieces (8 bytes of done flags): lane -> (row, piece)
+    for (int i = lane; i < 2 * T; i += 32) {
+        const int t = i >> 1, h = i & 1;
+        gae_cp_async(rs + t * GAE_CW + 4 * h, rew + (size_t)t * n + j0 + 4 * h, 1);
+        gae_cp_async(vs + t * GAE_CW + 4 * h, val + (size_t)t * n + j0 + 4 * h, 1);
     }
+    for (int t = lane; t < T; t += 32) gae_cp_async(ds + t * GAE_CW, done + (size_t)t * n + j0, 0);
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    if (!on) return;
+    if (lane >= GAE_CW) return;
+    const int j = j0 + lane;
     float last = 0.0f, nv = 0.0f;
 #pragma unroll 8
     for (int t = T - 1; t >= 0; --t) {
-        const float r = rs[t * 32 + lane], v = vs[t * 32 + lane];
-        const float om = __fsub_rn(1.0f, (float)reinterpret_cast<const uint8_t *>(ds + t * 8)[lane]);
+        const float r = rs[t * GAE_CW + lane], v = vs[t * GAE_CW + lane];
+        const float om = __fsub_rn(1.0f, (float)ds[t * GAE_CW + lane]);
         const float delta = __fsub_rn(__fadd_rn(r, __fmul_rn(__fmul_rn(g, nv), om)), v);
         const float A = __fadd_rn(delta, __fmul_rn(__fmul_rn(gl, om), last));
         const size_t i = (size_t)t * n + j;

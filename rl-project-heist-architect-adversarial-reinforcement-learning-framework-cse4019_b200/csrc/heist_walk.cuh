@@ -27,7 +27,7 @@ __host__ __device__ inline size_t walk_warp_bytes(int RW, int Kc) {   // fused m
 }
 
 template <int RPL, int W>
-__global__ void __launch_bounds__(WALK_WARPS * 32)
+__global__ void __launch_bounds__(WALK_WARPS * 32, 5)
 k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
        double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
        uint32_t *buf, int write_traj, int do_reset, const uint8_t *__restrict__ mask, int store_heading,

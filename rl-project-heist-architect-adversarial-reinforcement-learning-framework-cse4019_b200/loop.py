@@ -35,6 +35,8 @@ class AdversarialLoop:
         self.grid_in = hnets.empty_grid_input(env.num_envs, env.R, env.C, cfg.start_pos, cfg.vault_pos, env.device)
         self.tick = None
         self.graphed = False
+        if graph_tick and not env.cache_warning:   # Architect-decoded layouts are always covered by the visibility tables
+            env.set_mode(env.MODE_TABLES)
         if graph_tick:
             try:   # policy forward + sampling + env tick + dense state in ONE CUDA graph (ppo.GraphedTick)
                 self.tick = ppo.GraphedTick(env, solver, autoreset=True, amp_dtype=amp_dtype)

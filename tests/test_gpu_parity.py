@@ -836,6 +836,45 @@ def test_fused_tick_graph_survives_layout_changes():
     env.check_errors()
 
 
+def test_tables_only_mode_is_one_kernel_per_tick_and_reports_uncovered_layouts():
+    """HEIST_MODE_TABLES: the caller guarantees cache coverage, a tick is one kernel even inside a CUDA graph; a layout
+    that breaks the guarantee is a reported (sticky) error, not a silent divergence."""
+    cfg = EnvironmentConfig(max_steps=30)
+    N, T = 64, 45
+    env = BatchedHeistEnv(cfg, N)
+    env.set_mode(env.MODE_TABLES)
+    rng = np.random.default_rng(99)
+    am, cp = synthetic.sample_asset_maps(rng, N, 20, 20), synthetic.sample_cam_params(rng, N)
+    env.set_layout_from_asset_map(am, cp, 15)
+    env.check_errors()
+    oenvs, _ = oracle_envs(am, cp, cfg, 15)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, T, N)
+    a_static = torch.zeros(N, dtype=torch.int8, device="cuda")
+    state = torch.empty((N, 3, 20, 20), dtype=torch.float32, device="cuda")
+    n0 = env.launch_count()
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side), torch.cuda.graph(g, stream=side):
+        rew, done, status, _ = env.step_observe(a_static, autoreset=True, state_out=state)
+    assert env.launch_count() - n0 == 1   # one kernel captured
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    for t in range(T):
+        a_static.copy_(torch.as_tensor(acts[t]))
+        g.replay()
+        assert np.array_equal(rew.cpu().numpy(), ref["reward"][t]) and np.array_equal(status.cpu().numpy(), ref["status"][t]), t
+        assert np.array_equal(u32(env.visibility_bits), ref["vis_bits"][t]), t
+    assert np.array_equal(state.cpu().numpy(), np.stack([e.state_tensor() for e in oenvs]))
+    # a camera beyond the cache's range breaks the guarantee: reported
+    lays = [([], [{"row": 5, "col": 5, "fov_angle": 60.0, "heading": 0.0, "rotation_speed": 15.0, "vision_range": 9}], [])] * N
+    env.set_layout_explicit(lays, budget=np.full(N, 100, np.int32))
+    with pytest.raises(RuntimeError, match="not covered"):
+        env.check_errors()
+    env.close()
+
+
 def test_debug_bounds_build_reports_no_out_of_range_access():
     """compute-sanitizer is closed on the GPU pool, so the march is also run from a -DHEIST_DEBUG_BOUNDS build that
     range-checks every cell-map access (tests/sanitizer_small.py: four grid classes, resets, exact-path rays)."""
