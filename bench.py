@@ -33,7 +33,7 @@ def workload_config(args, world):
                         f"Solver-only rollout T={args.ticks}, auto-reset, uniform actions",
             "grid": [args.rows, args.cols], "envs_per_gpu": args.envs, "ticks_per_step": args.ticks,
             "budget": args.budget, "max_steps": 200, "parallelism": f"env-shard x{world} (no data-path collective)",
-            "visibility": {0: "angular cache (k_heads, k_cam_vis, k_seq, k_finish; ray-march for uncovered envs)",
+            "visibility": {0: "angular cache (k_heads, k_cam_vis_staged, k_seq, k_finish; ray-march for uncovered envs)",
                            1: "all-fp64 ray-march", 2: "filtered ray-march"}[args.mode],
             "l2": "flushed between timed iterations (256 MiB write)"}
 
@@ -420,13 +420,14 @@ def run_ours(args, rank, world, local_rank):
         if rank == 0:
             w3 = {"rows": 32, "cols": 32, "envs": 65536, "budget": 22, "exact_counts": (2, 4, 2), "ticks": 200, "mode": args.mode}
             t3 = Timer(torch, dist, dev, 1, flush)
-            r3 = rollout_leg({**ctx, "timer": t3, "world": 1}, w3, 3, 3, want_e2e=False)
+            r3 = rollout_leg({**ctx, "timer": t3, "world": 1}, w3, 3, 3, want_e2e=False, want_layout=True)
             b3 = b_step_bytes(32, 32, r3["kc"], r3["kg"])
             legs["config3"] = {"workload": "config3: 32x32 grid, 65536 envs on one GPU, budget 22 (4 cameras + 2 guards + 2 walls), T=200, auto-reset",
                                "value": r3["steps_per_iter"] * 3 / (r3["ms_value"] * 1e-3), "unit": UNIT, "n_gpus": 1,
                                "ms_per_step": r3["ms_value"] / 3, "steps": 3, "warmup": 3,
                                "hbm_frac": b3 * r3["steps_per_iter"] * 3 / (r3["ms_value"] * 1e-3) / 1e9 / peak,
-                               "bytes_per_env_step": b3, "cache_bytes": r3["cache_bytes"], "envs_cached": r3["envs_cached"]}
+                               "bytes_per_env_step": b3, "cache_bytes": r3["cache_bytes"], "envs_cached": r3["envs_cached"],
+                               "other_kernels": r3.get("extra", {})}
         ctx["timer"].barrier()
         n4 = 262144 // world
         w4 = {"rows": 64, "cols": 64, "envs": n4, "budget": 22, "exact_counts": (2, 4, 2), "ticks": 200, "mode": args.mode}

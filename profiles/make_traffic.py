@@ -19,10 +19,17 @@ def main():
     for r in rows[1:]:
         launches.setdefault(int(r[iid]), {"name": r[ik].split("(")[0].replace("void ", "")})[r[im]] = float(r[iv].replace(",", ""))
     seq = list(launches.values())
-    # one step of the cached path begins with the k_heads launch that has first = 1 (the L2 flush fill precedes it)
-    anchor = "at::native::vectorized_elementwise_kernel" if key == "step_cached" else "k_step_many"
-    idx = [i for i, l in enumerate(seq) if l["name"].startswith(anchor)]
-    step = seq[idx[-2]:idx[-1]] if key == "step_cached" else [seq[idx[3]]]
+    if key == "step_cached":
+        # a step of the cached path = the kernels after an L2-flush fill that is followed by k_heads, up to the next
+        # fill; the 4th such step is the first timed one of `bench.py --steps 2 --warmup 3`
+        fills = [i for i, l in enumerate(seq) if l["name"].startswith("at::vectorized_elementwise_kernel")
+                 and i + 1 < len(seq) and seq[i + 1]["name"].startswith("k_heads")]
+        start = fills[3]
+        end = next(i for i in range(start + 1, len(seq)) if seq[i]["name"].startswith("at::"))
+        step = seq[start + 1:end]
+    else:
+        idx = [i for i, l in enumerate(seq) if l["name"].startswith("k_step_many")]
+        step = [seq[idx[3]]]
     step = [l for l in step if l["name"].startswith("k_")]
     tot_t = sum(l["gpu__time_duration.sum"] for l in step)
     share = collections.OrderedDict()
