@@ -57,14 +57,15 @@ struct VcGeo {   // what a ray needs to know about the grid
 };
 __device__ __forceinline__ VcGeo vc_geo(const Dev &D) { VcGeo g; g.R = D.R; g.C = D.C; g.W = D.W; g.deg2rad = D.deg2rad; return g; }
 
-template <typename Mark>
-__device__ __forceinline__ void vc_ray(const VcGeo &D, const uint32_t *__restrict__ wall, int row, int col, double fov,
-                                       double heading, int num_rays, int nsamp, double unit, int ri, Mark mark) {
+// The angle of ray ri of a cone, in the reference's operation order (security.py:69-71).
+__device__ __forceinline__ double vc_ray_angle_deg(double fov, double heading, int num_rays, int ri) {
     const double half_fov = __ddiv_rn(fov, 2.0);
-    const double angle_deg =
-        __dadd_rn(__dsub_rn(heading, half_fov), __ddiv_rn(__dmul_rn(fov, (double)ri), (double)num_rays));
-    double dx, dy;
-    ray_dir(angle_deg, D.deg2rad, dx, dy);
+    return __dadd_rn(__dsub_rn(heading, half_fov), __ddiv_rn(__dmul_rn(fov, (double)ri), (double)num_rays));
+}
+// ... and its march from (row, col) along (dx, dy): nsamp samples `unit` apart (security.py:77-99, :176-190).
+template <typename Mark>
+__device__ __forceinline__ void vc_march(const VcGeo &D, const uint32_t *__restrict__ wall, int row, int col, double dx, double dy,
+                                         int nsamp, double unit, Mark mark) {
     const double dcol = (double)col, drow = (double)row;
     double dist = unit;
     for (int j = 1; j <= nsamp; ++j, dist += unit) {
@@ -74,6 +75,13 @@ __device__ __forceinline__ void vc_ray(const VcGeo &D, const uint32_t *__restric
         if ((wall[r * D.W + (c >> 5)] >> (c & 31)) & 1u) return;
         mark(r, c);
     }
+}
+template <typename Mark>
+__device__ __forceinline__ void vc_ray(const VcGeo &D, const uint32_t *__restrict__ wall, int row, int col, double fov,
+                                       double heading, int num_rays, int nsamp, double unit, int ri, Mark mark) {
+    double dx, dy;
+    ray_dir(vc_ray_angle_deg(fov, heading, num_rays, ri), D.deg2rad, dx, dy);
+    vc_march(D, wall, row, col, dx, dy, nsamp, unit, mark);
 }
 
 // Same march for the representative angle of a gap.  Inside a gap every sample of a ray stays at least mu = 4e-12
@@ -328,16 +336,16 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
         for (int i = n_points + tid; i < VC_POINTS; i += VC_BUILD_THREADS) P[i] = 0x3fffffff;
         if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = sh; D.vc_lo[o] = dom_lo; }
         // ---- 4. coarse index: points below each 1-degree bucket start ----
+        // IX[q] = first index i with p[i] >= dom_lo + q  (p[i]: even i from S.end, odd from S.key; p[n_points] = +inf).
+        // Point i answers every bucket q with p[i - 1] < dom_lo + q <= p[i]: each thread fills its points' buckets
+        // (the comparisons are the definition's own; the start estimate only saves steps).
         uint16_t *IX = D.vc_idx + o * VC_IDX;
-        for (int q = tid; q < VC_IDX; q += VC_BUILD_THREADS) {
-            const double a = dom_lo + (double)q;
-            int lo = 0, hi = n_points;   // first index with p >= a  (p[i]: even i from S.end, odd from S.key)
-            while (lo < hi) {
-                const int m = (lo + hi) >> 1;
-                const double pm = (m & 1) ? S.key[(m >> 1) + 1] : S.end[m >> 1];
-                if (pm < a) lo = m + 1; else hi = m;
-            }
-            IX[q] = (uint16_t)lo;
+        for (int i = tid; i <= n_points; i += VC_BUILD_THREADS) {
+            const double prev = i == 0 ? -1e308 : (((i - 1) & 1) ? S.key[((i - 1) >> 1) + 1] : S.end[(i - 1) >> 1]);
+            const double cur = i == n_points ? 1e308 : ((i & 1) ? S.key[(i >> 1) + 1] : S.end[i >> 1]);
+            int q = i == 0 ? 0 : max(0, min(VC_IDX, (int)floor(prev - dom_lo) - 1));
+            while (q < VC_IDX && !(dom_lo + (double)q > prev)) ++q;
+            for (; q < VC_IDX && dom_lo + (double)q <= cur; ++q) IX[q] = (uint16_t)i;
         }
         __syncthreads();
     }
@@ -366,19 +374,48 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
         }
         __syncthreads();
         const int nh = S.n_bands;
-        for (int combo = 0; combo < gi.x * nh; ++combo) {
-            const int idx = combo / nh, hs = combo - idx * nh;
-            const int row = D.guard_path[(o * D.L + idx) * 2], col = D.guard_path[(o * D.L + idx) * 2 + 1];
-            const double heading = D.vg_hval[o * HS + hs];
-            if (tid < VC_ROWS) S.mask[tid] = 0;
+        // The masks of all (waypoint, heading slot) pairs at once: one work item per (pair, ray), OR-ed into shared
+        // memory (two 16-bit window rows per word, the layout of vg_mask).  A ray's direction depends on the slot and
+        // the ray only -- not on the waypoint -- so the directions are evaluated once per (slot, ray) and shared by
+        // the waypoints (same arithmetic, same values).
+        const int NRAY = gi.w + 1, n_pair = gi.x * nh;
+        double2 *dirs = reinterpret_cast<double2 *>(S.key);               // key[] + end[]: 2 * VC_RAW doubles, free after the cameras
+        unsigned *gmask = reinterpret_cast<unsigned *>(&S.gm[0][0]);      // [pair][VC_ROWS / 2]
+        constexpr int PAIR_CAP = (VC_POINTS / 2) * 32 / (VC_ROWS * 2);
+        const bool shared_dirs = nh * NRAY <= VC_RAW;
+        __syncthreads();
+        if (shared_dirs)
+            for (int i = tid; i < nh * NRAY; i += VC_BUILD_THREADS) {
+                const int hs = i / NRAY, ri = i - hs * NRAY;
+                double dx, dy;
+                ray_dir(vc_ray_angle_deg(fov, D.vg_hval[o * HS + hs], gi.w, ri), geo.deg2rad, dx, dy);
+                dirs[i] = make_double2(dx, dy);
+            }
+        for (int p0 = 0; p0 < n_pair; p0 += PAIR_CAP) {
+            const int np = min(PAIR_CAP, n_pair - p0);
+            for (int i = tid; i < np * (VC_ROWS / 2); i += VC_BUILD_THREADS) gmask[i] = 0;
             __syncthreads();
-            for (int ri = tid; ri <= gi.w; ri += VC_BUILD_THREADS)
-                vc_ray(geo, wall, row, col, fov, heading, gi.w, gi.z, 1.0, ri, [&](int r, int c) {
-                    atomicOr(&S.mask[r - row + gi.z], 1u << (c - col + gi.z));
+            for (int it = tid; it < np * NRAY; it += VC_BUILD_THREADS) {
+                const int pb = it / NRAY, ri = it - pb * NRAY;
+                const int idx = (p0 + pb) / nh, hs = (p0 + pb) - idx * nh;
+                const int row = D.guard_path[(o * D.L + idx) * 2], col = D.guard_path[(o * D.L + idx) * 2 + 1];
+                double dx, dy;
+                if (shared_dirs) { const double2 d = dirs[hs * NRAY + ri]; dx = d.x; dy = d.y; }
+                else ray_dir(vc_ray_angle_deg(fov, D.vg_hval[o * HS + hs], gi.w, ri), geo.deg2rad, dx, dy);
+                unsigned *m = gmask + pb * (VC_ROWS / 2);
+                vc_march(geo, wall, row, col, dx, dy, gi.z, 1.0, [&](int r, int c) {
+                    const int wr = r - row + gi.z, wc = c - col + gi.z;
+                    atomicOr(&m[wr >> 1], 1u << (wc + 16 * (wr & 1)));
                 });
-            if (tid == 0) atomicOr(&S.mask[gi.z], 1u << gi.z);  // the guard's own tile is always lit (visibility.py:59)
+            }
+            // the guard's own tile is always lit (visibility.py:59)
+            for (int pb = tid; pb < np; pb += VC_BUILD_THREADS) atomicOr(&gmask[pb * (VC_ROWS / 2) + (gi.z >> 1)], 1u << (gi.z + 16 * (gi.z & 1)));
             __syncthreads();
-            if (tid < VC_ROWS) D.vg_mask[((o * D.L + idx) * HS + hs) * VC_ROWS + tid] = (uint16_t)S.mask[tid];
+            for (int i = tid; i < np * (VC_ROWS / 2); i += VC_BUILD_THREADS) {
+                const int pb = i / (VC_ROWS / 2), w = i - pb * (VC_ROWS / 2);
+                const int idx = (p0 + pb) / nh, hs = (p0 + pb) - idx * nh;
+                reinterpret_cast<uint32_t *>(D.vg_mask + ((o * D.L + idx) * HS + hs) * VC_ROWS)[w] = gmask[i];
+            }
             __syncthreads();
         }
     }
