@@ -265,18 +265,14 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
         // ---- 3. one representative ray per gap -> window mask ----
         for (int g = tid; g < nb0 - 1; g += VC_BUILD_THREADS) {
             const double mid = 0.5 * (S.end[g] + S.key[g + 1]);
-            unsigned rows[VC_ROWS / 2];
-#pragma unroll
-            for (int q = 0; q < VC_ROWS / 2; ++q) rows[q] = 0;
+            unsigned *rows = reinterpret_cast<unsigned *>(&S.gm[g][0]);   // the thread's own gap: plain read-modify-write
+            S.gm[g][0] = make_uint4(0, 0, 0, 0);
+            S.gm[g][1] = make_uint4(0, 0, 0, 0);
             vc_ray_angle(geo, wall, row, col, mid, nsamp, 0.5, [&](int r, int c) {
                 if (r == row && c == col) return;  // (r, c) != (self.row, self.col), security.py:93
                 const int wr = r - row + range, wc = c - col + range;
-                const unsigned bit = 1u << (wc + 16 * (wr & 1));
-#pragma unroll
-                for (int q = 0; q < VC_ROWS / 2; ++q) if (q == (wr >> 1)) rows[q] |= bit;
+                rows[wr >> 1] |= 1u << (wc + 16 * (wr & 1));
             });
-            S.gm[g][0] = make_uint4(rows[0], rows[1], rows[2], rows[3]);
-            S.gm[g][1] = make_uint4(rows[4], rows[5], rows[6], rows[7]);
         }
         __syncthreads();
         // ---- 3b. drop redundant bands.  A band that comes from ONE tie crossing separates two gaps whose tile
@@ -395,18 +391,19 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
             const int np = min(PAIR_CAP, n_pair - p0);
             for (int i = tid; i < np * (VC_ROWS / 2); i += VC_BUILD_THREADS) gmask[i] = 0;
             __syncthreads();
-            for (int it = tid; it < np * NRAY; it += VC_BUILD_THREADS) {
-                const int pb = it / NRAY, ri = it - pb * NRAY;
+            for (int pb = tid >> 5; pb < np; pb += VC_BUILD_THREADS / 32) {   // warp = pair, lane = ray
                 const int idx = (p0 + pb) / nh, hs = (p0 + pb) - idx * nh;
                 const int row = D.guard_path[(o * D.L + idx) * 2], col = D.guard_path[(o * D.L + idx) * 2 + 1];
-                double dx, dy;
-                if (shared_dirs) { const double2 d = dirs[hs * NRAY + ri]; dx = d.x; dy = d.y; }
-                else ray_dir(vc_ray_angle_deg(fov, D.vg_hval[o * HS + hs], gi.w, ri), geo.deg2rad, dx, dy);
                 unsigned *m = gmask + pb * (VC_ROWS / 2);
-                vc_march(geo, wall, row, col, dx, dy, gi.z, 1.0, [&](int r, int c) {
-                    const int wr = r - row + gi.z, wc = c - col + gi.z;
-                    atomicOr(&m[wr >> 1], 1u << (wc + 16 * (wr & 1)));
-                });
+                for (int ri = tid & 31; ri < NRAY; ri += 32) {
+                    double dx, dy;
+                    if (shared_dirs) { const double2 d = dirs[hs * NRAY + ri]; dx = d.x; dy = d.y; }
+                    else ray_dir(vc_ray_angle_deg(fov, D.vg_hval[o * HS + hs], gi.w, ri), geo.deg2rad, dx, dy);
+                    vc_march(geo, wall, row, col, dx, dy, gi.z, 1.0, [&](int r, int c) {
+                        const int wr = r - row + gi.z, wc = c - col + gi.z;
+                        atomicOr(&m[wr >> 1], 1u << (wc + 16 * (wr & 1)));
+                    });
+                }
             }
             // the guard's own tile is always lit (visibility.py:59)
             for (int pb = tid; pb < np; pb += VC_BUILD_THREADS) atomicOr(&gmask[pb * (VC_ROWS / 2) + (gi.z >> 1)], 1u << (gi.z + 16 * (gi.z & 1)));
