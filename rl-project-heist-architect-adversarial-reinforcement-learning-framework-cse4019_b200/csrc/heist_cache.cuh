@@ -333,15 +333,32 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
         if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = sh; D.vc_lo[o] = dom_lo; }
         // ---- 4. coarse index: points below each 1-degree bucket start ----
         // IX[q] = first index i with p[i] >= dom_lo + q  (p[i]: even i from S.end, odd from S.key; p[n_points] = +inf).
-        // Point i answers every bucket q with p[i - 1] < dom_lo + q <= p[i]: each thread fills its points' buckets
-        // (the comparisons are the definition's own; the start estimate only saves steps).
+        // Point i answers the buckets q with p[i - 1] < dom_lo + q <= p[i] (the definition's own comparisons): it marks
+        // the first of them, a running maximum over the buckets fills in the rest.
         uint16_t *IX = D.vc_idx + o * VC_IDX;
-        for (int i = tid; i <= n_points; i += VC_BUILD_THREADS) {
-            const double prev = i == 0 ? -1e308 : (((i - 1) & 1) ? S.key[((i - 1) >> 1) + 1] : S.end[(i - 1) >> 1]);
+        unsigned short *opens = S.newidx;   // (free after the compaction; VC_IDX <= VC_RAW)
+        for (int q = tid; q < VC_IDX; q += VC_BUILD_THREADS) opens[q] = 0;
+        __syncthreads();
+        for (int i = 1 + tid; i <= n_points; i += VC_BUILD_THREADS) {
+            const double prev = ((i - 1) & 1) ? S.key[((i - 1) >> 1) + 1] : S.end[(i - 1) >> 1];
             const double cur = i == n_points ? 1e308 : ((i & 1) ? S.key[(i >> 1) + 1] : S.end[i >> 1]);
-            int q = i == 0 ? 0 : max(0, min(VC_IDX, (int)floor(prev - dom_lo) - 1));
+            int q = max(0, min(VC_IDX, (int)floor(prev - dom_lo) - 1));
             while (q < VC_IDX && !(dom_lo + (double)q > prev)) ++q;
-            for (; q < VC_IDX && dom_lo + (double)q <= cur; ++q) IX[q] = (uint16_t)i;
+            if (q < VC_IDX && dom_lo + (double)q <= cur) opens[q] = (unsigned short)i;
+        }
+        __syncthreads();
+        {
+            constexpr int QB = (VC_IDX + VC_BUILD_THREADS - 1) / VC_BUILD_THREADS;
+            int mine = 0;
+#pragma unroll
+            for (int u = 0; u < QB; ++u) { const int q = tid * QB + u; if (q < VC_IDX) mine = max(mine, (int)opens[q]); }
+            const double before = vc_block_exscan_max((double)mine, S.red_d, tid);
+            int run = before > 0.0 ? (int)before : 0;
+#pragma unroll
+            for (int u = 0; u < QB; ++u) {
+                const int q = tid * QB + u;
+                if (q < VC_IDX) { run = max(run, (int)opens[q]); IX[q] = (uint16_t)run; }
+            }
         }
         __syncthreads();
     }
