@@ -116,12 +116,11 @@ __device__ __forceinline__ bool vc_guard_cacheable(double fov, int range, int nu
 struct VcSmem {
     double key[VC_RAW];   // merged band starts (sorted)
     double end[VC_RAW];   // ... and ends
-    unsigned first_flag[VC_BUILD_THREADS];   // merge scan: does the thread's first position open a band
-    unsigned short first_pos[VC_RAW];        // ... first position of merged band i
+    unsigned char first_flag[VC_BUILD_THREADS];   // merge scan: does the thread's first position open a band
     uint4 gm[VC_POINTS / 2][2];       // gap masks before compaction
-    unsigned short members[VC_RAW];   // 1: merged band i comes from a single raw band (one tie crossing)
-    unsigned short newidx[VC_RAW];    // band i -> index after dropping redundant bands (0xffff: dropped)
-    unsigned mask[VC_ROWS];
+    unsigned char members[VC_RAW];    // 1: merged band i comes from a single raw band (one tie crossing); saturates at 255
+    unsigned short newidx[VC_RAW];    // band i -> index after dropping redundant bands (0xffff: dropped); before that,
+                                      //   the merge scan's first position of merged band i; afterwards, the index marks
     uint32_t wall[HEIST_MAX_DIM * 2];   // the env's wall rows
     double red_d[VC_BUILD_THREADS / 32];
     int red_i[VC_BUILD_THREADS / 32];
@@ -162,7 +161,7 @@ __device__ __forceinline__ int vc_block_exscan_sum(int v, int *red, int tid, int
 }
 
 // One CTA per env: tables of all its cameras and guards.  Launched after every k_set_layout.
-__global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
+__global__ void __launch_bounds__(VC_BUILD_THREADS, 6) k_build_cache(Dev D) {
     __shared__ VcSmem S;
     const int env = blockIdx.x, tid = threadIdx.x;
     const int n_cams = D.env_s[(size_t)env * 4 + 0], n_guards = D.env_s[(size_t)env * 4 + 1];
@@ -234,9 +233,9 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
                 if (p < n_raw && st[u] < 1e308 && (p == 0 || st[u] > pm)) { flags |= 1u << u; ++cnt; }
                 pm = fmax(pm, en[u]);
             }
-            unsigned *first_flag = S.first_flag;
-            unsigned short *first_pos = S.first_pos;
-            first_flag[tid] = flags & 1u;
+            unsigned char *first_flag = S.first_flag;
+            unsigned short *first_pos = S.newidx;
+            first_flag[tid] = (unsigned char)(flags & 1u);
             int total;
             int bid = vc_block_exscan_sum(cnt, S.red_i, tid, total) - 1;   // band of the position before this thread's first
             const int bid0 = bid;
@@ -255,7 +254,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 5) k_build_cache(Dev D) {
                 if (flags & (1u << u)) ++bid;
                 pm = fmax(pm, en[u]);
                 const bool next_opens = (p + 1 >= n_raw) || (u + 1 < PER ? (flags >> (u + 1)) & 1u : first_flag[tid + 1]);
-                if (next_opens) { S.end[bid] = pm; S.members[bid] = (unsigned short)(p - (int)first_pos[bid] + 1); }
+                if (next_opens) { S.end[bid] = pm; S.members[bid] = (unsigned char)min(255, p - (int)first_pos[bid] + 1); }
             }
             __syncthreads();
             nb0 = total;   // gap g lies between band g and band g + 1
