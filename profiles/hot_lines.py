@@ -1,6 +1,6 @@
 """Per-source-line instruction / stall-sample shares of one kernel in an .ncu-rep (read here, no GPU).
 
-usage: python profiles/hot_lines.py report.ncu-rep libheist_b200.so kernel-substring [top]
+usage: python profiles/hot_lines.py report.ncu-rep libheist_b200.so kernel-substring [top [stall]]
 Joins the ncu SASS source page with nvdisasm line info of the same build (-lineinfo)."""
 import collections, csv, glob, io, os, re, subprocess, sys, tempfile
 
@@ -8,6 +8,7 @@ import collections, csv, glob, io, os, re, subprocess, sys, tempfile
 def main():
     rep, so, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
+    by_stall = len(sys.argv) > 5 and sys.argv[5] == "stall"   # sort by stall samples instead of instructions
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern, "-c", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, data = rows[1], rows[2:]
@@ -42,7 +43,7 @@ def main():
         agg[ln] += int(r[iex]); smp[ln] += int(r[ismp]); thr[ln] += float(r[ithr]) * int(r[iex])
     tot, tots = sum(agg.values()), max(1, sum(smp.values()))
     print(f"total warp-instructions {tot}, samples {tots}")
-    for ln, c in sorted(agg.items(), key=lambda x: -x[1])[:top]:
+    for ln, c in sorted(agg.items(), key=lambda x: -(smp[x[0]] if by_stall else x[1]))[:top]:
         print(f"{ln[0]}:{ln[1]:4d}  inst {c / tot * 100:5.2f}%  stall-samples {smp[ln] / tots * 100:5.2f}%  lanes {thr[ln] / max(c, 1):4.1f}")
 
 

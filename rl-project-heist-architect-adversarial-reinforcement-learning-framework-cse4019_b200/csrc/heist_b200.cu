@@ -294,7 +294,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         if (!disabled && need < free_b / 2 && seq_fits) {
             h->cache_bytes = need;
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
-            A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc);
+            A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc * 2);
             A(d.vg_mask, N * d.Kg * d.L * HS * VC_ROWS); A(d.vg_hval, N * d.Kg * HS);
             A(d.vg_hslot, N * d.Kg * d.L); A(d.vg_nh, N * d.Kg);
             if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc (visibility cache): %s", cudaGetErrorString(e)); }
@@ -543,12 +543,33 @@ struct HostIO {
 // FAST_PIPE_BLOCKS each (200 ticks = 25 blocks -> 5 chunks of 40 ticks): chunk i covers blocks [b0, b0 + nb).
 struct ChunkPlan {
     int n, total_blocks;
-    int first_block(int i) const { const int q = total_blocks / n, r = total_blocks % n; return i * q + std::min(i, r); }
+    int start[FAST_PIPE_MAX + 2];   // first tick block of chunk i; start[n] = total_blocks
+    int first_block(int i) const { return start[i]; }
 };
 static ChunkPlan chunk_plan(int total) {
     ChunkPlan p;
     p.total_blocks = (total + FAST_TB - 1) / FAST_TB;
+    // debug knob: explicit chunk sizes in tick blocks, e.g. HEIST_CHUNK_PLAN=7,7,6,3,2 (ignored unless they add up)
+    static const char *forced = getenv("HEIST_CHUNK_PLAN");
+    if (forced) {
+        int sizes[FAST_PIPE_MAX], k = 0, sum = 0;
+        for (const char *q = forced; *q && k < FAST_PIPE_MAX;) {
+            const int v = atoi(q);
+            if (v < 1 || v > FAST_PIPE_BLOCKS) { k = 0; break; }
+            sizes[k++] = v; sum += v;
+            while (*q && *q != ',') ++q;
+            if (*q == ',') ++q;
+        }
+        if (k >= 1 && sum == p.total_blocks) {
+            p.n = k; p.start[0] = 0;
+            for (int i = 0; i < k; ++i) p.start[i + 1] = p.start[i] + sizes[i];
+            return p;
+        }
+    }
     p.n = std::max(1, (p.total_blocks + FAST_PIPE_BLOCKS - 1) / FAST_PIPE_BLOCKS);
+    if (p.n > FAST_PIPE_MAX) { p.start[0] = 0; p.start[1] = p.total_blocks; return p; }   // (not pipelined: see fast_pipelined)
+    const int q = p.total_blocks / p.n, r = p.total_blocks % p.n;
+    for (int i = 0; i <= p.n; ++i) p.start[i] = i * q + std::min(i, r);
     return p;
 }
 

@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 6) k_build_cache(Dev D) {
         // padding: above every ray (real points are < 2^29, the first ray is clamped to +-2^29: no overflow in
         // point - first_ray + round_up, and (2^30 - 2^29) >> sh exceeds the ray count by construction of sh)
         for (int i = n_points + tid; i < VC_POINTS; i += VC_BUILD_THREADS) P[i] = 0x3fffffff;
-        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = sh; D.vc_lo[o] = dom_lo; }
+        if (tid == 0) { D.vc_meta[o * 2] = n_points; D.vc_meta[o * 2 + 1] = sh; D.vc_lo[o * 2] = dom_lo; D.vc_lo[o * 2 + 1] = fx_scale; }
         // ---- 4. coarse index: points below each 1-degree bucket start ----
         // IX[q] = first index i with p[i] >= dom_lo + q  (p[i]: even i from S.end, odd from S.key; p[n_points] = +inf).
         // Point i answers the buckets q with p[i - 1] < dom_lo + q <= p[i] (the definition's own comparisons): it marks

@@ -60,7 +60,7 @@ struct Dev {
     uint16_t *vc_mask;    // [N][Kc][VC_POINTS/2][VC_ROWS] window bitmap of gap g
     uint16_t *vc_idx;     // [N][Kc][VC_IDX] coarse index: boundary points below each 1-degree bucket
     int32_t *vc_meta;     // [N][Kc][2] n_points (-1: not cacheable), fixed-point shift of vc_p
-    double *vc_lo;        // [N][Kc] lower end of the cached angle domain
+    double *vc_lo;        // [N][Kc][2] lower end of the cached angle domain; fixed-point units per degree (fx_scale)
     uint16_t *vg_mask;    // [N][Kg][L][L+1][VC_ROWS] guard cone per (waypoint, heading slot)
     double *vg_hval;      // [N][Kg][L+1] distinct headings a guard can carry
     uint8_t *vg_hslot;    // [N][Kg][L] slot of guard_head[k] (255: unchanged)

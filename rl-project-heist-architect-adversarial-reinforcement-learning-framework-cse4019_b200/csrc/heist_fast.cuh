@@ -243,10 +243,9 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
         }
         Cm.h0 = h0;
         Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
-        Cm.dom_lo = D.vc_lo[o];
+        { const double2 lf = *reinterpret_cast<const double2 *>(D.vc_lo + o * 2); Cm.dom_lo = lf.x; Cm.fx_scale = lf.y; }
         Cm.n_gaps = D.vc_meta[o * 2] >> 1;
         Cm.sh = D.vc_meta[o * 2 + 1];
-        Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
         Cm.P2 = reinterpret_cast<const int2 *>(D.vc_p + o * VC_POINTS);
         Cm.MK4 = reinterpret_cast<const uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
     }
@@ -361,18 +360,20 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
     const int env = blockIdx.x, b = blockIdx.y * (nthr >> 5) + warp;
     if (!D.env_cached[env]) return;   // CTA-uniform
     const int Kc = D.Kc, RW = D.RW;
-    unsigned char *sp = smem;
-    FastCam *cams = reinterpret_cast<FastCam *>(sp);   sp += (size_t)Kc * sizeof(FastCam);
-    int2 *P2s = reinterpret_cast<int2 *>(sp);           sp += (size_t)CVS_P2 * 8;
-    uint4 *M0s = reinterpret_cast<uint4 *>(sp);         sp += (size_t)(VC_POINTS / 2) * 16;   // first / second half of the masks,
-    uint4 *M1s = reinterpret_cast<uint4 *>(sp);         sp += (size_t)(VC_POINTS / 2) * 16;   // split: conflict-free LDS.128
-    sp += (size_t)warp * camvis_staged_warp_bytes(RW, Kc);
-    double *h0_s = reinterpret_cast<double *>(sp);      sp += (size_t)Kc * 8;
-    double *pre_head = reinterpret_cast<double *>(sp);  sp += (size_t)FAST_TB * Kc * 8;   // [tick][camera]
-    int *pre_s0 = reinterpret_cast<int *>(sp);          sp += (size_t)FAST_TB * Kc * 4;
-    int *pre_fx = reinterpret_cast<int *>(sp);          sp += (size_t)FAST_TB * Kc * 4;
-    uint32_t *mask_s = reinterpret_cast<uint32_t *>(sp); sp += (size_t)FAST_TB * 32;      // [tick] window mask of the camera in hand
-    uint32_t *vis_s = reinterpret_cast<uint32_t *>(sp);                                    // [tick][RW]
+    unsigned off = 0;   // (32-bit offsets: the carving is a handful of integer adds)
+    auto take = [&](unsigned bytes) { unsigned char *p = smem + off; off += bytes; return p; };
+    FastCam *cams = reinterpret_cast<FastCam *>(take((unsigned)Kc * (unsigned)sizeof(FastCam)));
+    int2 *P2s = reinterpret_cast<int2 *>(take(CVS_P2 * 8));
+    uint4 *M0s = reinterpret_cast<uint4 *>(take((VC_POINTS / 2) * 16));   // first / second half of the masks,
+    uint4 *M1s = reinterpret_cast<uint4 *>(take((VC_POINTS / 2) * 16));   // split: conflict-free LDS.128
+    const unsigned vis_bytes = ((unsigned)FAST_TB * (unsigned)RW * 4u + 15u) & ~15u;
+    off += (unsigned)warp * ((unsigned)Kc * (8u + FAST_TB * 16u) + FAST_TB * 32u + vis_bytes);   // = camvis_staged_warp_bytes
+    double *h0_s = reinterpret_cast<double *>(take((unsigned)Kc * 8u));
+    double *pre_head = reinterpret_cast<double *>(take((unsigned)(FAST_TB * Kc) * 8u));   // [tick][camera]
+    int *pre_s0 = reinterpret_cast<int *>(take((unsigned)(FAST_TB * Kc) * 4u));
+    int *pre_fx = reinterpret_cast<int *>(take((unsigned)(FAST_TB * Kc) * 4u));
+    uint32_t *mask_s = reinterpret_cast<uint32_t *>(take(FAST_TB * 32));                  // [tick] window mask of the camera in hand
+    uint32_t *vis_s = reinterpret_cast<uint32_t *>(take(vis_bytes));                      // [tick][RW]
     const int n_cams = D.env_s[(size_t)env * 4];
     if (tid < n_cams) {
         const size_t o = (size_t)env * Kc + tid;
@@ -381,10 +382,9 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         Cm.fov = D.cam_f[o * 2]; Cm.speed = D.cam_f[o * 2 + 1];
         Cm.h0 = 0.0;
         Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
-        Cm.dom_lo = D.vc_lo[o];
+        { const double2 lf = *reinterpret_cast<const double2 *>(D.vc_lo + o * 2); Cm.dom_lo = lf.x; Cm.fx_scale = lf.y; }
         Cm.n_gaps = D.vc_meta[o * 2] >> 1;
         Cm.sh = D.vc_meta[o * 2 + 1];
-        Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
         Cm.P2 = reinterpret_cast<const int2 *>(D.vc_p + o * VC_POINTS);
         Cm.MK4 = reinterpret_cast<const uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
     }
@@ -392,7 +392,8 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
     const int t_begin = b * FAST_TB, t_end = active ? min(T, (b + 1) * FAST_TB) : t_begin;
     const int n_t = t_end - t_begin;
     if (active && lane < n_cams) h0_s[lane] = heads[((size_t)b * D.N + env) * Kc + lane];
-    for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
+    if (!(RPL == 1 && W == 1))   // (one-word grids keep their rows in registers; vis_s then only serves the exact path)
+        for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
     __syncthreads();
     // Per (tick, camera) of the block, in parallel lanes: heading, window start from the coarse index, first ray in
     // fixed point (see k_cam_vis).
@@ -513,6 +514,8 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
             }
         }
         if (bands) {   // warp-uniform; rare
+            if (RPL == 1 && W == 1 && !any_exact)
+                for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
             any_exact = true;
             __syncwarp();
             for (int t2 = 0; t2 < n_t; ++t2) {
@@ -531,9 +534,10 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         if (RPL == 1 && W == 1) {
             if (lane < RW) {
                 dst += lane;
+                const uint32_t *xs = vis_s + lane;
 #pragma unroll
-                for (int tt = 0; tt < FAST_TB; ++tt)
-                    if (tt < n_t) dst[tt * stride] = any_exact ? (vr[tt] | vis_s[tt * RW + lane]) : vr[tt];
+                for (int tt = 0; tt < FAST_TB; ++tt, dst += stride, xs += RW)   // (pointer steps: no 64-bit multiply per store)
+                    if (tt < n_t) *dst = any_exact ? (vr[tt] | *xs) : vr[tt];
             }
         } else {
             for (int tt = 0; tt < n_t; ++tt, dst += stride)

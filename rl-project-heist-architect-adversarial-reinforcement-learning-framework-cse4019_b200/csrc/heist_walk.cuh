@@ -27,7 +27,7 @@ __host__ __device__ inline size_t walk_warp_bytes(int RW, int Kc) {   // fused m
 }
 
 template <int RPL, int W>
-__global__ void __launch_bounds__(WALK_WARPS * 32, 5)
+__global__ void __launch_bounds__(WALK_WARPS * 32, 7)
 k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
        double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
        uint32_t *buf, int write_traj, int do_reset, const uint8_t *__restrict__ mask, int store_heading,
@@ -141,10 +141,9 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
             if (advance) { h = py_mod360(__dadd_rn(h, Cm.speed)); D.cam_heading[o] = h; }
             Cm.h0 = h;
             Cm.row = ci[0]; Cm.col = ci[1]; Cm.range = ci[2]; Cm.num_rays = ci[3];
-            Cm.dom_lo = D.vc_lo[o];
+            { const double2 lf = *reinterpret_cast<const double2 *>(D.vc_lo + o * 2); Cm.dom_lo = lf.x; Cm.fx_scale = lf.y; }
             Cm.n_gaps = D.vc_meta[o * 2] >> 1;
             Cm.sh = D.vc_meta[o * 2 + 1];
-            Cm.fx_scale = (1.0 / (Cm.fov / (double)Cm.num_rays)) * (double)(1 << Cm.sh);
             Cm.P2 = reinterpret_cast<const int2 *>(D.vc_p + o * VC_POINTS);
             Cm.MK4 = reinterpret_cast<const uint4 *>(D.vc_mask + o * (size_t)(VC_POINTS / 2) * VC_ROWS);
             const double base = h - Cm.fov * 0.5;
