@@ -520,6 +520,12 @@ static void launch_finish(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
     const dim3 g3((unsigned)((h->N + 7) / 8), (unsigned)(!c.write_traj ? 1 : (c.Tc + FIN_TB - 1) / FIN_TB)), g4((unsigned)((h->N + 7) / 8), (unsigned)c.Tc);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
+    if (c.write_traj && c.autoreset && !c.do_reset) {   // the rollout path: guards OR-ed into the finished camera rows
+        if (d.C > 32) k_finish_or<2><<<g3, 256, 0, s>>>(d, c.Tc, c.cam, c.grec, c.fin, c.last_t);
+        else k_finish_or<1><<<g3, 256, 0, s>>>(d, c.Tc, c.cam, c.grec, c.fin, c.last_t);
+        h->launches += 1;
+        return;
+    }
 #define GO(RPL, W)                                                                                       \
     do {                                                                                                 \
         k_finish<RPL, W><<<g3, 256, 0, s>>>(d, c.Tc, c.cam, c.grec, c.fin, c.last_t, !c.write_traj, m);   \

@@ -902,6 +902,56 @@ k_finish(Dev D, int T, uint32_t *buf, const uint16_t *__restrict__ grec, const u
     }
 }
 
+// k_finish_or: k_finish for launches that auto-reset and keep the trajectory (the rollout path).  There every tick of
+// every env is rebuilt, and the camera rows are already in place -- so instead of reading and re-writing whole maps
+// (lane = grid row), a lane takes one (tick, guard) pair of the warp's env and ORs the guard's cone rows into the
+// map with fire-and-forget atomics (RED.OR at L2; only rows with a lit tile are touched, and guards sharing a row
+// need no ordering).  ~4x fewer instructions and no read of the maps.  The env's current map D.vis is refreshed
+// from the finished last tick by the block that holds it (L2 loads: the atomics do not pass through L1).
+template <int W>
+__global__ void __launch_bounds__(256)
+k_finish_or(Dev D, int T, uint32_t *buf, const uint16_t *__restrict__ grec, const uint8_t *__restrict__ fin,
+            const int32_t *__restrict__ last_t) {
+    const int lane = threadIdx.x & 31;   // grid: x = env / 8, y = tick block
+    const int env = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (env >= D.N || !D.env_cached[env]) return;
+    const int lt = last_t[env];
+    const int t0 = blockIdx.y * FIN_TB, t1 = min(T, t0 + FIN_TB);
+    const int n_guards = D.env_s[(size_t)env * 4 + 1], L = D.L, Kg = D.Kg, RW = D.RW;
+    static_assert(FIN_TB * VC_MAX_GUARDS == 32, "lane = (tick, guard)");
+    const int t = t0 + (lane >> 2), g = lane & 3;
+    if (t < t1 && g < n_guards) {
+        const size_t o = (size_t)t * D.N + env, go = (size_t)env * Kg + g;
+        if (fin[o]) {
+            const unsigned rec = grec[o * Kg + g];
+            const int k = rec & 255, hs = rec >> 8;
+            const int rng = D.guard_i[go * 4 + 2];
+            const int row0 = (int)D.guard_path[(go * L + k) * 2] - rng, col0 = (int)D.guard_path[(go * L + k) * 2 + 1] - rng;
+            const uint4 *m = reinterpret_cast<const uint4 *>(D.vg_mask + ((go * L + k) * (size_t)(L + 1) + hs) * VC_ROWS);
+            const uint4 m0 = __ldg(m), m1 = __ldg(m + 1);
+            const uint32_t words[VC_ROWS / 2] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+            uint32_t *rows = buf + o * RW;
+#pragma unroll
+            for (int wr = 0; wr < VC_ROWS; ++wr) {
+                const unsigned bits = (wr & 1) ? (words[wr >> 1] >> 16) : (words[wr >> 1] & 0xffffu);
+                const int r = row0 + wr;
+                if (bits && (unsigned)r < (unsigned)D.R) {
+                    uint32_t v[W];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) v[w] = 0;
+                    fast_or_row<W>(v, bits, col0);
+#pragma unroll
+                    for (int w = 0; w < W; ++w) if (v[w]) atomicOr(&rows[r * W + w], v[w]);
+                }
+            }
+        }
+    }
+    if (lt >= t0 && lt < t1) {
+        __syncwarp();
+        for (int i = lane; i < RW; i += 32) D.vis[(size_t)env * RW + i] = __ldcg(buf + ((size_t)lt * D.N + env) * RW + i);
+    }
+}
+
 // k_fill (no auto-reset only): ticks an env spent done copy its current map, final once k_finish has run.
 template <int W>
 __global__ void __launch_bounds__(256)
