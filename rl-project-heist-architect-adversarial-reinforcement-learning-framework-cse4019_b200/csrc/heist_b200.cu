@@ -542,7 +542,7 @@ struct HostIO {
     const int8_t *actions; float *reward; uint8_t *done, *status;
 };
 
-#define FAST_PIPE_BLOCKS 7     // tick blocks (of FAST_TB ticks) per pipelined chunk, at most
+#define FAST_PIPE_BLOCKS 8     // tick blocks (of FAST_TB ticks) per pipelined chunk, at most
 #define FAST_PIPE_MAX 64       // chunks (events) per launch
 
 // A pipelined launch of `total` ticks is cut into n chunks of (almost) equal numbers of whole tick blocks, at most
@@ -572,10 +572,22 @@ static ChunkPlan chunk_plan(int total) {
             return p;
         }
     }
-    p.n = std::max(1, (p.total_blocks + FAST_PIPE_BLOCKS - 1) / FAST_PIPE_BLOCKS);
-    if (p.n > FAST_PIPE_MAX) { p.start[0] = 0; p.start[1] = p.total_blocks; return p; }   // (not pipelined: see fast_pipelined)
-    const int q = p.total_blocks / p.n, r = p.total_blocks % p.n;
-    for (int i = 0; i <= p.n; ++i) p.start[i] = i * q + std::min(i, r);
+    // The launch ends with the LAST chunk's k_seq and k_finish_or running alone (nothing left to overlap them with),
+    // so the chunks taper towards the end: full chunks first, then 6 and 3 tick blocks (measured on config 2,
+    // T = 200: 8,8,6,3 -> 1.76e9 env-steps/s; the even 7,6,6,6 -> 1.71e9; finer tapers lose to their extra launches).
+    const int B = p.total_blocks, M = FAST_PIPE_BLOCKS;
+    p.start[0] = 0;
+    if (B < 8 || B > M * (FAST_PIPE_MAX - 2)) { p.n = B < 8 ? 1 : FAST_PIPE_MAX + 1; p.start[1] = B; return p; }   // (not pipelined: see fast_pipelined)
+    int sizes[FAST_PIPE_MAX], k = 0;
+    if (B <= M) { sizes[k++] = B / 2; sizes[k++] = B - B / 2; }   // (reversed below: the larger half first)
+    else {
+        int left = B;
+        const int tail[2] = {3, 6};
+        for (int i = 0; left > 0; ++i) { const int want = i < 2 ? tail[i] : M, take = std::min(want, left); sizes[k++] = take; left -= take; }
+        if (k >= 2 && sizes[k - 1] < 3 && sizes[k - 1] + sizes[k - 2] <= M) { sizes[k - 2] += sizes[k - 1]; --k; }   // no tiny first chunk
+    }
+    p.n = k;
+    for (int i = 0; i < k; ++i) p.start[i + 1] = p.start[i] + sizes[k - 1 - i];
     return p;
 }
 
