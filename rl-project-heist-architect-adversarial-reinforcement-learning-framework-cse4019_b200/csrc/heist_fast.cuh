@@ -50,6 +50,7 @@ struct FastCam {
     const int2 *P2;         // gap g = boundary points 2g (its start), 2g + 1 (its end), fixed point (heist_cache.cuh)
     const uint4 *MK4;       // ... and its window mask: uint4 2g, 2g + 1
     int row, col, range, num_rays, n_gaps, sh;
+    int poff, moff;         // k_cam_vis_staged: where the table sits in the CTA's staging buffers (entries)
 };
 
 // Asynchronous global -> shared copies (LDGSTS): fire and forget, no register staging, so a burst of them is one
@@ -395,6 +396,30 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
     if (!(RPL == 1 && W == 1))   // (one-word grids keep their rows in registers; vis_s then only serves the exact path)
         for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
     __syncthreads();
+    uint32_t vr[FAST_TB];   // one-word grids: the ticks' rows (lane = grid row) stay in registers
+#pragma unroll
+    for (int t2 = 0; t2 < FAST_TB; ++t2) vr[t2] = 0;
+    bool any_exact = false;   // exactly marched rays put their tiles into vis_s
+    // The tables of as many cameras as fit are staged TOGETHER (typically all of an env's: ~100 gaps each of 512
+    // slots), back to back: one burst of copies and one barrier pair per group instead of per camera.
+    auto stage_group = [&](int k0) -> int {   // issue the copies of cameras k0 .. k1 - 1 (as many as fit); returns k1
+        int k1 = k0;
+        for (int poff = 0, moff = 0; k1 < n_cams; ++k1) {
+            const FastCam &Cs = cams[k1];
+            const int n = Cs.n_gaps, need_p = ((n + 1) & ~1) + 96, need_m = max(n, 1);   // points: + the padding a scan can run into
+            if (k1 > k0 && (poff + need_p > CVS_P2 || moff + need_m > VC_POINTS / 2)) break;
+            const uint4 *src = reinterpret_cast<const uint4 *>(Cs.P2);
+            uint4 *dst = reinterpret_cast<uint4 *>(P2s + poff);
+            uint4 *m0 = M0s + moff, *m1 = M1s + moff;
+            for (int i = tid; i < (n + 1) / 2; i += nthr) cp_async16(dst + i, src + i);
+            for (int i = tid; i < 2 * n; i += nthr) cp_async16(((i & 1) ? m1 : m0) + (i >> 1), Cs.MK4 + i);
+            for (int i = ((n + 1) & ~1) + tid; i < need_p; i += nthr) P2s[poff + i] = make_int2(0x3fffffff, 0x3fffffff);   // no ray reaches it
+            if (tid == 0) { cams[k1].poff = poff; cams[k1].moff = moff; }
+            poff += need_p; moff += need_m;
+        }
+        return k1;
+    };
+    int k0 = 0, k1 = stage_group(0);   // (cams visible: barrier above) -- the copies fly while the pre-phase computes
     // Per (tick, camera) of the block, in parallel lanes: heading, window start from the coarse index, first ray in
     // fixed point (see k_cam_vis).
     for (int idx = lane; idx < n_t * n_cams; idx += 32) {
@@ -409,25 +434,14 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         pre_s0[tt * Kc + k] = max(0, (int)IX[q] - 1) & ~1;
         pre_fx[tt * Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
     }
-    uint32_t vr[FAST_TB];   // one-word grids: the ticks' rows (lane = grid row) stay in registers
-#pragma unroll
-    for (int t2 = 0; t2 < FAST_TB; ++t2) vr[t2] = 0;
-    bool any_exact = false;   // exactly marched rays put their tiles into vis_s
-    for (int k = 0; k < n_cams; ++k) {
+    for (; k0 < n_cams;) {
+    cp_async_wait_all();
+    __syncthreads();
+    for (int k = k0; k < k1 && active; ++k) {   // (no barrier inside: idle warps go straight to the next group's barrier)
         const FastCam &Cm = cams[k];
-        const int n_gaps = Cm.n_gaps;
-        __syncthreads();   // the previous camera's table is no longer read (k = 0: cams / pre-phase visible)
-        {   // stage: points (8 B per gap) and masks (2 x 16 B per gap, de-interleaved); padding no ray reaches
-            const uint4 *src = reinterpret_cast<const uint4 *>(Cm.P2);
-            uint4 *dst = reinterpret_cast<uint4 *>(P2s);
-            for (int i = tid; i < (n_gaps + 1) / 2; i += nthr) cp_async16(dst + i, src + i);
-            for (int i = tid; i < 2 * n_gaps; i += nthr) cp_async16(((i & 1) ? M1s : M0s) + (i >> 1), Cm.MK4 + i);
-            // padding a scan can run into: it stops within 64 + 32 gaps of the last real one
-            for (int i = ((n_gaps + 1) & ~1) + tid; i < CVS_P2; i += nthr) P2s[i] = make_int2(0x3fffffff, 0x3fffffff);
-            cp_async_wait_all();
-        }
-        __syncthreads();
-        if (!active) continue;   // (no barrier inside: idle warps go straight to the next camera's barrier)
+        const int n_gaps = max(Cm.n_gaps, 1), n_pad = ((Cm.n_gaps + 1) & ~1) + 96;
+        const int2 *P2c = P2s + Cm.poff;
+        const uint4 *M0c = M0s + Cm.moff, *M1c = M1s + Cm.moff;
         const int sh = Cm.sh, NR = Cm.num_rays + 1;
         const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
         // The scan.  With the table in shared memory, per-lane addressing is cheap, so the warp scans the windows of ALL
@@ -446,13 +460,13 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         int in_gaps = 0;          // rays found inside my gaps (rays below the first gap looked at, or past the last real
         bool more = have;         //   one, are outside the window start's guarantee / the cached domain: they count as band rays)
         for (int gbase = s0 >> 1;; gbase += 4 * CVS_GPL) {
-            const int g0 = min(gbase, CVS_P2 - 4 * CVS_GPL) + q;   // (only a finished tick can be clamped)
+            const int g0 = min(gbase, n_pad - 4 * CVS_GPL) + q;   // (only a finished tick can be clamped)
             int hi_last = 0;
 #pragma unroll
             for (int i = 0; i < CVS_GPL; ++i) {
                 const int g = g0 + 4 * i;
-                const int2 p = P2s[g];
-                const uint4 m0 = M0s[min(g, VC_POINTS / 2 - 1)], m1 = M1s[min(g, VC_POINTS / 2 - 1)];
+                const int2 p = P2c[g];
+                const uint4 m0 = M0c[min(g, n_gaps - 1)], m1 = M1c[min(g, n_gaps - 1)];
                 const int lo = max(0, min(NR, (p.x + bias) >> sh)), hi = max(0, min(NR, (p.y + bias) >> sh));
                 const int cnt = more ? hi - lo : 0;
                 in_gaps += cnt;
@@ -521,11 +535,17 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
             for (int t2 = 0; t2 < n_t; ++t2) {
                 if (!((bands >> (4 * t2)) & 0xfu)) continue;
                 const int b2 = ((1 << sh) - 1) - pre_fx[t2 * Kc + k];
-                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2s, pre_head[t2 * Kc + k],
+                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2c, pre_head[t2 * Kc + k],
                                       pre_s0[t2 * Kc + k], b2, lane);
             }
         }
         __syncwarp();
+    }
+    k0 = k1;
+    if (k0 < n_cams) {
+        __syncthreads();   // the group's tables are no longer read
+        k1 = stage_group(k0);
+    }
     }
     __syncwarp();
     {
