@@ -476,7 +476,9 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const unsigned g1 = (unsigned)(((long long)h->N * nblk + FAST_WARPS - 1) / FAST_WARPS);
     const uint8_t *m = c.do_reset ? c.mask : nullptr;
     if (c.heads && nblk >= 2 && !c.do_reset) {   // many ticks: per-camera tables staged in shared memory
-        const int wpc = nblk <= CVS_MAX_WARPS ? nblk : 4;   // warps (tick blocks) per CTA
+        int wpc = nblk <= CVS_MAX_WARPS ? nblk : 4;   // warps (tick blocks) per CTA
+        static const char *wpc_env = getenv("HEIST_CVS_WPC");   // debug knob
+        if (wpc_env && atoi(wpc_env) >= 1 && atoi(wpc_env) <= CVS_MAX_WARPS) wpc = std::min(nblk, atoi(wpc_env));
         const dim3 g((unsigned)h->N, (unsigned)((nblk + wpc - 1) / wpc));
         const size_t sm = camvis_staged_bytes(d.RW, d.Kc, wpc);
 #define GO(RPL, W) k_cam_vis_staged<RPL, W><<<g, wpc * 32, sm, s>>>(d, c.Tc, nblk, c.heads, c.cam)

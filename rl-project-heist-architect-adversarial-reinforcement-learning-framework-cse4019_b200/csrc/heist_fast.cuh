@@ -353,7 +353,7 @@ __device__ __noinline__ void cam_exact_scan_staged(VcGeo D, const uint32_t *__re
 }
 
 template <int RPL, int W>
-__global__ void __launch_bounds__(CVS_MAX_WARPS * 32, 4)
+__global__ void __launch_bounds__(CVS_MAX_WARPS * 32, 6)
 k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr unsigned FULL = 0xffffffffu;
