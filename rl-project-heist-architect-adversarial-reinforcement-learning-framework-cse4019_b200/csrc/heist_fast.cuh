@@ -701,11 +701,18 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         const int words = n_here * RW;
         __syncwarp();
         if (vec_ok) {
-            const int q4 = words >> 2;
-            for (int tt = 0; tt < n_st; ++tt) {
-                const uint4 *src = reinterpret_cast<const uint4 *>(cam_vis + ((size_t)(ts0 + tt) * N + env0) * RW);
-                uint4 *dst = reinterpret_cast<uint4 *>(cam_s + (size_t)tt * SEQ_EPW * RW);
-                for (int i = lane; i < q4; i += 32) cp_async16(dst + i, src + i);
+            // one flat list of 16-byte items over (tick, quad of words): a lane walks it in steps of 32 with pointer
+            // increments -- no division and no 64-bit multiply per item
+            const int q4 = words >> 2, dstep = (SEQ_EPW * RW) >> 2;   // uint4 per tick: real / slot in shared memory
+            const size_t sstep = ((size_t)N * RW) >> 2;               // ... and per tick of cam_vis
+            int tt = lane / q4, i = lane - tt * q4;
+            const int dt = 32 / q4, di = 32 - dt * q4;
+            const uint4 *src = reinterpret_cast<const uint4 *>(cam_vis + ((size_t)ts0 * N + env0) * RW) + (size_t)tt * sstep;
+            uint4 *dst = reinterpret_cast<uint4 *>(cam_s) + tt * dstep;
+            while (tt < n_st) {
+                cp_async16(dst + i, src + i);
+                i += di; tt += dt; src += (size_t)dt * sstep; dst += dt * dstep;
+                if (i >= q4) { i -= q4; ++tt; src += sstep; dst += dstep; }
             }
         } else {
             for (int tt = 0; tt < n_st; ++tt) {
@@ -725,13 +732,15 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         __syncwarp();
     }
     // ---- pass A, the chain: per tick only what the NEXT tick depends on; the rest goes into a one-word record ----
-    for (int t = ts0; t < ts0 + n_st; ++t) {
-        const size_t o = (size_t)t * N + env;
+    uint16_t *grec_p = grec + ((size_t)ts0 * N + env) * Kg + j;   // (stepped per tick: no 64-bit multiply on the chain)
+    for (int t = ts0; t < ts0 + n_st; ++t, grec_p += (size_t)N * Kg) {
         const uint32_t *cam_row = cam_s + ((size_t)(t - ts0) * SEQ_EPW + q) * RW;
         const int a_cur = act_s[(t - ts0) * SEQ_EPW + q];
         const bool live = valid && !(E.flags & F_DONE);   // a done env is not mutated (:232-233)
         // move (:239-246): blocked by the grid edge or a WALL tile
-        const int nr = E.r + (a_cur == 2) - (a_cur == 1), nc = E.c + (a_cur == 4) - (a_cur == 3);
+        // (actions 0..4 = stay, up, down, left, right: row / column step + 1 as 2-bit fields of a constant)
+        const unsigned a2 = 2u * (unsigned)min(max(a_cur, 0), 7);
+        const int nr = E.r + (int)((0x5561u >> a2) & 3u) - 1, nc = E.c + (int)((0x5615u >> a2) & 3u) - 1;
         const bool go_there = live && free_tile(nr, nc);
         E.r = go_there ? nr : E.r;
         E.c = go_there ? nc : E.c;
@@ -783,7 +792,7 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         // the visibility map of tick t is final: tell k_finish how to complete it
         const bool rebuilt = rec & SEQ_REBUILT;
         last = rebuilt ? t : last;
-        if (rebuilt && has_g) grec[o * Kg + j] = (uint16_t)(gk | (ghs << 8));
+        if (rebuilt && has_g) *grec_p = (uint16_t)(gk | (ghs << 8));
         if (valid && j == 0) rec_s[(t - ts0) * SEQ_EPW + q] = rec;
     }
     __syncwarp();
