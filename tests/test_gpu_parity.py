@@ -955,6 +955,54 @@ def test_wild_explicit_layouts_match_oracle(R, C, N, T, seed):
     assert np.array_equal(env.observe().cpu().numpy(), np.stack([e.state_tensor() for e in oenvs]))
 
 
+@pytest.mark.parametrize("R,C,T", [(20, 20, 200), (40, 64, 136)])
+def test_guard_heavy_rollout_on_the_pipelined_path(R, C, T):
+    """Up to four guards per env with wide cones that overlap each other and the camera cones, all table-driven, T
+    ticks through the pipelined launch: the guards are OR-ed into the finished camera rows with atomics (k_finish_or,
+    one- and two-word rows); maps, rewards and final guard states equal the oracle's."""
+    rng = np.random.default_rng(4242 + R)
+    N = 96
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=23, start_pos=(1, 1))
+    env = BatchedHeistEnv(cfg, N, max_walls=32, max_cams=4, max_guards=4, max_path=12)
+    lays = []
+    for _ in range(N):
+        walls = [(int(rng.integers(0, R)), int(rng.integers(0, C))) for _ in range(int(rng.integers(0, 25)))]
+        cams = [{"row": int(rng.integers(0, R)), "col": int(rng.integers(0, C)), "fov_angle": float(rng.uniform(30, 120)),
+                 "heading": float(rng.uniform(0, 360)), "rotation_speed": float(rng.uniform(5, 35)),
+                 "vision_range": int(rng.choice([3, 6, 7]))} for _ in range(int(rng.integers(0, 4)))]
+        guards = []
+        for _ in range(int(rng.integers(1, 5))):
+            r0, c0 = int(rng.integers(2, R - 2)), int(rng.integers(2, C - 2))   # patrols close together: cones overlap
+            path = [(min(R - 1, max(0, r0 + int(rng.integers(-2, 3)))), min(C - 1, max(0, c0 + int(rng.integers(-2, 3)))))
+                    for _ in range(int(rng.integers(1, 13)))]
+            guards.append({"patrol_path": path, "speed": int(rng.choice([1, 1, 2, 3, -1])), "vision_range": int(rng.choice([4, 6, 7])),
+                           "fov_angle": float(rng.choice([90.0, 120.0, 180.0, 57.3]))})
+        lays.append((walls, cams, guards))
+    env.set_layout_explicit(lays, budget=np.full(N, 1000, np.int32))
+    env.check_errors()
+    assert env.cache_stats()[0] == N   # every env on the table-driven path
+    oenvs = []
+    for w, c, g in lays:
+        e = ho.OracleEnv(R, C, max_steps=23, budget=1000)
+        e.set_layout(w, c, g)
+        oenvs.append(e)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, T, N)
+    out = env.step_many(acts, autoreset=True, want_vis=True)
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
+    assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
+    assert np.array_equal(out["reward"].cpu().numpy(), ref["reward"])
+    assert np.array_equal(u32(env.visibility_bits), np.stack([ho.pack_bits(e.visibility) for e in oenvs]))
+    gh, gx = env.guard_heading.cpu().numpy(), env.guard_idx.cpu().numpy()
+    for j, e in enumerate(oenvs):
+        gs, ghead = e.guards_state()
+        ng = e.info()["n_guards"]
+        assert np.array_equal(gx[j, :ng], gs[:, 2]) and np.array_equal(gh[j, :ng], ghead), j
+    env.close()
+
+
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 7, 130])
 def test_env_counts_not_multiple_of_cta(N):
     cfg = EnvironmentConfig(max_steps=40)
