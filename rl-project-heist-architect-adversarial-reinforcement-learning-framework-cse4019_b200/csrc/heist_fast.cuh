@@ -43,8 +43,8 @@ __device__ __forceinline__ int fast_adv0(const Dev &D, int env, int do_reset) {
 
 #define FAST_TB 8      // ticks per k_cam_vis warp
 
-// Per-camera constants of a k_cam_vis warp (shared memory).
-struct FastCam {
+// Per-camera constants of a k_cam_vis warp (shared memory; a multiple of 16 bytes: the staged tables follow it).
+struct alignas(16) FastCam {
     double speed, fov, fx_scale, dom_lo;
     double h0;              // heading at the block's first tick
     const int2 *P2;         // gap g = boundary points 2g (its start), 2g + 1 (its end), fixed point (heist_cache.cuh)
@@ -320,7 +320,8 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
 #define CVS_GPL 8      // gaps a lane takes per pass (4 lanes per tick: 32 consecutive gaps per tick and pass)
 
 __host__ __device__ inline size_t camvis_staged_warp_bytes(int RW, int Kc) {
-    return (size_t)Kc * 8 + (size_t)FAST_TB * Kc * 16 + (size_t)FAST_TB * 32 + (((size_t)FAST_TB * RW * 4 + 15) & ~(size_t)15);
+    // h0_s f64[Kc] | pre_fx i32[8][Kc] | pre_s0 u16[8][Kc] | (16-byte aligned) mask_s 8 x 32 B | vis_s u32[8][RW]
+    return ((((size_t)Kc * (8 + FAST_TB * 6)) + 15) & ~(size_t)15) + (size_t)FAST_TB * 32 + (((size_t)FAST_TB * RW * 4 + 15) & ~(size_t)15);
 }
 #define CVS_MAX_WARPS 8
 __host__ __device__ inline size_t camvis_staged_bytes(int RW, int Kc, int warps) {
@@ -368,11 +369,12 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
     uint4 *M0s = reinterpret_cast<uint4 *>(take((VC_POINTS / 2) * 16));   // first / second half of the masks,
     uint4 *M1s = reinterpret_cast<uint4 *>(take((VC_POINTS / 2) * 16));   // split: conflict-free LDS.128
     const unsigned vis_bytes = ((unsigned)FAST_TB * (unsigned)RW * 4u + 15u) & ~15u;
-    off += (unsigned)warp * ((unsigned)Kc * (8u + FAST_TB * 16u) + FAST_TB * 32u + vis_bytes);   // = camvis_staged_warp_bytes
-    double *h0_s = reinterpret_cast<double *>(take((unsigned)Kc * 8u));
-    double *pre_head = reinterpret_cast<double *>(take((unsigned)(FAST_TB * Kc) * 8u));   // [tick][camera]
-    int *pre_s0 = reinterpret_cast<int *>(take((unsigned)(FAST_TB * Kc) * 4u));
-    int *pre_fx = reinterpret_cast<int *>(take((unsigned)(FAST_TB * Kc) * 4u));
+    const unsigned pre_bytes = ((unsigned)Kc * (8u + FAST_TB * 6u) + 15u) & ~15u;
+    off += (unsigned)warp * (pre_bytes + FAST_TB * 32u + vis_bytes);   // = camvis_staged_warp_bytes
+    unsigned char *pre_base = take(pre_bytes);
+    double *h0_s = reinterpret_cast<double *>(pre_base);                                            // heading at the block's first tick
+    int *pre_fx = reinterpret_cast<int *>(pre_base + (unsigned)Kc * 8u);                            // [tick][camera] first ray, fixed point
+    uint16_t *pre_s0 = reinterpret_cast<uint16_t *>(pre_base + (unsigned)Kc * (8u + FAST_TB * 4u));  // [tick][camera] window start (point index)
     uint32_t *mask_s = reinterpret_cast<uint32_t *>(take(FAST_TB * 32));                  // [tick] window mask of the camera in hand
     uint32_t *vis_s = reinterpret_cast<uint32_t *>(take(vis_bytes));                      // [tick][RW]
     const int n_cams = D.env_s[(size_t)env * 4];
@@ -430,8 +432,7 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         for (int a = 0; a < tt; ++a) h = py_mod360(__dadd_rn(h, Cm.speed));
         const double base = h - Cm.fov * 0.5;
         const int q = max(0, min(VC_IDX - 1, (int)floor(base - Cm.dom_lo)));
-        pre_head[tt * Kc + k] = h;
-        pre_s0[tt * Kc + k] = max(0, (int)IX[q] - 1) & ~1;
+        pre_s0[tt * Kc + k] = (uint16_t)(max(0, (int)IX[q] - 1) & ~1);
         pre_fx[tt * Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
     }
     for (; k0 < n_cams;) {
@@ -535,8 +536,9 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
             for (int t2 = 0; t2 < n_t; ++t2) {
                 if (!((bands >> (4 * t2)) & 0xfu)) continue;
                 const int b2 = ((1 << sh) - 1) - pre_fx[t2 * Kc + k];
-                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2c, pre_head[t2 * Kc + k],
-                                      pre_s0[t2 * Kc + k], b2, lane);
+                double h = h0_s[k];   // the tick's heading again (as in the pre-phase)
+                for (int a = 0; a < t2; ++a) h = py_mod360(__dadd_rn(h, Cm.speed));
+                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2c, h, (int)pre_s0[t2 * Kc + k], b2, lane);
             }
         }
         __syncwarp();
