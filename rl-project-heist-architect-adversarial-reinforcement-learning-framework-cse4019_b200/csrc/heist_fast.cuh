@@ -308,13 +308,14 @@ k_cam_vis(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__
 }
 
 // ---------------------------------------------------------------------------------------------
-// k_cam_vis_staged: the many-tick variant.  A CTA owns one env and FAST_WARPS consecutive tick blocks (32 ticks:
-// cameras turn 5-35 degrees per tick, so such a stretch sweeps a camera's whole table); warp = tick block.  Per
-// camera the CTA first STAGES the camera's table -- boundary points and gap masks, ~10 KB, one coalesced copy --
-// in shared memory, then every warp scans the windows of its 8 ticks from there.  The scan's loads are then
-// shared-memory loads (~30 cycles instead of an L2 / HBM round trip per (tick, camera)), both 32-gap passes of an
-// iteration are evaluated together (independent instruction streams), and a table is read from HBM once per 32
-// ticks.  Rows are accumulated per tick in shared memory (lane = grid row).
+// k_cam_vis_staged: the many-tick variant.  A CTA owns one env and the tick blocks of one pipelined chunk (up to 8:
+// cameras turn 5-35 degrees per tick, so such a stretch sweeps a camera's whole table); warp = tick block.  The CTA
+// STAGES the tables of as many of the env's cameras as fit -- boundary points and gap masks, ~4 KB per camera, one
+// burst of cp.async that is in flight while the warps compute their ticks' headings and window starts -- in shared
+// memory, then every warp scans the windows of its 8 ticks from there, lane = (tick, quarter of the window's gaps).
+// The scan's loads are shared-memory loads (~30 cycles instead of an L2 / HBM round trip per (tick, camera)) and a
+// table is read from HBM once per chunk.  Rows are accumulated per tick in registers (one-word grids, lane = grid
+// row) or shared memory.  Compiled for six CTAs per SM (40 registers): the kernel is latency-bound, occupancy pays.
 // ---------------------------------------------------------------------------------------------
 #define CVS_P2 640     // staged boundary-point pairs: VC_POINTS / 2 real slots + padding a scan can run into
 #define CVS_GPL 8      // gaps a lane takes per pass (4 lanes per tick: 32 consecutive gaps per tick and pass)
@@ -435,119 +436,119 @@ k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint3
         pre_s0[tt * Kc + k] = (uint16_t)(max(0, (int)IX[q] - 1) & ~1);
         pre_fx[tt * Kc + k] = (int)fmax(-536870912.0, fmin(536870912.0, floor((base - Cm.dom_lo) * Cm.fx_scale)));
     }
-    for (; k0 < n_cams;) {
-    cp_async_wait_all();
-    __syncthreads();
-    for (int k = k0; k < k1 && active; ++k) {   // (no barrier inside: idle warps go straight to the next group's barrier)
-        const FastCam &Cm = cams[k];
-        const int n_gaps = max(Cm.n_gaps, 1), n_pad = ((Cm.n_gaps + 1) & ~1) + 96;
-        const int2 *P2c = P2s + Cm.poff;
-        const uint4 *M0c = M0s + Cm.moff, *M1c = M1s + Cm.moff;
-        const int sh = Cm.sh, NR = Cm.num_rays + 1;
-        const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
-        // The scan.  With the table in shared memory, per-lane addressing is cheap, so the warp scans the windows of ALL
-        // its ticks at once: lane = (tick tt, q); in a pass the four lanes of a tick take the gaps gbase + 4 i + q,
-        // i < CVS_GPL (32 consecutive gaps per tick and pass, the four lanes on four neighbouring table entries).  Per
-        // gap: ray counts below its two boundary points from the tick's first-ray position; the gap holds a ray iff
-        // they differ (its 32-byte mask is OR-ed in, branch-free).  Rays inside BANDS are found by counting: every ray
-        // lies either in a gap or in a band, so the bands hold one iff the gaps' counts do not add up to all rays.
-        const int tt = lane >> 2, q = lane & 3;
-        const bool have = tt < n_t;
-        int bias = 0, s0 = 0;
-        if (have) { bias = ((1 << sh) - 1) - pre_fx[tt * Kc + k]; s0 = pre_s0[tt * Kc + k]; }   // rays below point p: clamp((p + bias) >> sh, 0, NR)
-        uint32_t acc[VC_ROWS / 2];
+    while (k0 < n_cams) {   // one group of staged tables per trip
+        cp_async_wait_all();
+        __syncthreads();
+        for (int k = k0; k < k1 && active; ++k) {   // (no barrier inside: idle warps go straight to the next group's barrier)
+            const FastCam &Cm = cams[k];
+            const int n_gaps = max(Cm.n_gaps, 1), n_pad = ((Cm.n_gaps + 1) & ~1) + 96;
+            const int2 *P2c = P2s + Cm.poff;
+            const uint4 *M0c = M0s + Cm.moff, *M1c = M1s + Cm.moff;
+            const int sh = Cm.sh, NR = Cm.num_rays + 1;
+            const int row0 = Cm.row - Cm.range, col0 = Cm.col - Cm.range, nrow = 2 * Cm.range;
+            // The scan.  With the table in shared memory, per-lane addressing is cheap, so the warp scans the windows of ALL
+            // its ticks at once: lane = (tick tt, q); in a pass the four lanes of a tick take the gaps gbase + 4 i + q,
+            // i < CVS_GPL (32 consecutive gaps per tick and pass, the four lanes on four neighbouring table entries).  Per
+            // gap: ray counts below its two boundary points from the tick's first-ray position; the gap holds a ray iff
+            // they differ (its 32-byte mask is OR-ed in, branch-free).  Rays inside BANDS are found by counting: every ray
+            // lies either in a gap or in a band, so the bands hold one iff the gaps' counts do not add up to all rays.
+            const int tt = lane >> 2, q = lane & 3;
+            const bool have = tt < n_t;
+            int bias = 0, s0 = 0;
+            if (have) { bias = ((1 << sh) - 1) - pre_fx[tt * Kc + k]; s0 = pre_s0[tt * Kc + k]; }   // rays below point p: clamp((p + bias) >> sh, 0, NR)
+            uint32_t acc[VC_ROWS / 2];
 #pragma unroll
-        for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
-        int in_gaps = 0;          // rays found inside my gaps (rays below the first gap looked at, or past the last real
-        bool more = have;         //   one, are outside the window start's guarantee / the cached domain: they count as band rays)
-        for (int gbase = s0 >> 1;; gbase += 4 * CVS_GPL) {
-            const int g0 = min(gbase, n_pad - 4 * CVS_GPL) + q;   // (only a finished tick can be clamped)
-            int hi_last = 0;
+            for (int i = 0; i < VC_ROWS / 2; ++i) acc[i] = 0;
+            int in_gaps = 0;          // rays found inside my gaps (rays below the first gap looked at, or past the last real
+            bool more = have;         //   one, are outside the window start's guarantee / the cached domain: they count as band rays)
+            for (int gbase = s0 >> 1;; gbase += 4 * CVS_GPL) {
+                const int g0 = min(gbase, n_pad - 4 * CVS_GPL) + q;   // (only a finished tick can be clamped)
+                int hi_last = 0;
 #pragma unroll
-            for (int i = 0; i < CVS_GPL; ++i) {
-                const int g = g0 + 4 * i;
-                const int2 p = P2c[g];
-                const uint4 m0 = M0c[min(g, n_gaps - 1)], m1 = M1c[min(g, n_gaps - 1)];
-                const int lo = max(0, min(NR, (p.x + bias) >> sh)), hi = max(0, min(NR, (p.y + bias) >> sh));
-                const int cnt = more ? hi - lo : 0;
-                in_gaps += cnt;
-                const uint32_t sel = cnt > 0 ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
-                or_and(acc[0], m0.x, sel); or_and(acc[1], m0.y, sel); or_and(acc[2], m0.z, sel); or_and(acc[3], m0.w, sel);
-                or_and(acc[4], m1.x, sel); or_and(acc[5], m1.y, sel); or_and(acc[6], m1.z, sel); or_and(acc[7], m1.w, sel);
-                hi_last = hi;
-            }
-            const int carry = __shfl_sync(FULL, hi_last, lane | 3);   // rays below the end of the tick's last gap of this pass
-            more = more && carry < NR;
-            if (!__any_sync(FULL, more)) break;
-        }
-        in_gaps += __shfl_xor_sync(FULL, in_gaps, 1);
-        in_gaps += __shfl_xor_sync(FULL, in_gaps, 2);
-        const bool band = have && in_gaps != NR;
-        // the four quarters of a tick -> one mask per tick, in shared memory
-#pragma unroll
-        for (int i = 0; i < VC_ROWS / 2; ++i) {
-            acc[i] |= __shfl_xor_sync(FULL, acc[i], 1);
-            acc[i] |= __shfl_xor_sync(FULL, acc[i], 2);
-        }
-        const unsigned bands = __ballot_sync(FULL, band);
-        if (q == 0) {
-            reinterpret_cast<uint4 *>(mask_s)[tt * 2] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
-            reinterpret_cast<uint4 *>(mask_s)[tt * 2 + 1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
-        }
-        __syncwarp();
-        // lane = grid row: window row wr of every tick's mask (two 16-bit rows per word) into the tick's row words --
-        // registers for grids of one word per row and lane (up to 32 x 32), shared memory otherwise
-        if (RPL == 1 && W == 1) {
-            const int wr = lane - row0;
-            if (wr >= 0 && wr <= nrow) {
-                const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + wr;
-#pragma unroll
-                for (int t2 = 0; t2 < FAST_TB; ++t2) {
-                    const unsigned bits = mrow[t2 * VC_ROWS];   // (ticks beyond n_t hold stale masks: never written out)
-                    vr[t2] |= col0 >= 0 ? (bits << col0) : (bits >> (-col0));
+                for (int i = 0; i < CVS_GPL; ++i) {
+                    const int g = g0 + 4 * i;
+                    const int2 p = P2c[g];
+                    const uint4 m0 = M0c[min(g, n_gaps - 1)], m1 = M1c[min(g, n_gaps - 1)];
+                    const int lo = max(0, min(NR, (p.x + bias) >> sh)), hi = max(0, min(NR, (p.y + bias) >> sh));
+                    const int cnt = more ? hi - lo : 0;
+                    in_gaps += cnt;
+                    const uint32_t sel = cnt > 0 ? 0xffffffffu : 0u;   // the gap holds a ray: every ray inside marks the same tiles
+                    or_and(acc[0], m0.x, sel); or_and(acc[1], m0.y, sel); or_and(acc[2], m0.z, sel); or_and(acc[3], m0.w, sel);
+                    or_and(acc[4], m1.x, sel); or_and(acc[5], m1.y, sel); or_and(acc[6], m1.z, sel); or_and(acc[7], m1.w, sel);
+                    hi_last = hi;
                 }
+                const int carry = __shfl_sync(FULL, hi_last, lane | 3);   // rays below the end of the tick's last gap of this pass
+                more = more && carry < NR;
+                if (!__any_sync(FULL, more)) break;
             }
-        } else {
-            for (int t2 = 0; t2 < n_t; ++t2) {
-                uint32_t *rows = vis_s + t2 * RW;
-                const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + t2 * VC_ROWS;
+            in_gaps += __shfl_xor_sync(FULL, in_gaps, 1);
+            in_gaps += __shfl_xor_sync(FULL, in_gaps, 2);
+            const bool band = have && in_gaps != NR;
+            // the four quarters of a tick -> one mask per tick, in shared memory
 #pragma unroll
-                for (int a = 0; a < RPL; ++a) {
-                    const int wr = lane + 32 * a - row0;
-                    if (wr >= 0 && wr <= nrow) {
-                        const unsigned bits = mrow[wr];
-                        if (bits) {
-                            uint32_t v[W];
+            for (int i = 0; i < VC_ROWS / 2; ++i) {
+                acc[i] |= __shfl_xor_sync(FULL, acc[i], 1);
+                acc[i] |= __shfl_xor_sync(FULL, acc[i], 2);
+            }
+            const unsigned bands = __ballot_sync(FULL, band);
+            if (q == 0) {
+                reinterpret_cast<uint4 *>(mask_s)[tt * 2] = make_uint4(acc[0], acc[1], acc[2], acc[3]);
+                reinterpret_cast<uint4 *>(mask_s)[tt * 2 + 1] = make_uint4(acc[4], acc[5], acc[6], acc[7]);
+            }
+            __syncwarp();
+            // lane = grid row: window row wr of every tick's mask (two 16-bit rows per word) into the tick's row words --
+            // registers for grids of one word per row and lane (up to 32 x 32), shared memory otherwise
+            if (RPL == 1 && W == 1) {
+                const int wr = lane - row0;
+                if (wr >= 0 && wr <= nrow) {
+                    const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + wr;
 #pragma unroll
-                            for (int w = 0; w < W; ++w) v[w] = 0;
-                            fast_or_row<W>(v, bits, col0);
+                    for (int t2 = 0; t2 < FAST_TB; ++t2) {
+                        const unsigned bits = mrow[t2 * VC_ROWS];   // (ticks beyond n_t hold stale masks: never written out)
+                        vr[t2] |= col0 >= 0 ? (bits << col0) : (bits >> (-col0));
+                    }
+                }
+            } else {
+                for (int t2 = 0; t2 < n_t; ++t2) {
+                    uint32_t *rows = vis_s + t2 * RW;
+                    const uint16_t *mrow = reinterpret_cast<const uint16_t *>(mask_s) + t2 * VC_ROWS;
 #pragma unroll
-                            for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                    for (int a = 0; a < RPL; ++a) {
+                        const int wr = lane + 32 * a - row0;
+                        if (wr >= 0 && wr <= nrow) {
+                            const unsigned bits = mrow[wr];
+                            if (bits) {
+                                uint32_t v[W];
+#pragma unroll
+                                for (int w = 0; w < W; ++w) v[w] = 0;
+                                fast_or_row<W>(v, bits, col0);
+#pragma unroll
+                                for (int w = 0; w < W; ++w) rows[(lane + 32 * a) * W + w] |= v[w];
+                            }
                         }
                     }
                 }
             }
-        }
-        if (bands) {   // warp-uniform; rare
-            if (RPL == 1 && W == 1 && !any_exact)
-                for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
-            any_exact = true;
-            __syncwarp();
-            for (int t2 = 0; t2 < n_t; ++t2) {
-                if (!((bands >> (4 * t2)) & 0xfu)) continue;
-                const int b2 = ((1 << sh) - 1) - pre_fx[t2 * Kc + k];
-                double h = h0_s[k];   // the tick's heading again (as in the pre-phase)
-                for (int a = 0; a < t2; ++a) h = py_mod360(__dadd_rn(h, Cm.speed));
-                cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2c, h, (int)pre_s0[t2 * Kc + k], b2, lane);
+            if (bands) {   // warp-uniform; rare
+                if (RPL == 1 && W == 1 && !any_exact)
+                    for (int i = lane; i < FAST_TB * RW; i += 32) vis_s[i] = 0;
+                any_exact = true;
+                __syncwarp();
+                for (int t2 = 0; t2 < n_t; ++t2) {
+                    if (!((bands >> (4 * t2)) & 0xfu)) continue;
+                    const int b2 = ((1 << sh) - 1) - pre_fx[t2 * Kc + k];
+                    double h = h0_s[k];   // the tick's heading again (as in the pre-phase)
+                    for (int a = 0; a < t2; ++a) h = py_mod360(__dadd_rn(h, Cm.speed));
+                    cam_exact_scan_staged(vc_geo(D), D.wall + (size_t)env * RW, vis_s + t2 * RW, &Cm, P2c, h, (int)pre_s0[t2 * Kc + k], b2, lane);
+                }
             }
+            __syncwarp();
         }
-        __syncwarp();
-    }
-    k0 = k1;
-    if (k0 < n_cams) {
-        __syncthreads();   // the group's tables are no longer read
-        k1 = stage_group(k0);
-    }
+        k0 = k1;
+        if (k0 < n_cams) {
+            __syncthreads();   // the group's tables are no longer read
+            k1 = stage_group(k0);
+        }
     }
     __syncwarp();
     {

@@ -3,20 +3,19 @@
 // Reference: HeistEnvironment.reset / step (environment.py:183-299), Guard.update (security.py:145-159),
 // DynamicVisibilityMap.update (visibility.py:31-65; the guards' part: cones + own tiles).
 //
-// k_cam_vis (heist_fast.cuh) has already written the union of the CAMERA cones of every tick of the chunk into
-// buf[t][env] (cameras never react to the Solver).  What is left is inherently sequential in t -- move, patrol,
-// detection, vault / timeout, rewards, auto-reset -- but tiny, and independent between envs.  Round 1 ran it as one
-// THREAD per env (k_seq: 128 warps for 4 096 envs, each alone on a scheduler, ~500 dependent warp-instructions per tick
-// => a 75 us serial wall per 32-tick chunk) followed by a warp-per-env pass that OR-ed the guards in (k_finish).  Here
-// a warp owns the env for the whole chunk:
-//   * the scalar state (position, tick, guard indices) is warp-uniform; 4 096 warps interleave on the schedulers, so
-//     the per-tick chain is hidden instead of exposed;
-//   * lane = grid row: the env's wall rows live in registers (a move test is one shuffle), the camera rows of the
-//     next ticks are prefetched (they do not depend on the state), the guards' cached cone rows are OR-ed in by the
-//     lane that owns the row, detection is one shuffle of the Solver's row -- and the completed map is written back
-//     in place, so there is no second pass and no (waypoint, slot) record traffic between kernels;
+// One launch = a few ticks (normally ONE: heist_step / heist_reset / heist_step_observe; long rollouts go through
+// k_cam_vis_staged + k_seq + k_finish_or in heist_fast.cuh).  A warp owns the env:
+//   * buf == nullptr (the fused single tick): the camera cones of the tick are scanned right here from the cache
+//     tables in global memory (scan_window), the new headings are stored, and -- for heist_step_observe -- the dense
+//     (3, R, C) state is written from the registers that hold the finished map; otherwise k_cam_vis has already
+//     written the union of the camera cones of every tick into buf[t][env] (cameras never react to the Solver);
+//   * the scalar state (position, tick, guard indices) is warp-uniform;
+//   * lane = grid row: the env's wall rows live in registers (a move test is one shuffle), the guards' cached cone
+//     rows are OR-ed in by the lane that owns the row, detection is one shuffle of the Solver's row;
 //   * lane = tick for the per-tick scalars: actions are fetched 32 ticks at a time (lane l holds tick t0 + l) and
 //     reward / done / status are collected the same way and stored once per 32 ticks.
+// The tick is a chain of dependent round trips (~900 instructions, ~11 us even on an empty GPU), so the kernel is
+// compiled for 7 CTAs per SM: all 4 096 warps of the bench batch are resident at once.
 #pragma once
 #include "heist_fast.cuh"
 
