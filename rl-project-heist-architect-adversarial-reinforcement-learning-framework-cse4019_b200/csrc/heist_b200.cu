@@ -286,7 +286,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
         cudaMemGetInfo(&free_b, &total_b);
         const size_t HS = (size_t)d.L + 1;
         const size_t need = N * d.Kc * ((size_t)VC_POINTS * 4 + (size_t)(VC_POINTS / 2) * VC_ROWS * 2 + VC_IDX * 2 + 24) +
-                            N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L + 4);
+                            N * d.Kg * ((size_t)d.L * HS * VC_ROWS * 2 + HS * 8 + d.L * 5 + 4);
         const bool seq_fits = seq_warp_bytes(d.RW, d.L) <= (size_t)160 * 1024 &&
                               FAST_WARPS * camvis_warp_bytes(d.RW, d.Kc) <= (size_t)160 * 1024 && d.L <= 32;   // lane = waypoint
         const bool disabled = off && off[0] == '1';
@@ -296,7 +296,7 @@ extern "C" int heist_create(const HeistParams *params, int num_envs, int device,
             A(d.vc_p, N * d.Kc * VC_POINTS); A(d.vc_mask, N * d.Kc * (VC_POINTS / 2) * VC_ROWS);
             A(d.vc_idx, N * d.Kc * VC_IDX); A(d.vc_meta, N * d.Kc * 2); A(d.vc_lo, N * d.Kc * 2);
             A(d.vg_mask, N * d.Kg * d.L * HS * VC_ROWS); A(d.vg_hval, N * d.Kg * HS);
-            A(d.vg_hslot, N * d.Kg * d.L); A(d.vg_nh, N * d.Kg);
+            A(d.vg_hslot, N * d.Kg * d.L); A(d.vg_nh, N * d.Kg); A(d.vg_reach, N * d.Kg * d.L);
             if (e != cudaSuccess) { heist_destroy(h); return fail((int)e, "heist_create: cudaMalloc (visibility cache): %s", cudaGetErrorString(e)); }
         } else if (!disabled) {
             // not an error -- every env is ray-marched (same results, several times slower) -- but never silent
@@ -1024,7 +1024,7 @@ extern "C" int heist_check_errors(HeistHandle *h, void *stream) {
                     (flags & ERR_WAYPOINT) ? " guard waypoint outside the grid" : "",
                     (flags & ERR_RAYS) ? " fov/vision_range too large" : "",
                     (flags & ERR_BOUNDS) ? " cell-map access out of range (debug build)" : "",
-                    (flags & ERR_STATE) ? " guard heading in the state view is not one of its path's headings" : "",
+                    (flags & ERR_STATE) ? " guard state in the state view (heading / waypoint) is not one the guard can reach on its path" : "",
                     (flags & ERR_UNCOVERED) ? " layout not covered by the visibility cache (HEIST_MODE_TABLES)" : "");
     }
     return 0;

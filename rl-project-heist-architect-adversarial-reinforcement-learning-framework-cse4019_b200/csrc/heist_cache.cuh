@@ -383,14 +383,41 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 6) k_build_cache(Dev D) {
             }
             D.vg_nh[o] = nh;
             S.n_bands = nh;
-        }
+            // Which (waypoint, slot) pairs can the guard ever be in?  It starts on waypoint 0 with the default heading
+            // (k_set_layout), a reset puts it back there with whatever heading it carries (environment.py:205-208),
+            // and a move from waypoint i lands on i + stride carrying slot hslot[i] (or the old one when the move is
+            // no move, security.py:145-159): a fixed point over at most L words.  Only those cones are built (a
+            // patrol ring: ~11 of 32); the step kernels report a state outside the set (ERR_STATE: hand-written).
+            uint32_t *reach = reinterpret_cast<uint32_t *>(S.members);   // (free after the cameras)
+            const int len = gi.x, stp = len >= 2 ? py_imod(gi.y, len) : 0;
+            for (int k = 0; k < len; ++k) reach[k] = 0;
+            reach[0] = nh >= 32 ? 0xffffffffu : (1u << nh) - 1u;
+            for (bool changed = true; changed;) {
+                changed = false;
+                for (int k = 0; k < len; ++k) {
+                    if (!reach[k]) continue;
+                    int nxt = k + stp; if (nxt >= len) nxt -= len;
+                    const int s = D.vg_hslot[o * D.L + k];
+                    const uint32_t add = s == 255 ? reach[k] : 1u << min(s, 31);
+                    if (add & ~reach[nxt]) { reach[nxt] |= add; changed = true; }
+                }
+            }
+            int n_list = 0;
+            for (int k = 0; k < len; ++k) {
+                D.vg_reach[o * D.L + k] = reach[k];
+                for (int s = 0; s < nh; ++s)
+                    if (((reach[k] >> min(s, 31)) & 1u) && n_list < VC_RAW) S.newidx[n_list++] = (unsigned short)(k * 64 + s);
+            }
+            S.n_raw = n_list;   // (never more than ~300: a waypoint other than 0 carries every slot only behind a chain of
+        }                       //  no-move steps from 0, and every such step is one slot less in the path: the list's 1 024 suffice)
         __syncthreads();
         const int nh = S.n_bands;
         // The masks of all (waypoint, heading slot) pairs at once: one work item per (pair, ray), OR-ed into shared
         // memory (two 16-bit window rows per word, the layout of vg_mask).  A ray's direction depends on the slot and
         // the ray only -- not on the waypoint -- so the directions are evaluated once per (slot, ray) and shared by
         // the waypoints (same arithmetic, same values).
-        const int NRAY = gi.w + 1, n_pair = gi.x * nh;
+        const int NRAY = gi.w + 1, n_pair = S.n_raw;
+        const unsigned short *pair_list = S.newidx;   // waypoint * 64 + slot
         double2 *dirs = reinterpret_cast<double2 *>(S.key);               // key[] + end[]: 2 * VC_RAW doubles, free after the cameras
         unsigned *gmask = reinterpret_cast<unsigned *>(&S.gm[0][0]);      // [pair][VC_ROWS / 2]
         constexpr int PAIR_CAP = (VC_POINTS / 2) * 32 / (VC_ROWS * 2);
@@ -408,7 +435,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 6) k_build_cache(Dev D) {
             for (int i = tid; i < np * (VC_ROWS / 2); i += VC_BUILD_THREADS) gmask[i] = 0;
             __syncthreads();
             for (int pb = tid >> 5; pb < np; pb += VC_BUILD_THREADS / 32) {   // warp = pair, lane = ray
-                const int idx = (p0 + pb) / nh, hs = (p0 + pb) - idx * nh;
+                const int idx = pair_list[p0 + pb] >> 6, hs = pair_list[p0 + pb] & 63;
                 const int row = D.guard_path[(o * D.L + idx) * 2], col = D.guard_path[(o * D.L + idx) * 2 + 1];
                 unsigned *m = gmask + pb * (VC_ROWS / 2);
                 for (int ri = tid & 31; ri < NRAY; ri += 32) {
@@ -426,7 +453,7 @@ __global__ void __launch_bounds__(VC_BUILD_THREADS, 6) k_build_cache(Dev D) {
             __syncthreads();
             for (int i = tid; i < np * (VC_ROWS / 2); i += VC_BUILD_THREADS) {
                 const int pb = i / (VC_ROWS / 2), w = i - pb * (VC_ROWS / 2);
-                const int idx = (p0 + pb) / nh, hs = (p0 + pb) - idx * nh;
+                const int idx = pair_list[p0 + pb] >> 6, hs = pair_list[p0 + pb] & 63;
                 reinterpret_cast<uint32_t *>(D.vg_mask + ((o * D.L + idx) * HS + hs) * VC_ROWS)[w] = gmask[i];
             }
             __syncthreads();

@@ -65,6 +65,8 @@ struct Dev {
     double *vg_hval;      // [N][Kg][L+1] distinct headings a guard can carry
     uint8_t *vg_hslot;    // [N][Kg][L] slot of guard_head[k] (255: unchanged)
     int32_t *vg_nh;       // [N][Kg] number of heading slots (-1: not cacheable)
+    uint32_t *vg_reach;   // [N][Kg][L] bit min(slot, 31): the guard can stand on this waypoint carrying this heading slot --
+                          //   only those (waypoint, slot) cones are built
     uint8_t *env_cached;  // [N] every asset of the env is served by the cache
     int *n_uncached;      // [1] envs left to the ray-march kernel
     int skip_cached;      // launch flag: the ray-march kernel leaves cached envs to k_fast

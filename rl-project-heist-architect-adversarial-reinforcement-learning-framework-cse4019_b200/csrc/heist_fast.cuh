@@ -662,6 +662,7 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         for (int s = 0; s < nh; ++s)
             if (__double_as_longlong(D.vg_hval[go * (L + 1) + s]) == __double_as_longlong(h)) { hs = s; break; }
         if (hs < 0) { atomicOr(D.err, ERR_STATE); hs = 0; }
+        if (!((D.vg_reach[go * L + min(max(gk, 0), L - 1)] >> min(hs, 31)) & 1u)) atomicOr(D.err, ERR_STATE);   // a cone that was never built
         ghs = hs;
         gmask = D.vg_mask + go * L * (size_t)(L + 1) * VC_ROWS;
         gkn = gk + gstp; if (gkn >= glen) gkn -= glen;

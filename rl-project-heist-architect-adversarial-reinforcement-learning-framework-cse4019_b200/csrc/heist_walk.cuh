@@ -82,7 +82,8 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
             const unsigned m0 = __ballot_sync(FULL, lane < nh && __double_as_longlong(hv[lane]) == hb);
             const unsigned m1 = __ballot_sync(FULL, lane + 32 < nh && __double_as_longlong(hv[min(lane + 32, L)]) == hb);
             ghs[g] = m0 ? __ffs(m0) - 1 : (m1 ? 31 + __ffs(m1) : 0);
-            if (!(m0 | m1) && lane == 0) atomicOr(D.err, ERR_STATE);
+            if (lane == 0 && (!(m0 | m1) || !((D.vg_reach[o * L + min(max(gk[g], 0), L - 1)] >> min(ghs[g], 31)) & 1u)))
+                atomicOr(D.err, ERR_STATE);   // (a heading of no waypoint, or a (waypoint, slot) cone that was never built)
             gmask[g] = D.vg_mask + o * L * (size_t)(L + 1) * VC_ROWS;
             gw[g] = __shfl_sync(FULL, pw[g], gk[g]);
         }

@@ -991,6 +991,7 @@ def test_guard_heavy_rollout_on_the_pipelined_path(R, C, T):
     acts = synthetic.sample_actions(rng, T, N)
     out = env.step_many(acts, autoreset=True, want_vis=True)
     ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    env.check_errors()   # (every state the guards went through had its cone built: no ERR_STATE)
     assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"])
     assert np.array_equal(out["status"].cpu().numpy(), ref["status"])
     assert np.array_equal(out["reward"].cpu().numpy(), ref["reward"])
@@ -1060,6 +1061,55 @@ def test_errors_are_reported_not_swallowed():
         env.set_layout_explicit([([], [], [{"patrol_path": [(25, 3)]}])] * 8)
     with pytest.raises(KeyError):
         heist_b200.HeistEnvironment(EnvironmentConfig(grid_rows=10, grid_cols=10)).step(7)
+
+
+@pytest.mark.parametrize("speed", [1, 3, -1, 8, 0])
+def test_guard_cones_cover_every_reachable_state_and_only_those(speed):
+    """The guards' cones are tabulated per (waypoint, heading slot) for the pairs a patrol can reach (k_build_cache):
+    strides that skip waypoints, steps that are no move (heading kept), resets at every phase of the patrol -- single
+    ticks and rollouts equal the oracle with no state error; a (waypoint, heading) pair written by hand into the state
+    that no patrol reaches is reported, not served from an unbuilt table."""
+    cfg = EnvironmentConfig(max_steps=7)
+    N, T = 32, 70
+    env = BatchedHeistEnv(cfg, N, max_path=12)
+    rng = np.random.default_rng(99 + speed)
+    lays = []
+    for i in range(N):
+        r0, c0 = int(rng.integers(4, 15)), int(rng.integers(4, 15))
+        ring = [(r0 - 1, c0 - 1), (r0 - 1, c0), (r0 - 1, c0 + 1), (r0, c0 + 1), (r0 + 1, c0 + 1), (r0 + 1, c0), (r0 + 1, c0 - 1), (r0, c0 - 1)]
+        if i % 3 == 1:
+            ring[2] = ring[1]; ring[5] = ring[4]          # no-move steps
+        if i % 3 == 2:
+            ring = ring[:int(rng.integers(1, 8))] + [(r0 + 2, c0 - 2)]
+        lays.append(([(9, 9)], [], [{"patrol_path": ring, "speed": speed, "vision_range": 4, "fov_angle": 90.0}]))
+    env.set_layout_explicit(lays, budget=np.full(N, 100, np.int32))
+    assert env.cache_stats()[0] == N
+    oenvs = []
+    for w, c, g in lays:
+        e = ho.OracleEnv(20, 20, max_steps=7, budget=100)
+        e.set_layout(w, c, g)
+        oenvs.append(e)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, T, N)
+    ref = ho.rollout(oenvs, acts, autoreset=True, want_vis=True)
+    for t in range(8):   # single ticks (k_walk) ...
+        _, done, _ = env.step(acts[t])
+        env.reset(mask=done)
+        assert np.array_equal(u32(env.visibility_bits), ref["vis_bits"][t]), t
+    out = env.step_many(acts[8:], autoreset=True, want_vis=True)   # ... then the rollout kernels from that state
+    env.check_errors()
+    assert np.array_equal(u32(out["vis_bits"]), ref["vis_bits"][8:])
+    assert np.array_equal(out["status"].cpu().numpy(), ref["status"][8:])
+    if speed == 1:   # waypoint 4 of a ring is always entered heading south (270); heading 90 (a slot of the path) never gets there
+        env.set_layout_explicit(lays[:1] * N, budget=np.full(N, 100, np.int32))
+        env.reset()
+        env.guard_idx[:, 0] = 4
+        env.guard_heading[:, 0] = 90.0
+        env.step(acts[0])
+        with pytest.raises(RuntimeError, match="guard state"):
+            env.check_errors()
+    env.close()
 
 
 def test_single_tick_api_with_masked_resets_matches_oracle():
