@@ -1,7 +1,9 @@
 """Per-source-line instruction / stall-sample shares of one kernel in an .ncu-rep (read here, no GPU).
 
-usage: python profiles/hot_lines.py report.ncu-rep libheist_b200.so kernel-substring [top [stall]]
-Joins the ncu SASS source page with nvdisasm line info of the same build (-lineinfo)."""
+usage: python profiles/hot_lines.py report.ncu-rep libheist_b200.so kernel-substring [top [stall|inst [mangled]]]
+Joins the ncu SASS source page with nvdisasm line info of the same build (-lineinfo).  `mangled`: substring of the
+.text section of the instantiation that was captured (e.g. k_walkILi1ELi1E) -- templates have several, and their
+offsets overlap."""
 import collections, csv, glob, io, os, re, subprocess, sys, tempfile
 
 
@@ -9,6 +11,7 @@ def main():
     rep, so, kern = sys.argv[1:4]
     top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     by_stall = len(sys.argv) > 5 and sys.argv[5] == "stall"   # sort by stall samples instead of instructions
+    mangled = sys.argv[6] if len(sys.argv) > 6 else kern
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "-k", "regex:" + kern, "-c", "1"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr, data = rows[1], rows[2:]
@@ -25,7 +28,7 @@ def main():
     a2l, cur, inside = {}, None, False
     for l in dis:
         if l.startswith("//-") and ".text." in l:
-            inside = kern in l
+            inside = mangled in l
             continue
         if not inside:
             continue

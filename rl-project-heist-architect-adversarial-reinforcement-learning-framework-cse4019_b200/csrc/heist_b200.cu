@@ -499,11 +499,14 @@ static void launch_walk(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
     const Dev &d = h->d;
     const unsigned g2 = (unsigned)((h->N + WALK_WARPS - 1) / WALK_WARPS);
     const size_t sm = WALK_WARPS * walk_warp_bytes(d.RW, d.Kc);
-#define GO(RPL, W) k_walk<RPL, W><<<g2, WALK_WARPS * 32, sm, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
-                                                                 c.done, c.status, c.cam, c.write_traj, c.do_reset, c.mask, c.store_heading, c.state)
+    // c.cam == nullptr: the fused single tick (cones + step + auto-reset + dense state, T <= 1)
+#define GO1(RPL, W, F) k_walk<RPL, W, F><<<g2, WALK_WARPS * 32, sm, s>>>(d, c.actions, c.do_reset ? 0 : c.Tc, c.autoreset, c.reward, c.reward64, \
+                                                                       c.done, c.status, c.cam, c.write_traj, c.do_reset, c.mask, c.store_heading, c.state)
+#define GO(RPL, W) do { if (c.cam) GO1(RPL, W, false); else GO1(RPL, W, true); } while (0)
     if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
     else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
+#undef GO1
     h->launches += 1;
 }
 

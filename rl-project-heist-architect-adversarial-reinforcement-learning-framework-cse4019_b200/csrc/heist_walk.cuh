@@ -25,13 +25,13 @@ __host__ __device__ inline size_t walk_warp_bytes(int RW, int Kc) {   // fused m
     return (((size_t)Kc * sizeof(FastCam) + (size_t)RW * 4) + 15) & ~(size_t)15;
 }
 
-template <int RPL, int W>
+template <int RPL, int W, bool FUSED>
 __global__ void __launch_bounds__(WALK_WARPS * 32, 7)
 k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__restrict__ reward,
        double *__restrict__ reward64, uint8_t *__restrict__ done, uint8_t *__restrict__ status_out,
        uint32_t *buf, int write_traj, int do_reset, const uint8_t *__restrict__ mask, int store_heading,
        float *__restrict__ state_out) {
-    // buf == nullptr: FUSED single tick (T <= 1) -- the camera cones of the tick are computed right here from the
+    // FUSED (buf == nullptr): single tick (T <= 1) -- the camera cones of the tick are computed right here from the
     // cache tables (one launch instead of k_cam_vis + k_walk), the new headings are stored, and, if state_out is
     // given, the dense (3, R, C) state the policy reads next is written from the registers that hold the finished map.
     extern __shared__ __align__(16) unsigned char smem[];
@@ -63,30 +63,12 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
     int gk[G], ghs[G], glen[G], gstp[G], grng[G];   // waypoint, heading slot, path length, stride, range
     unsigned pw[G], gw[G];                          // lane k: patrol word of waypoint k (row | col << 8 | slot << 16,
     const uint16_t *gmask[G];                       //   slot taken when LEAVING it, 255 = unchanged); gw: word at gk
+    if (lane < n_guards) {   // the guards' records are read after the camera scan (their registers would only be
+        const size_t o = (size_t)env * Kg + lane;   // spilled across it): requested now, so the reads below hit L1
+        const void *pf[8] = {D.guard_i + o * 4, D.guard_path + o * L * 2, D.vg_hslot + o * L, D.guard_heading + o,
+                             D.guard_idx + o, D.vg_nh + o, D.vg_hval + o * (L + 1), D.vg_reach + o * L};
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-        gk[g] = ghs[g] = 0; glen[g] = 1; gstp[g] = 0; grng[g] = 0; pw[g] = gw[g] = 0; gmask[g] = D.vg_mask;
-        if (g < n_guards) {
-            const size_t o = (size_t)env * Kg + g;
-            const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);   // len, speed, range, num_rays
-            glen[g] = gi.x; gstp[g] = gi.x >= 2 ? py_imod(gi.y, gi.x) : 0; grng[g] = gi.z;
-            gk[g] = D.guard_idx[o];
-            if (lane < gi.x)
-                pw[g] = (unsigned)D.guard_path[(o * L + lane) * 2] | ((unsigned)D.guard_path[(o * L + lane) * 2 + 1] << 8) |
-                        ((unsigned)D.vg_hslot[o * L + lane] << 16);
-            // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
-            // state view; it is reported (ERR_STATE) and treated as the default heading.
-            const long long hb = __double_as_longlong(D.guard_heading[o]);
-            const int nh = D.vg_nh[o];
-            const double *hv = D.vg_hval + o * (L + 1);   // at most L + 1 <= 33 distinct headings
-            const unsigned m0 = __ballot_sync(FULL, lane < nh && __double_as_longlong(hv[lane]) == hb);
-            const unsigned m1 = __ballot_sync(FULL, lane + 32 < nh && __double_as_longlong(hv[min(lane + 32, L)]) == hb);
-            ghs[g] = m0 ? __ffs(m0) - 1 : (m1 ? 31 + __ffs(m1) : 0);
-            if (lane == 0 && (!(m0 | m1) || !((D.vg_reach[o * L + min(max(gk[g], 0), L - 1)] >> min(ghs[g], 31)) & 1u)))
-                atomicOr(D.err, ERR_STATE);   // (a heading of no waypoint, or a (waypoint, slot) cone that was never built)
-            gmask[g] = D.vg_mask + o * L * (size_t)(L + 1) * VC_ROWS;
-            gw[g] = __shfl_sync(FULL, pw[g], gk[g]);
-        }
+        for (int i = 0; i < 8; ++i) asm volatile("prefetch.global.L1 [%0];" ::"l"(pf[i]));
     }
 
     // wall bit at (nr, nc), all arguments warp-uniform; outside the grid blocks (:242-245)
@@ -124,7 +106,7 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
     for (int a = 0; a < RPL; ++a)
 #pragma unroll
         for (int w = 0; w < W; ++w) camrows[a][w] = 0u;
-    if (!buf) {
+    if (FUSED) {
         // Cameras of a live env rotate once before the cones are cast (:251-252); a reset, or the tick a done env
         // spends on the "already done" early-out, keeps the headings (:205-208, :232-233).
         const bool advance = !do_reset && T > 0 && !(E.flags & F_DONE);
@@ -175,13 +157,38 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
         }
         store_heading = 0;   // stored above
     }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        gk[g] = ghs[g] = 0; glen[g] = 1; gstp[g] = 0; grng[g] = 0; pw[g] = gw[g] = 0; gmask[g] = D.vg_mask;
+        if (g < n_guards) {
+            const size_t o = (size_t)env * Kg + g;
+            const int4 gi = *reinterpret_cast<const int4 *>(D.guard_i + o * 4);   // len, speed, range, num_rays
+            glen[g] = gi.x; gstp[g] = gi.x >= 2 ? py_imod(gi.y, gi.x) : 0; grng[g] = gi.z;
+            gk[g] = D.guard_idx[o];
+            if (lane < gi.x)
+                pw[g] = (unsigned)D.guard_path[(o * L + lane) * 2] | ((unsigned)D.guard_path[(o * L + lane) * 2 + 1] << 8) |
+                        ((unsigned)D.vg_hslot[o * L + lane] << 16);
+            // heading -> slot.  A heading that is none of the path's can only have been written by hand into the
+            // state view; it is reported (ERR_STATE) and treated as the default heading.
+            const long long hb = __double_as_longlong(D.guard_heading[o]);
+            const int nh = D.vg_nh[o];
+            const double *hv = D.vg_hval + o * (L + 1);   // at most L + 1 <= 33 distinct headings
+            const unsigned m0 = __ballot_sync(FULL, lane < nh && __double_as_longlong(hv[lane]) == hb);
+            const unsigned m1 = __ballot_sync(FULL, lane + 32 < nh && __double_as_longlong(hv[min(lane + 32, L)]) == hb);
+            ghs[g] = m0 ? __ffs(m0) - 1 : (m1 ? 31 + __ffs(m1) : 0);
+            if (lane == 0 && (!(m0 | m1) || !((D.vg_reach[o * L + min(max(gk[g], 0), L - 1)] >> min(ghs[g], 31)) & 1u)))
+                atomicOr(D.err, ERR_STATE);   // (a heading of no waypoint, or a (waypoint, slot) cone that was never built)
+            gmask[g] = D.vg_mask + o * L * (size_t)(L + 1) * VC_ROWS;
+            gw[g] = __shfl_sync(FULL, pw[g], gk[g]);
+        }
+    }
     auto load_rows = [&](uint32_t (&v)[RPL][W], int t) {
 #pragma unroll
         for (int a = 0; a < RPL; ++a)
 #pragma unroll
             for (int w = 0; w < W; ++w) {
                 const int r = lane + 32 * a;
-                v[a][w] = !buf ? camrows[a][w] : (r < R ? buf[((size_t)t * N + env) * RW + r * W + w] : 0u);
+                v[a][w] = FUSED ? camrows[a][w] : (r < R ? buf[((size_t)t * N + env) * RW + r * W + w] : 0u);
             }
     };
     auto store_rows = [&](const uint32_t (&v)[RPL][W], int t) {
@@ -202,6 +209,92 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
         or_guards(cur);
         T = 0;
     }
+    // One env step (environment.py:216-299) on the camera cones v of the tick; returns whether the map was rebuilt.
+    auto tick_step = [&](uint32_t (&v)[RPL][W], int act, double &rw) -> bool {
+        rw = 0.0;
+        status = HEIST_ALREADY_DONE;
+        if (E.flags & F_DONE) return false;   // a done env is not mutated (:232-233)
+        // move (:239-246): blocked by the grid edge or a WALL tile
+        const int nr = E.r + (act == 2) - (act == 1), nc = E.c + (act == 4) - (act == 3);
+        if (!blocked(nr, nc)) { E.r = nr; E.c = nc; }
+        ++n_adv;   // cameras rotate (:251-252): their cones for this tick are v
+#pragma unroll
+        for (int g = 0; g < G; ++g) {   // Guard.update (security.py:145-159)
+            if (g < n_guards && glen[g] >= 2) {
+                const int hsl = (gw[g] >> 16) & 255;
+                if (hsl != 255) ghs[g] = hsl;   // 255: the move is (0, 0), heading unchanged
+                gk[g] += gstp[g]; if (gk[g] >= glen[g]) gk[g] -= glen[g];
+                gw[g] = __shfl_sync(FULL, pw[g], gk[g]);
+            }
+        }
+        or_guards(v);   // visibility rebuild (:257-258): camera cones OR guard cones / own tiles
+        uint32_t mine = v[0][0];
+        if (W == 2 && (E.c >> 5)) mine = v[0][W - 1];
+        if (RPL == 2 && E.r >= 32) { mine = v[RPL - 1][0]; if (W == 2 && (E.c >> 5)) mine = v[RPL - 1][W - 1]; }
+        const bool detected = (__shfl_sync(FULL, mine, E.r & 31) >> (E.c & 31)) & 1u;
+        // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297)
+        rw = D.reward_step;
+        status = HEIST_RUNNING;
+        const int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
+        rw = __dadd_rn(rw, __dmul_rn((double)(E.prev - curr), 0.1));
+        E.prev = curr;
+        if (curr <= 3 && E.init > 3) rw = __dadd_rn(rw, __dmul_rn(0.05, (double)(3 - curr)));
+        if (detected) {
+            E.flags |= F_DETECTED | F_DONE;
+            rw = __dadd_rn(rw, D.reward_detection);
+            status = HEIST_DETECTED;
+        }
+        if (E.r == D.vault_r && E.c == D.vault_c) {
+            E.flags |= F_VAULT | F_DONE;
+            rw = __dadd_rn(rw, D.reward_vault);
+            status = HEIST_VAULT_REACHED;
+        }
+        E.tick += 1;
+        if (E.tick >= D.max_steps) {
+            E.flags |= F_DONE;
+            status = HEIST_TIMEOUT;
+            double cf = __dsub_rn(1.0, __ddiv_rn((double)curr, (double)max(E.init, 1)));
+            if (!(cf > 0.0)) cf = 0.0;
+            rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
+        }
+        if (status == HEIST_VAULT_REACHED) E.n_vault++;        // training.py:535-540
+        else if (status == HEIST_DETECTED) E.n_detect++;
+        else if (status == HEIST_TIMEOUT) E.n_timeout++;
+        return true;
+    };
+    // the trainer's `if done: reset()`: same cameras (the cones of tick t), guards at waypoint 0
+    auto tick_autoreset = [&](uint32_t (&v)[RPL][W], int t) {
+        reset_state();
+#pragma unroll
+        for (int a = 0; a < RPL; ++a)
+#pragma unroll
+            for (int w = 0; w < W; ++w) v[a][w] = 0u;
+        load_rows(v, t);
+        or_guards(v);
+    };
+    if (FUSED) {   // exactly one tick (or none: a reset), nothing of the multi-tick machinery below
+        if (T > 0) {
+            uint32_t v[RPL][W];
+            load_rows(v, 0);
+            const int act = actions[env];   // (one address for the warp: a broadcast)
+            double rw;
+            bool rebuilt = tick_step(v, act, rw);
+            const int dn = (E.flags & F_DONE) ? 1 : 0, st = status;
+            if (autoreset && dn) { tick_autoreset(v, 0); rebuilt = true; }
+            if (rebuilt) {
+#pragma unroll
+                for (int a = 0; a < RPL; ++a)
+#pragma unroll
+                    for (int w = 0; w < W; ++w) cur[a][w] = v[a][w];
+            }
+            if (lane == 0) {
+                if (reward) reward[env] = (float)rw;
+                if (reward64) reward64[env] = rw;
+                if (done) done[env] = (uint8_t)dn;
+                if (status_out) status_out[env] = (uint8_t)st;
+            }
+        }
+    } else {
     // lane l holds the action of tick tb + l; the next 32 are requested one group ahead
     int a_now = 0, a_next = 0;
     if (lane < T) a_now = actions[(size_t)lane * N + env];
@@ -222,69 +315,10 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
                 for (int w = 0; w < W; ++w) v[a][w] = pre[j][a][w];
             if (t + WALK_PF < T) load_rows(pre[j], t + WALK_PF);
             const int act = __shfl_sync(FULL, a_now, t & 31);
-            double rw = 0.0;
-            bool rebuilt = false;
-            status = HEIST_ALREADY_DONE;
-            if (!(E.flags & F_DONE)) {   // a done env is not mutated (:232-233)
-                // move (:239-246): blocked by the grid edge or a WALL tile
-                const int nr = E.r + (act == 2) - (act == 1), nc = E.c + (act == 4) - (act == 3);
-                if (!blocked(nr, nc)) { E.r = nr; E.c = nc; }
-                ++n_adv;   // cameras rotate (:251-252): their cones for this tick are buf[t]
-#pragma unroll
-                for (int g = 0; g < G; ++g) {   // Guard.update (security.py:145-159)
-                    if (g < n_guards && glen[g] >= 2) {
-                        const int hsl = (gw[g] >> 16) & 255;
-                        if (hsl != 255) ghs[g] = hsl;   // 255: the move is (0, 0), heading unchanged
-                        gk[g] += gstp[g]; if (gk[g] >= glen[g]) gk[g] -= glen[g];
-                        gw[g] = __shfl_sync(FULL, pw[g], gk[g]);
-                    }
-                }
-                or_guards(v);   // visibility rebuild (:257-258): camera cones OR guard cones / own tiles
-                uint32_t mine = v[0][0];
-                if (W == 2 && (E.c >> 5)) mine = v[0][W - 1];
-                if (RPL == 2 && E.r >= 32) { mine = v[RPL - 1][0]; if (W == 2 && (E.c >> 5)) mine = v[RPL - 1][W - 1]; }
-                const bool detected = (__shfl_sync(FULL, mine, E.r & 31) >> (E.c & 31)) & 1u;
-                // shaping (:261-269), detection (:273-281), vault (:284-288), timeout (:291-297)
-                rw = D.reward_step;
-                status = HEIST_RUNNING;
-                const int curr = abs(E.r - D.vault_r) + abs(E.c - D.vault_c);
-                rw = __dadd_rn(rw, __dmul_rn((double)(E.prev - curr), 0.1));
-                E.prev = curr;
-                if (curr <= 3 && E.init > 3) rw = __dadd_rn(rw, __dmul_rn(0.05, (double)(3 - curr)));
-                if (detected) {
-                    E.flags |= F_DETECTED | F_DONE;
-                    rw = __dadd_rn(rw, D.reward_detection);
-                    status = HEIST_DETECTED;
-                }
-                if (E.r == D.vault_r && E.c == D.vault_c) {
-                    E.flags |= F_VAULT | F_DONE;
-                    rw = __dadd_rn(rw, D.reward_vault);
-                    status = HEIST_VAULT_REACHED;
-                }
-                E.tick += 1;
-                if (E.tick >= D.max_steps) {
-                    E.flags |= F_DONE;
-                    status = HEIST_TIMEOUT;
-                    double cf = __dsub_rn(1.0, __ddiv_rn((double)curr, (double)max(E.init, 1)));
-                    if (!(cf > 0.0)) cf = 0.0;
-                    rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
-                }
-                if (status == HEIST_VAULT_REACHED) E.n_vault++;        // training.py:535-540
-                else if (status == HEIST_DETECTED) E.n_detect++;
-                else if (status == HEIST_TIMEOUT) E.n_timeout++;
-                rebuilt = true;
-            }
+            double rw;
+            bool rebuilt = tick_step(v, act, rw);
             if (lane == (t & 31)) { o_rw = (float)rw; o_rw64 = rw; o_dn = (E.flags & F_DONE) ? 1 : 0; o_st = status; }
-            if (autoreset && (E.flags & F_DONE)) {   // the trainer's `if done: reset()`: same cameras, guards at waypoint 0
-                reset_state();
-#pragma unroll
-                for (int a = 0; a < RPL; ++a)
-#pragma unroll
-                    for (int w = 0; w < W; ++w) v[a][w] = 0u;
-                load_rows(v, t);
-                or_guards(v);
-                rebuilt = true;
-            }
+            if (autoreset && (E.flags & F_DONE)) { tick_autoreset(v, t); rebuilt = true; }
             if (rebuilt) {
 #pragma unroll
                 for (int a = 0; a < RPL; ++a)
@@ -306,6 +340,7 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
             }
         }
     }
+    }
 
     // ---- store ----
 #pragma unroll
@@ -319,40 +354,49 @@ k_walk(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *_
         // HeistEnvironment.get_state_tensor (environment.py:347-374) from the finished map in registers: channel 0 the
         // tile codes / 5, channel 1 the visibility map, channel 2 Solver +1 / vault -1 (vault wins) + distance
         // gradient; one float4 (4 cells, C % 4 == 0) per store, same arithmetic as k_observe_vec4.
-        const int quads = D.RC >> 2, vcell = D.vault_r * C + D.vault_c, scell = E.r * C + E.c;
+        const int quads = D.RC >> 2, total = 3 * quads, vcell = D.vault_r * C + D.vault_c, scell = E.r * C + E.c;
         float4 *dst = reinterpret_cast<float4 *>(state_out) + (size_t)env * 3 * quads;
-        for (int q0 = 0; q0 < 3 * quads; q0 += 32) {   // (every lane takes every trip: the shuffles below need them all)
-            const int q = q0 + lane;
-            const bool on = q < 3 * quads;
-            const int ch = (q >= quads) + (q >= 2 * quads);
-            const int cell = on ? (q - ch * quads) << 2 : 0;
-            const int r = cell / C, c = cell - r * C;
+        // lane's quad q = q0 + lane walks the three channels 32 quads (128 cells) per trip: (channel, cell, row, col)
+        // advance incrementally -- one integer division per lane up front instead of one per store
+        int q = lane;
+        int ch = (q >= quads) + (q >= 2 * quads);
+        int cell = (q - ch * quads) << 2;
+        int r = cell / C, c = cell - r * C;
+        const int dr = 128 / C, dc = 128 - dr * C;
+        for (int q0 = 0; q0 < total; q0 += 32) {   // (every lane takes every trip: the shuffles below need them all)
+            const bool on = q < total;
             uint32_t word = 0;
+            if (q0 + 31 >= quads && q0 < 2 * quads) {   // warp-uniform: some lane is in channel 1 (the visibility map)
 #pragma unroll
-            for (int a = 0; a < RPL; ++a)
+                for (int a = 0; a < RPL; ++a)
 #pragma unroll
-                for (int w2 = 0; w2 < W; ++w2) {
-                    const uint32_t x = __shfl_sync(FULL, cur[a][w2], r & 31);
-                    if ((r >> 5) == a && (c >> 5) == w2) word = x;
-                }
+                    for (int w2 = 0; w2 < W; ++w2) {
+                        const uint32_t x = __shfl_sync(FULL, cur[a][w2], r & 31);
+                        if ((r >> 5) == a && (c >> 5) == w2) word = x;
+                    }
+            }
+            const int my_q = q, my_ch = ch, my_cell = cell, my_c = c;
+            q += 32; cell += 128; c += dc; r += dr;
+            if (c >= C) { c -= C; ++r; }
+            while (cell >= D.RC) { cell -= D.RC; r -= R; ++ch; }
             if (!on) continue;
             float4 v;
-            if (ch == 0) {
-                const uchar4 t4 = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + cell);
+            if (my_ch == 0) {
+                const uchar4 t4 = *reinterpret_cast<const uchar4 *>(D.tile + (size_t)env * D.RC + my_cell);
                 v.x = __fmul_rn((float)t4.x, 0.2f); v.y = __fmul_rn((float)t4.y, 0.2f);
                 v.z = __fmul_rn((float)t4.z, 0.2f); v.w = __fmul_rn((float)t4.w, 0.2f);
-            } else if (ch == 1) {
-                const uint32_t bits = word >> (c & 31);
+            } else if (my_ch == 1) {
+                const uint32_t bits = word >> (my_c & 31);
                 v.x = (float)(bits & 1u); v.y = (float)((bits >> 1) & 1u); v.z = (float)((bits >> 2) & 1u); v.w = (float)((bits >> 3) & 1u);
             } else {
-                const float4 g = *reinterpret_cast<const float4 *>(D.pos_tab + cell);
-                const float b0 = (cell + 0 == vcell) ? -1.0f : ((cell + 0 == scell) ? 1.0f : 0.0f);
-                const float b1 = (cell + 1 == vcell) ? -1.0f : ((cell + 1 == scell) ? 1.0f : 0.0f);
-                const float b2 = (cell + 2 == vcell) ? -1.0f : ((cell + 2 == scell) ? 1.0f : 0.0f);
-                const float b3 = (cell + 3 == vcell) ? -1.0f : ((cell + 3 == scell) ? 1.0f : 0.0f);
+                const float4 g = *reinterpret_cast<const float4 *>(D.pos_tab + my_cell);
+                const float b0 = (my_cell + 0 == vcell) ? -1.0f : ((my_cell + 0 == scell) ? 1.0f : 0.0f);
+                const float b1 = (my_cell + 1 == vcell) ? -1.0f : ((my_cell + 1 == scell) ? 1.0f : 0.0f);
+                const float b2 = (my_cell + 2 == vcell) ? -1.0f : ((my_cell + 2 == scell) ? 1.0f : 0.0f);
+                const float b3 = (my_cell + 3 == vcell) ? -1.0f : ((my_cell + 3 == scell) ? 1.0f : 0.0f);
                 v.x = __fadd_rn(b0, g.x); v.y = __fadd_rn(b1, g.y); v.z = __fadd_rn(b2, g.z); v.w = __fadd_rn(b3, g.w);
             }
-            __stcs(dst + q, v);   // write-once stream
+            __stcs(dst + my_q, v);   // write-once stream
         }
     }
     if (lane == 0) {
