@@ -466,7 +466,7 @@ static cudaError_t grow(T **buf, size_t *cap, size_t need) {
 struct FastChunk {
     const int8_t *actions; float *reward; double *reward64; uint8_t *done, *status;
     uint32_t *cam; const double *heads; uint16_t *grec; uint8_t *fin; int32_t *last_t;
-    int Tc, autoreset, do_reset, write_traj, store_heading; const uint8_t *mask;
+    int Tc, autoreset, do_reset, write_traj, store_heading, rev; const uint8_t *mask;
     float *state;   // fused single tick only: dense (3, R, C) state written by k_walk
 };
 
@@ -481,7 +481,7 @@ static void launch_cam_vis(HeistHandle *h, const FastChunk &c, cudaStream_t s) {
         if (wpc_env && atoi(wpc_env) >= 1 && atoi(wpc_env) <= CVS_MAX_WARPS) wpc = std::min(nblk, atoi(wpc_env));
         const dim3 g((unsigned)h->N, (unsigned)((nblk + wpc - 1) / wpc));
         const size_t sm = camvis_staged_bytes(d.RW, d.Kc, wpc);
-#define GO(RPL, W) k_cam_vis_staged<RPL, W><<<g, wpc * 32, sm, s>>>(d, c.Tc, nblk, c.heads, c.cam)
+#define GO(RPL, W) k_cam_vis_staged<RPL, W><<<g, wpc * 32, sm, s>>>(d, c.Tc, nblk, c.heads, c.cam, c.rev)
         if (d.R > 32) { if (d.C > 32) GO(2, 2); else GO(2, 1); }
         else { if (d.C > 32) GO(1, 2); else GO(1, 1); }
 #undef GO
@@ -613,7 +613,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
     const int total = do_reset ? 1 : T;
     const unsigned gh = (unsigned)((N * d.Kc + 127) / 128);
     FastChunk c;
-    c.autoreset = autoreset; c.do_reset = do_reset; c.write_traj = vis_traj ? 1 : 0; c.mask = mask; c.state = nullptr;
+    c.autoreset = autoreset; c.do_reset = do_reset; c.write_traj = vis_traj ? 1 : 0; c.mask = mask; c.state = nullptr; c.rev = 0;
 
     // Pipelined: with auto-reset no env is ever left done at a chunk boundary, so the camera headings of the whole
     // launch are known up front (k_heads once) and k_cam_vis of chunk c + 1 does not wait for k_walk of chunk c.
@@ -660,6 +660,7 @@ static int launch_fast(HeistHandle *h, const int8_t *actions, int T, int autores
             cudaStream_t sc = (i & 1) ? h->s_cam2 : s;
             int t0;
             c.Tc = chunk_ticks(i, t0);
+            c.rev = i & 1;   // snake over the envs: see k_cam_vis_staged
             const size_t off = (size_t)t0 * N;
             if (i > 0) CUDA_TRY(cudaStreamWaitEvent(sc, h->ev_heads[i], 0));
             c.actions = actions + off; c.reward = reward ? reward + off : nullptr; c.reward64 = reward64 ? reward64 + off : nullptr;

@@ -357,11 +357,13 @@ __device__ __noinline__ void cam_exact_scan_staged(VcGeo D, const uint32_t *__re
 
 template <int RPL, int W>
 __global__ void __launch_bounds__(CVS_MAX_WARPS * 32, 6)
-k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out) {
+k_cam_vis_staged(Dev D, int T, int nblk, const double *__restrict__ heads, uint32_t *__restrict__ out, int rev) {
     extern __shared__ __align__(16) unsigned char smem[];
     constexpr unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, nthr = blockDim.x;
-    const int env = blockIdx.x, b = blockIdx.y * (nthr >> 5) + warp;
+    // rev: the chunks of a launch walk the envs in alternating directions -- what the previous chunk read last (the
+    // tables of the envs it ended on) is what the L2 still holds when the next one starts
+    const int env = rev ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x, b = blockIdx.y * (nthr >> 5) + warp;
     if (!D.env_cached[env]) return;   // CTA-uniform
     const int Kc = D.Kc, RW = D.RW;
     unsigned off = 0;   // (32-bit offsets: the carving is a handful of integer adds)
