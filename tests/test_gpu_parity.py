@@ -1112,6 +1112,46 @@ def test_guard_cones_cover_every_reachable_state_and_only_those(speed):
     env.close()
 
 
+@pytest.mark.parametrize("R,C", [(5, 4), (8, 8), (7, 12), (20, 20), (33, 36), (40, 64), (64, 64), (64, 4), (6, 16)])
+def test_fused_tick_dense_state_on_odd_grid_shapes(R, C):
+    """heist_step_observe writes the (3, R, C) state from the fused tick kernel with incrementally advanced
+    (channel, cell, row, column) indices: grids whose channels are shorter than one warp trip (5x4: 15 float4 in all),
+    end inside a trip (7x12, 33x36), or take two lanes / two words per row (40x64, 64x64) -- every tick's state equals
+    the oracle's get_state_tensor (environment.py:347-374), with auto-resets on the way."""
+    cfg = EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=9, start_pos=(1, 1), vault_pos=(R - 2, C - 2))
+    N, T = 40, 24
+    env = BatchedHeistEnv(cfg, N, max_path=8)
+    rng = np.random.default_rng(R * 100 + C)
+    lays = []
+    for _ in range(N):
+        walls = [(int(rng.integers(0, R)), int(rng.integers(0, C))) for _ in range(int(rng.integers(0, 6)))]
+        cams = [{"row": int(rng.integers(0, R)), "col": int(rng.integers(0, C)), "fov_angle": float(rng.uniform(30, 120)),
+                 "heading": float(rng.uniform(0, 360)), "rotation_speed": float(rng.uniform(5, 35)), "vision_range": int(rng.integers(1, 7))}
+                for _ in range(int(rng.integers(0, 3)))]
+        path = [(int(rng.integers(0, R)), int(rng.integers(0, C))) for _ in range(int(rng.integers(1, 6)))]
+        guards = [{"patrol_path": path, "speed": 1, "vision_range": 3, "fov_angle": 90.0}] if rng.random() < 0.6 else []
+        lays.append((walls, cams, guards))
+    env.set_layout_explicit(lays, budget=np.full(N, 1000, np.int32))
+    env.check_errors()
+    assert env.cache_stats()[0] == N
+    oenvs = []
+    for w, c, g in lays:
+        e = ho.OracleEnv(R, C, max_steps=9, budget=1000, start=(1, 1), vault=(R - 2, C - 2))
+        e.set_layout(w, c, g)
+        oenvs.append(e)
+    env.reset()
+    ho.reset_all(oenvs)
+    acts = synthetic.sample_actions(rng, T, N)
+    state = torch.empty(N, 3, R, C, device="cuda")
+    for t in range(T):
+        rew, done, status, _ = env.step_observe(acts[t], autoreset=True, state_out=state)
+        ref = ho.rollout(oenvs, acts[t:t + 1], autoreset=True, want_vis=False)
+        assert np.array_equal(status.cpu().numpy(), ref["status"][0]), t
+        assert np.array_equal(state.cpu().numpy(), np.stack([e.state_tensor() for e in oenvs])), t
+    env.check_errors()
+    env.close()
+
+
 def test_single_tick_api_with_masked_resets_matches_oracle():
     """heist_step + heist_reset(mask) at batch scale, the pattern of a policy-in-the-loop driver."""
     cfg = EnvironmentConfig(max_steps=25)
