@@ -685,6 +685,9 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     };
 
     int status = HEIST_RUNNING;
+    unsigned rec_last = 0;   // record of the launch's last tick (-> status)
+    bool stepped = false;
+    int outcomes = 0;        // pass B: episodes of env (lane & 7) ended by vault | detection << 10 | timeout << 20
     int n_adv = 0;           // camera updates executed by this launch
     int last = -1;           // last tick of this launch whose visibility map was rebuilt
     if (do_reset) {
@@ -704,22 +707,26 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     const bool moving = has_g && glen >= 2;
     for (int ts0 = 0; ts0 < T; ts0 += TS) {
     const int n_st = min(TS, T - ts0);
+    stepped = true;
     {   // stage the camera rows and the actions of ticks [ts0, ts0 + n_st) of this warp's (contiguous) envs
         const int words = n_here * RW;
         __syncwarp();
         if (vec_ok) {
-            // one flat list of 16-byte items over (tick, quad of words): a lane walks it in steps of 32 with pointer
-            // increments -- no division and no 64-bit multiply per item
+            // 16-byte items, tick by tick: a lane keeps its column(s) of the tick's q4 items and steps both pointers by
+            // one tick -- two adds per copy, no division, no multiply
             const int q4 = words >> 2, dstep = (SEQ_EPW * RW) >> 2;   // uint4 per tick: real / slot in shared memory
             const size_t sstep = ((size_t)N * RW) >> 2;               // ... and per tick of cam_vis
-            int tt = lane / q4, i = lane - tt * q4;
-            const int dt = 32 / q4, di = 32 - dt * q4;
-            const uint4 *src = reinterpret_cast<const uint4 *>(cam_vis + ((size_t)ts0 * N + env0) * RW) + (size_t)tt * sstep;
-            uint4 *dst = reinterpret_cast<uint4 *>(cam_s) + tt * dstep;
-            while (tt < n_st) {
-                cp_async16(dst + i, src + i);
-                i += di; tt += dt; src += (size_t)dt * sstep; dst += dt * dstep;
-                if (i >= q4) { i -= q4; ++tt; src += sstep; dst += dstep; }
+            const uint4 *src = reinterpret_cast<const uint4 *>(cam_vis + ((size_t)ts0 * N + env0) * RW) + lane;
+            uint4 *dst = reinterpret_cast<uint4 *>(cam_s) + lane;
+            if (q4 <= 64) {   // (one-word grids up to 32 rows: at most two items per lane and tick)
+                const bool one = lane < q4, two = lane + 32 < q4;
+                for (int tt = 0; tt < n_st; ++tt, src += sstep, dst += dstep) {
+                    if (one) cp_async16(dst, src);
+                    if (two) cp_async16(dst + 32, src + 32);
+                }
+            } else {
+                for (int tt = 0; tt < n_st; ++tt, src += sstep, dst += dstep)
+                    for (int i = lane; i < q4; i += 32) cp_async16(dst + i - lane, src + i - lane);
             }
         } else {
             for (int tt = 0; tt < n_st; ++tt) {
@@ -785,10 +792,7 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
         rec |= (detected ? SEQ_DET : 0u) | (at_vault ? SEQ_VAULT : 0u) | (tout ? SEQ_TOUT : 0u);
         E.prev = live ? abs(E.r - D.vault_r) + abs(E.c - D.vault_c) : E.prev;
         E.flags |= (detected ? (F_DETECTED | F_DONE) : 0) | (at_vault ? (F_VAULT | F_DONE) : 0) | (tout ? F_DONE : 0);
-        status = !live ? HEIST_ALREADY_DONE : (tout ? HEIST_TIMEOUT : (at_vault ? HEIST_VAULT_REACHED : (detected ? HEIST_DETECTED : HEIST_RUNNING)));
-        E.n_vault += status == HEIST_VAULT_REACHED;        // training.py:535-540
-        E.n_detect += status == HEIST_DETECTED;
-        E.n_timeout += status == HEIST_TIMEOUT;
+        rec_last = rec;   // (the launch's final status and the outcome counters are derived off the chain: below / pass B)
         // the trainer's `if done: reset()` (environment.py:183-214): headings persist, guards back to waypoint 0
         const bool rs = valid && autoreset && (E.flags & F_DONE);
         E.r = rs ? D.start_r : E.r; E.c = rs ? D.start_c : E.c;
@@ -829,6 +833,7 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
                 rw = __dadd_rn(rw, __dmul_rn(cf, 2.0));
             }
             dn = (rec & (SEQ_DET | SEQ_VAULT | SEQ_TOUT)) ? 1 : 0;
+            outcomes += (st == HEIST_VAULT_REACHED ? 1 : 0) | (st == HEIST_DETECTED ? 1 << 10 : 0) | (st == HEIST_TIMEOUT ? 1 << 20 : 0);   // training.py:535-540
         }
         if (reward) reward[o] = (float)rw;
         if (reward64) reward64[o] = rw;
@@ -838,6 +843,15 @@ k_seq(Dev D, const int8_t *__restrict__ actions, int T, int autoreset, float *__
     }
     }
 
+    // Outcome counters: pass B's lane l saw the ticks of env l & 7 -> join the four lanes of an env, hand the sum to
+    // the env's quad (at most 256 ticks per launch: 10-bit fields).  Status of the launch's last tick from its record.
+    outcomes += __shfl_xor_sync(FULL, outcomes, 8);
+    outcomes += __shfl_xor_sync(FULL, outcomes, 16);
+    outcomes = __shfl_sync(FULL, outcomes, q);
+    E.n_vault += outcomes & 1023; E.n_detect += (outcomes >> 10) & 1023; E.n_timeout += (outcomes >> 20) & 1023;
+    if (stepped)
+        status = !(rec_last & SEQ_LIVE) ? HEIST_ALREADY_DONE
+                 : ((rec_last & SEQ_TOUT) ? HEIST_TIMEOUT : ((rec_last & SEQ_VAULT) ? HEIST_VAULT_REACHED : ((rec_last & SEQ_DET) ? HEIST_DETECTED : HEIST_RUNNING)));
     // ---- store ----
     if (!valid) return;
     if (j == 0) {
