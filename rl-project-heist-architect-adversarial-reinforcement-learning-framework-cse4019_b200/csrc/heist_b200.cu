@@ -578,18 +578,23 @@ static ChunkPlan chunk_plan(int total) {
         }
     }
     // The launch ends with the LAST chunk's k_seq and k_finish_or running alone (nothing left to overlap them with),
-    // so the chunks taper towards the end: full chunks first, then 6 and 3 tick blocks (measured on config 2,
-    // T = 200: 8,8,6,3 -> 1.76e9 env-steps/s; the even 7,6,6,6 -> 1.71e9; finer tapers lose to their extra launches).
-    const int B = p.total_blocks, M = FAST_PIPE_BLOCKS;
+    // so the last chunk is short; the others take 7 tick blocks: 7-warp camera CTAs fit SEVEN to an SM (49 warps; 8-warp
+    // CTAs six = 48) and the shorter chunks hand the sequential chain its rows earlier.  Measured on config 2, T = 200
+    // (25 blocks): 7,7,7,4 -> 2.07e9 env-steps/s; 8,8,6,3 -> 2.04e9; 7,7,6,5 / 6,7,7,5 / 7,6,6,6 -> 2.02e9; 8,8,5,4 / 8,7,6,4
+    // -> 2.04-2.05e9; 7,7,7,3,1 / 7,7,7,2,2 -> 1.98-2.00e9 (finer tapers lose to their extra launches and small CTAs).
+    const int B = p.total_blocks, M = FAST_PIPE_BLOCKS, FULL_BLOCKS = 7;
     p.start[0] = 0;
-    if (B < 8 || B > M * (FAST_PIPE_MAX - 2)) { p.n = B < 8 ? 1 : FAST_PIPE_MAX + 1; p.start[1] = B; return p; }   // (not pipelined: see fast_pipelined)
-    int sizes[FAST_PIPE_MAX], k = 0;
-    if (B <= M) { sizes[k++] = B / 2; sizes[k++] = B - B / 2; }   // (reversed below: the larger half first)
+    if (B < 8 || B > FULL_BLOCKS * (FAST_PIPE_MAX - 2)) { p.n = B < 8 ? 1 : FAST_PIPE_MAX + 1; p.start[1] = B; return p; }   // (not pipelined: see fast_pipelined)
+    int sizes[FAST_PIPE_MAX], k = 0;   // (filled last chunk first, reversed below)
+    if (B <= M) { sizes[k++] = B / 2; sizes[k++] = B - B / 2; }   // (the larger half first)
     else {
         int left = B;
-        const int tail[2] = {3, 6};
-        for (int i = 0; left > 0; ++i) { const int want = i < 2 ? tail[i] : M, take = std::min(want, left); sizes[k++] = take; left -= take; }
-        if (k >= 2 && sizes[k - 1] < 3 && sizes[k - 1] + sizes[k - 2] <= M) { sizes[k - 2] += sizes[k - 1]; --k; }   // no tiny first chunk
+        int fwd[FAST_PIPE_MAX], nf = 0;
+        while (left > FULL_BLOCKS + 3) { fwd[nf++] = FULL_BLOCKS; left -= FULL_BLOCKS; }   // 7, 7, 7, ...
+        // what is left (4 .. 10 blocks): one short chunk, or two with the shorter one last
+        if (left <= 5) fwd[nf++] = left;
+        else { const int lastc = left >= 8 ? 4 : 3; fwd[nf++] = left - lastc; fwd[nf++] = lastc; }
+        for (int i = nf - 1; i >= 0; --i) sizes[k++] = fwd[i];
     }
     p.n = k;
     for (int i = 0; i < k; ++i) p.start[i + 1] = p.start[i] + sizes[k - 1 - i];
