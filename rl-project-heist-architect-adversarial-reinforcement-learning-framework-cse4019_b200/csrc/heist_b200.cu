@@ -578,8 +578,9 @@ static ChunkPlan chunk_plan(int total) {
         }
     }
     // The launch ends with the LAST chunk's k_seq and k_finish_or running alone (nothing left to overlap them with),
-    // so the last chunk is short; the others take 7 tick blocks: 7-warp camera CTAs fit SEVEN to an SM (49 warps; 8-warp
-    // CTAs six = 48) and the shorter chunks hand the sequential chain its rows earlier.  Measured on config 2, T = 200
+    // so the last chunk is short; the others take 7 tick blocks: the shorter chunks hand the sequential chain (k_seq, busy
+    // back to back from the end of the first camera chunk on) its rows earlier and more evenly -- six camera CTAs per SM
+    // either way (a 7-warp CTA is allocated like an 8-warp one).  Measured on config 2, T = 200
     // (25 blocks): 7,7,7,4 -> 2.07e9 env-steps/s; 8,8,6,3 -> 2.04e9; 7,7,6,5 / 6,7,7,5 / 7,6,6,6 -> 2.02e9; 8,8,5,4 / 8,7,6,4
     // -> 2.04-2.05e9; 7,7,7,3,1 / 7,7,7,2,2 -> 1.98-2.00e9 (finer tapers lose to their extra launches and small CTAs).
     const int B = p.total_blocks, M = FAST_PIPE_BLOCKS, FULL_BLOCKS = 7;
