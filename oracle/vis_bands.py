@@ -42,3 +42,42 @@ def tie_bands(vision_range, fov):
         else:
             merged.append([s, e])
     return [tuple(b) for b in merged]
+
+
+def guard_reach(heading_table, speed):
+    """Restatement of k_build_cache's reachable-pair fixed point (csrc/heist_cache.cuh): which heading slots a guard
+    can carry on each waypoint.  heading_table[i] = heading after leaving waypoint i (NaN: the move is no move).
+    Slot 0 is the default heading 0.0, further slots the distinct table headings in order of appearance (compared by
+    bit pattern, like the kernel).  Returns (slot_values, reach) with reach[i] = set of slots on waypoint i."""
+    import math
+    import struct
+    bits = lambda x: struct.pack("<d", x)
+    n = len(heading_table)
+    vals = [0.0]
+    hslot = []
+    for h in heading_table:
+        if math.isnan(h):
+            hslot.append(255)
+            continue
+        for s, v in enumerate(vals):
+            if bits(v) == bits(h):
+                break
+        else:
+            vals.append(h)
+            s = len(vals) - 1
+        hslot.append(s)
+    stride = speed % n if n >= 2 else 0          # Python int %, as py_imod
+    reach = [set() for _ in range(n)]
+    reach[0] = set(range(len(vals)))             # a reset puts the guard on waypoint 0 with whatever heading it carries
+    changed = True
+    while changed:
+        changed = False
+        for k in range(n):
+            if not reach[k]:
+                continue
+            nxt = (k + stride) % n
+            add = reach[k] if hslot[k] == 255 else {hslot[k]}
+            if not add <= reach[nxt]:
+                reach[nxt] |= add
+                changed = True
+    return vals, reach

@@ -47,3 +47,44 @@ def test_bands_are_thin():
     widths = np.array([e - s for s, e in bands[1:-1]])
     assert widths.max() < 1e-3 and np.median(widths) < 1e-8     # the widest are the tangent crossings at d = k + 0.5
     assert widths.sum() < 0.01                                  # of a 480-degree domain
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_guard_cone_pairs_cover_every_state_a_patrol_reaches(seed):
+    """The guards' cones are tabulated only for the (waypoint, heading) pairs of k_build_cache's fixed point
+    (oracle.vis_bands.guard_reach restates it).  Property: a guard driven by the reference's rules -- Guard.update
+    (security.py:145-159: index advance with Python %, heading from the move unless it is no move) and reset
+    (environment.py:205-208: back to waypoint 0, heading kept) at arbitrary ticks -- never leaves that set; and the set
+    is small (a ring: about its length plus its headings)."""
+    import math
+    import struct
+    import heist_b200
+    from oracle.vis_bands import guard_reach
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.integers(1, 13))
+    if seed % 3 == 0:   # the Architect's patrol ring (networks.py:324-335), clamped near a border
+        r0, c0 = int(rng.integers(1, 4)), int(rng.integers(1, 4))
+        path = [(max(1, r0 + dr - 1), max(1, c0 + dc - 1)) for dr, dc in ((0, 0), (0, 1), (0, 2), (1, 2), (2, 2), (2, 1), (2, 0), (1, 0))]
+    else:               # arbitrary paths with repeated waypoints (no-move steps)
+        path = [(int(rng.integers(0, 4)), int(rng.integers(0, 4))) for _ in range(n)]
+    speed = int(rng.choice([1, 1, 2, 3, 5, -1, -2, 0, len(path)]))
+    vals, reach = guard_reach(heist_b200.guard_heading_table(path, speed), speed)
+    slot = {struct.pack("<d", v): s for s, v in enumerate(vals)}
+    idx, heading = 0, 0.0
+    seen = set()
+    for t in range(4000):
+        if rng.random() < 0.05:
+            idx = 0                                           # reset(): current_idx = 0, heading kept
+        elif len(path) >= 2:                                  # Guard.update
+            old = idx
+            idx = (idx + speed) % len(path)
+            dr, dc = path[idx][0] - path[old][0], path[idx][1] - path[old][1]
+            if dr != 0 or dc != 0:
+                heading = math.degrees(math.atan2(-dr, dc)) % 360.0
+        s = slot[struct.pack("<d", heading)]                   # (a heading that is no slot would be a KeyError)
+        assert s in reach[idx], (path, speed, t, idx, heading)
+        seen.add((idx, s))
+    total = sum(len(r) for r in reach)
+    assert len(seen) <= total <= len(path) * len(vals)
+    if seed % 3 == 0 and speed == 1:
+        assert total <= len(path) + 2 * len(vals)             # a ring: ~11 of its 32 pairs
