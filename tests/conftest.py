@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 GOLDEN = os.path.join(ROOT, "tests", "golden", "heist_golden.npz")
 GOLDEN_R2 = os.path.join(ROOT, "tests", "golden", "heist_golden_r2.npz")   # make_golden_r2.py: tie angles, big grids, trainer tapes
+GOLDEN_R3 = os.path.join(ROOT, "tests", "golden", "heist_golden_r3.npz")   # make_golden_r3.py: guard patrols (strides, no-move steps, resets at every phase)
 
 
 def pytest_configure(config):
@@ -43,3 +44,8 @@ def golden():
 @pytest.fixture(scope="session")
 def golden2():
     return Golden(GOLDEN_R2)
+
+
+@pytest.fixture(scope="session")
+def golden3():
+    return Golden(GOLDEN_R3)

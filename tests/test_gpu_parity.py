@@ -51,6 +51,15 @@ def test_round2_traces_step_many(golden2, mode):
     _step_many_traces(golden2, mode)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_round3_patrol_traces_bit_exact(golden3, mode):
+    """tests/golden/heist_golden_r3.npz (recorded from the reference): guard patrols with strides, no-move steps, one- and
+    two-waypoint paths, up to four overlapping guards and resets on every phase of a patrol -- the cached path serves
+    them from the cones of the reachable (waypoint, heading) pairs only; single ticks and the rollout kernels."""
+    _single_tick_traces(golden3, mode)
+    _step_many_traces(golden3, mode)
+
+
 def _single_tick_traces(golden, mode, only=lambda n: True):
     for (R, C, ms, T), names in _groups(golden).items():
         names = [n for n in names if only(n)]

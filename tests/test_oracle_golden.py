@@ -32,6 +32,14 @@ def test_round2_traces_bit_exact(golden2):
     _check_traces(golden2)
 
 
+def test_round3_patrol_traces_bit_exact(golden3):
+    """Guard patrols with strides, no-move steps, one- and two-waypoint paths, up to four guards, short episodes whose
+    resets fall on every phase of a patrol (security.py:145-159, environment.py:205-208) -- recorded from the reference."""
+    assert len(golden3.traces) == 10 and all(t["valid"] for t in golden3.traces.values())
+    assert sum(int(golden3.arr(n, "done").sum()) for n in golden3.traces) >= 300
+    _check_traces(golden3)
+
+
 def test_trainer_tapes(golden2):
     """The call sequence AdversarialTrainer._run_one_episode made on the reference env (training.py:418-600):
     the oracle reproduces every recorded return value."""
