@@ -11,6 +11,9 @@ Run in the build container only (the reference tree is not present on the GPU bo
              episodes (max_steps 7 ... 13, not multiples of the path lengths) so that resets fall on every phase of a
              patrol.  The visibility tables hold a guard's cone only for the (waypoint, heading) pairs the patrol can
              reach; these traces pin that set against the reference itself.
+* shape*   - grids that are not the usual squares (5x4, 7x12, 33x36, 40x64, 64x8, 6x16) with get_state_tensor
+             (environment.py:347-374) recorded after EVERY step: the fused tick kernel writes that tensor with its own
+             index arithmetic (channels shorter than a warp trip, rows of two words, two rows per lane).
 """
 import json
 import os
@@ -51,6 +54,17 @@ def patrol_layout(rng, kind):
     return walls, cams, guards, 1000
 
 
+def shape_layout(rng, R, C):
+    walls = [(int(rng.integers(1, R - 1)), int(rng.integers(1, C - 1))) for _ in range(int(rng.integers(0, 4)))]
+    walls = [w for w in walls if w not in ((1, 1), (R - 2, C - 2))]
+    cams = [{"row": int(rng.integers(1, R - 1)), "col": int(rng.integers(1, C - 1)), "fov_angle": float(np.float32(rng.uniform(40, 110))),
+             "heading": float(np.float32(rng.uniform(0, 360))), "rotation_speed": float(np.float32(rng.uniform(5, 35))),
+             "vision_range": int(rng.integers(2, 7))} for _ in range(int(rng.integers(1, 3)))]
+    guards = [{"patrol_path": mg.patrol(int(rng.integers(1, R - 1)), int(rng.integers(1, C - 1)), R, C), "speed": 1,
+               "vision_range": 3, "fov_angle": 90.0}]
+    return walls, cams, guards, 1000
+
+
 def main():
     store, meta = {}, {"traces": [], "numpy": np.__version__}
     rng = np.random.default_rng(20261020)
@@ -59,8 +73,10 @@ def main():
         for k in range(2):
             ms = [7, 11, 13, 9, 10][len(cases) % 5]
             cases.append((f"patrol_{kind}_{k}", 20, 20, ms, patrol_layout(rng, kind), rng.integers(0, 5, 150).astype(np.int8)))
+    for R, C in ((5, 4), (7, 12), (33, 36), (40, 64), (64, 8), (6, 16)):
+        cases.append((f"shape_{R}x{C}", R, C, 9, shape_layout(rng, R, C), mg.biased_actions(rng, 48)))
     for name, R, C, ms, layout, actions in cases:
-        rec = mg.run_trace(R, C, ms, layout, actions, want_state_every=17)
+        rec = mg.run_trace(R, C, ms, layout, actions, want_state_every=1 if name.startswith("shape") else 17)
         walls, cams, guards, budget = layout
         meta["traces"].append({"name": name, "R": R, "C": C, "max_steps": ms, "budget": budget,
                                "walls": [list(map(int, w)) for w in walls], "cameras": cams,

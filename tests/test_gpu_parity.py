@@ -60,6 +60,31 @@ def test_round3_patrol_traces_bit_exact(golden3, mode):
     _step_many_traces(golden3, mode)
 
 
+def test_round3_shape_traces_fused_state_every_tick(golden3):
+    """The shape* traces of heist_golden_r3.npz (5x4 ... 40x64, recorded from the reference with get_state_tensor after
+    EVERY step): heist_step_observe -- the fused tick kernel writing the (3, R, C) state with its own index arithmetic --
+    reproduces every state, reward and status; resets by mask as the trainer does."""
+    for n in [n for n in golden3.traces if n.startswith("shape")]:
+        t = golden3.traces[n]
+        R, C = t["R"], t["C"]
+        env = BatchedHeistEnv(EnvironmentConfig(grid_rows=R, grid_cols=C, max_steps=t["max_steps"]), 1, max_path=8)
+        lay = golden3.layout(n)
+        assert bool(env.set_layout_explicit([lay[:3]], budget=np.array([lay[3]])).item()) == t["valid"]
+        env.check_errors()
+        assert env.cache_stats()[0] == 1   # (table-driven: the fused kernel is what runs)
+        env.reset()
+        acts, states = golden3.arr(n, "actions"), golden3.arr(n, "state")
+        state = torch.empty(1, 3, R, C, device="cuda")
+        for k in range(len(acts)):
+            rew, done, status, _ = env.step_observe(acts[k:k + 1], autoreset=False, state_out=state)
+            assert rew.item() == np.float32(golden3.arr(n, "reward")[k]) and status.item() == golden3.arr(n, "status")[k], (n, k)
+            assert np.array_equal(state[0].cpu().numpy(), states[k]), (n, k)
+            env.reset(mask=done)
+            assert np.array_equal(u32(env.visibility_bits)[0], golden3.arr(n, "vis_post")[k]), (n, k)
+        env.check_errors()
+        env.close()
+
+
 def _single_tick_traces(golden, mode, only=lambda n: True):
     for (R, C, ms, T), names in _groups(golden).items():
         names = [n for n in names if only(n)]

@@ -35,8 +35,11 @@ def test_round2_traces_bit_exact(golden2):
 def test_round3_patrol_traces_bit_exact(golden3):
     """Guard patrols with strides, no-move steps, one- and two-waypoint paths, up to four guards, short episodes whose
     resets fall on every phase of a patrol (security.py:145-159, environment.py:205-208) -- recorded from the reference."""
-    assert len(golden3.traces) == 10 and all(t["valid"] for t in golden3.traces.values())
-    assert sum(int(golden3.arr(n, "done").sum()) for n in golden3.traces) >= 300
+    assert sum(n.startswith("patrol") for n in golden3.traces) == 10 and all(t["valid"] for t in golden3.traces.values())
+    assert sum(int(golden3.arr(n, "done").sum()) for n in golden3.traces if n.startswith("patrol")) >= 300
+    # ... and six grids that are not the usual squares, get_state_tensor recorded after every step
+    assert sum(n.startswith("shape") for n in golden3.traces) == 6
+    assert all(len(golden3.arr(n, "state_t")) == len(golden3.arr(n, "actions")) for n in golden3.traces if n.startswith("shape"))
     _check_traces(golden3)
 
 
